@@ -1,0 +1,215 @@
+// field.cuh -- BLS12-381 Fr / Fq / Fq2 in 32-bit limbs, Montgomery form (R = 2^(32 N)).
+//
+// Memory image == arkworks `Fp256` / `Fp384` (4 / 6 little-endian u64 Montgomery limbs), so Rust
+// slices of `E::Fr` cross the C ABI zero-copy (reference: src/commitment/commit.rs:20-21 `into_repr`
+// is the only place the reference leaves Montgomery form).
+//
+// Device code uses the generated PTX carry chains (fp_gen.cuh: mad.lo.cc/madc.hi.cc pairs that ptxas
+// fuses into IMAD.WIDE.U32 with carry predicates); host code (transcript-side scalar work,
+// serialization, final affine conversion) uses the portable 64-bit-accumulator path below.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include "fp_gen.cuh"
+
+#if defined(__CUDACC__)
+#define SB_HD __host__ __device__ __forceinline__
+#define SB_D __device__ __forceinline__
+#else
+#define SB_HD inline
+#define SB_D inline
+#endif
+
+struct FrParams {
+    static constexpr int N = FR_LIMBS;
+    static constexpr uint32_t INV = FR_INV32;
+    SB_HD static constexpr uint32_t mod(int i) { constexpr uint32_t m[N] = FR_MOD_INIT; return m[i]; }
+    SB_HD static constexpr uint32_t r1(int i) { constexpr uint32_t m[N] = FR_R1_INIT; return m[i]; }
+    SB_HD static constexpr uint32_t r2(int i) { constexpr uint32_t m[N] = FR_R2_INIT; return m[i]; }
+#if defined(__CUDACC__)
+    SB_D static void mul_ptx(uint32_t* r, const uint32_t* a, const uint32_t* b) { fr_mul_ptx(r, a, b); }
+    SB_D static void add_ptx(uint32_t* r, const uint32_t* a, const uint32_t* b) { fr_add_ptx(r, a, b); }
+    SB_D static void sub_ptx(uint32_t* r, const uint32_t* a, const uint32_t* b) { fr_sub_ptx(r, a, b); }
+#endif
+};
+struct FqParams {
+    static constexpr int N = FQ_LIMBS;
+    static constexpr uint32_t INV = FQ_INV32;
+    SB_HD static constexpr uint32_t mod(int i) { constexpr uint32_t m[N] = FQ_MOD_INIT; return m[i]; }
+    SB_HD static constexpr uint32_t r1(int i) { constexpr uint32_t m[N] = FQ_R1_INIT; return m[i]; }
+    SB_HD static constexpr uint32_t r2(int i) { constexpr uint32_t m[N] = FQ_R2_INIT; return m[i]; }
+#if defined(__CUDACC__)
+    SB_D static void mul_ptx(uint32_t* r, const uint32_t* a, const uint32_t* b) { fq_mul_ptx(r, a, b); }
+    SB_D static void add_ptx(uint32_t* r, const uint32_t* a, const uint32_t* b) { fq_add_ptx(r, a, b); }
+    SB_D static void sub_ptx(uint32_t* r, const uint32_t* a, const uint32_t* b) { fq_sub_ptx(r, a, b); }
+#endif
+};
+
+template <class P>
+struct alignas(16) Fp {
+    static constexpr int N = P::N;
+    uint32_t l[N];
+
+    SB_HD static Fp zero() { Fp z; for (int i = 0; i < N; i++) z.l[i] = 0; return z; }
+    SB_HD static Fp one() { Fp z; for (int i = 0; i < N; i++) z.l[i] = P::r1(i); return z; }
+    SB_HD static Fp rr() { Fp z; for (int i = 0; i < N; i++) z.l[i] = P::r2(i); return z; }
+    SB_HD bool is_zero() const { uint32_t x = 0; for (int i = 0; i < N; i++) x |= l[i]; return x == 0; }
+    SB_HD bool operator==(const Fp& o) const { uint32_t x = 0; for (int i = 0; i < N; i++) x |= l[i] ^ o.l[i]; return x == 0; }
+    SB_HD bool operator!=(const Fp& o) const { return !(*this == o); }
+
+    // ---- portable paths (host; also usable on device for cross-checking the PTX path)
+    SB_HD static bool geq_mod(const uint32_t* a) {
+        for (int i = N - 1; i >= 0; i--) {
+            if (a[i] > P::mod(i)) return true;
+            if (a[i] < P::mod(i)) return false;
+        }
+        return true;
+    }
+    SB_HD static void sub_mod(uint32_t* a) {
+        uint64_t borrow = 0;
+        for (int i = 0; i < N; i++) {
+            uint64_t d = (uint64_t)a[i] - P::mod(i) - borrow;
+            a[i] = (uint32_t)d; borrow = (d >> 32) & 1;
+        }
+    }
+    SB_HD static Fp add_portable(const Fp& a, const Fp& b) {
+        Fp o; uint64_t c = 0;
+        for (int i = 0; i < N; i++) { c += (uint64_t)a.l[i] + b.l[i]; o.l[i] = (uint32_t)c; c >>= 32; }
+        if (c || geq_mod(o.l)) sub_mod(o.l);
+        return o;
+    }
+    SB_HD static Fp sub_portable(const Fp& a, const Fp& b) {
+        Fp o; uint64_t borrow = 0;
+        for (int i = 0; i < N; i++) {
+            uint64_t d = (uint64_t)a.l[i] - b.l[i] - borrow;
+            o.l[i] = (uint32_t)d; borrow = (d >> 32) & 1;
+        }
+        if (borrow) {
+            uint64_t c = 0;
+            for (int i = 0; i < N; i++) { c += (uint64_t)o.l[i] + P::mod(i); o.l[i] = (uint32_t)c; c >>= 32; }
+        }
+        return o;
+    }
+    SB_HD static Fp mul_portable(const Fp& a, const Fp& b) {
+        uint32_t t[N + 2];
+        for (int i = 0; i < N + 2; i++) t[i] = 0;
+        for (int i = 0; i < N; i++) {
+            uint64_t c = 0;
+            for (int j = 0; j < N; j++) { c += (uint64_t)a.l[j] * b.l[i] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
+            c += t[N]; t[N] = (uint32_t)c; t[N + 1] = (uint32_t)(c >> 32);
+            uint32_t m = t[0] * P::INV;
+            c = (uint64_t)m * P::mod(0) + t[0]; c >>= 32;
+            for (int j = 1; j < N; j++) { c += (uint64_t)m * P::mod(j) + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
+            c += t[N]; t[N - 1] = (uint32_t)c; t[N] = t[N + 1] + (uint32_t)(c >> 32);
+        }
+        Fp o;
+        for (int i = 0; i < N; i++) o.l[i] = t[i];
+        if (t[N] || geq_mod(o.l)) sub_mod(o.l);
+        return o;
+    }
+
+    // ---- dispatch
+    SB_HD static Fp add(const Fp& a, const Fp& b) {
+#if defined(__CUDA_ARCH__)
+        Fp o; P::add_ptx(o.l, a.l, b.l); return o;
+#else
+        return add_portable(a, b);
+#endif
+    }
+    SB_HD static Fp sub(const Fp& a, const Fp& b) {
+#if defined(__CUDA_ARCH__)
+        Fp o; P::sub_ptx(o.l, a.l, b.l); return o;
+#else
+        return sub_portable(a, b);
+#endif
+    }
+    SB_HD static Fp mul(const Fp& a, const Fp& b) {
+#if defined(__CUDA_ARCH__)
+        Fp o; P::mul_ptx(o.l, a.l, b.l); return o;
+#else
+        return mul_portable(a, b);
+#endif
+    }
+    SB_HD static Fp sqr(const Fp& a) { return mul(a, a); }
+    SB_HD static Fp dbl(const Fp& a) { return add(a, a); }
+    SB_HD static Fp neg(const Fp& a) { return sub(zero(), a); }
+
+    // Montgomery <-> canonical ("into_repr")
+    SB_HD static Fp from_canonical(const Fp& c) { return mul(c, rr()); }
+    SB_HD Fp to_canonical() const { Fp o = zero(); o.l[0] = 1; return mul(*this, o); }
+    SB_HD static Fp from_u32(uint32_t v) { Fp o = zero(); o.l[0] = v; return from_canonical(o); }
+
+    // host helpers
+    static Fp pow_host(const Fp& a, const uint32_t* e, int nlimbs) {
+        Fp acc = one();
+        for (int i = nlimbs * 32 - 1; i >= 0; i--) {
+            acc = sqr(acc);
+            if ((e[i / 32] >> (i % 32)) & 1) acc = mul(acc, a);
+        }
+        return acc;
+    }
+    static Fp inv_host(const Fp& a) { return inv(a); }
+    // Fermat inversion a^(p-2), a != 0 (also used on the device by the batch-affine kernels)
+#if defined(__CUDACC__)
+    __host__ __device__ __noinline__
+#endif
+    static Fp inv(const Fp& a) {
+        uint32_t e[N], borrow = 2;                       // e = p - 2
+        for (int i = 0; i < N; i++) { uint32_t m = P::mod(i); e[i] = m - borrow; borrow = (m < borrow) ? 1u : 0u; }
+        Fp acc = one();
+#pragma unroll 1
+        for (int i = N * 32 - 1; i >= 0; i--) {
+            acc = sqr(acc);
+            if ((e[i / 32] >> (i % 32)) & 1) acc = mul(acc, a);
+        }
+        return acc;
+    }
+    static int cmp_canonical_host(const Fp& a, const Fp& b) {
+        Fp ca = a.to_canonical(), cb = b.to_canonical();
+        for (int i = N - 1; i >= 0; i--) {
+            if (ca.l[i] > cb.l[i]) return 1;
+            if (ca.l[i] < cb.l[i]) return -1;
+        }
+        return 0;
+    }
+};
+
+typedef Fp<FrParams> Fr;
+typedef Fp<FqParams> Fq;
+
+// Fq2 = Fq[u] / (u^2 + 1)
+struct alignas(16) Fq2 {
+    Fq c0, c1;
+    SB_HD static Fq2 zero() { Fq2 z; z.c0 = Fq::zero(); z.c1 = Fq::zero(); return z; }
+    SB_HD static Fq2 one() { Fq2 z; z.c0 = Fq::one(); z.c1 = Fq::zero(); return z; }
+    SB_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    SB_HD bool operator==(const Fq2& o) const { return c0 == o.c0 && c1 == o.c1; }
+    SB_HD bool operator!=(const Fq2& o) const { return !(*this == o); }
+    SB_HD static Fq2 add(const Fq2& a, const Fq2& b) { Fq2 o; o.c0 = Fq::add(a.c0, b.c0); o.c1 = Fq::add(a.c1, b.c1); return o; }
+    SB_HD static Fq2 sub(const Fq2& a, const Fq2& b) { Fq2 o; o.c0 = Fq::sub(a.c0, b.c0); o.c1 = Fq::sub(a.c1, b.c1); return o; }
+    SB_HD static Fq2 dbl(const Fq2& a) { return add(a, a); }
+    SB_HD static Fq2 neg(const Fq2& a) { Fq2 o; o.c0 = Fq::neg(a.c0); o.c1 = Fq::neg(a.c1); return o; }
+    SB_HD static Fq2 mul(const Fq2& a, const Fq2& b) {
+        Fq v0 = Fq::mul(a.c0, b.c0), v1 = Fq::mul(a.c1, b.c1);
+        Fq s = Fq::mul(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
+        Fq2 o; o.c0 = Fq::sub(v0, v1); o.c1 = Fq::sub(Fq::sub(s, v0), v1); return o;
+    }
+    SB_HD static Fq2 sqr(const Fq2& a) {
+        Fq s = Fq::add(a.c0, a.c1), d = Fq::sub(a.c0, a.c1), m = Fq::mul(a.c0, a.c1);
+        Fq2 o; o.c0 = Fq::mul(s, d); o.c1 = Fq::dbl(m); return o;
+    }
+    static Fq2 inv_host(const Fq2& a) { return inv(a); }
+#if defined(__CUDACC__)
+    __host__ __device__
+#endif
+    static Fq2 inv(const Fq2& a) {
+        Fq n = Fq::add(Fq::sqr(a.c0), Fq::sqr(a.c1));
+        Fq ni = Fq::inv(n);
+        Fq2 o; o.c0 = Fq::mul(a.c0, ni); o.c1 = Fq::neg(Fq::mul(a.c1, ni)); return o;
+    }
+    // arkworks QuadExtField ordering: c1 first, then c0
+    static int cmp_canonical_host(const Fq2& a, const Fq2& b) {
+        int c = Fq::cmp_canonical_host(a.c1, b.c1);
+        return c ? c : Fq::cmp_canonical_host(a.c0, b.c0);
+    }
+};

@@ -1,0 +1,316 @@
+// kernels_fr.cu -- scalar-field kernels: eq pyramid, segmented sparse products, fused
+// fold+evaluate sumcheck rounds, opening fold.  sm_100a; integer pipe + HBM bound, no tensor cores
+// (no step of this path is a dense contraction).
+#include "kernels_fr.cuh"
+
+unsigned long long g_sb_launches = 0;
+
+// ------------------------------------------------------------------ helpers
+template <class T>
+SB_D T ldcg_elem(const T* p) {      // L2-coherent load (data produced by other CTAs of this launch)
+    T out;
+    const uint4* src = reinterpret_cast<const uint4*>(p);
+    uint4* dst = reinterpret_cast<uint4*>(&out);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) dst[i] = __ldcg(src + i);
+    return out;
+}
+
+SB_D Fr warp_reduce_fr(Fr v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Fr o;
+#pragma unroll
+        for (int i = 0; i < Fr::N; i++) o.l[i] = __shfl_down_sync(0xffffffffu, v.l[i], off);
+        v = Fr::add(v, o);
+    }
+    return v;
+}
+
+// Block tree reduction of K accumulators, then grid-level finish by the last CTA to arrive.
+template <int K>
+SB_D void reduce_finish(Fr (&acc)[K], Fr* out, Fr* block_partials, unsigned int* ticket) {
+    __shared__ Fr sh[K][32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        Fr v = warp_reduce_fr(acc[k]);
+        if (lane == 0) sh[k][warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            Fr v = lane < nwarps ? sh[k][lane] : Fr::zero();
+            v = warp_reduce_fr(v);
+            if (lane == 0) st_elem(&block_partials[(size_t)blockIdx.x * K + k], v);
+        }
+        if (lane == 0) {
+            __threadfence();
+            unsigned int t = atomicAdd(ticket, 1u);
+            is_last = (t == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    Fr s[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) s[k] = Fr::zero();
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < K; k++) s[k] = Fr::add(s[k], ldcg_elem(&block_partials[(size_t)i * K + k]));
+    }
+    __syncthreads();   // sh reuse
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        Fr v = warp_reduce_fr(s[k]);
+        if (lane == 0) sh[k][warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            Fr v = lane < nwarps ? sh[k][lane] : Fr::zero();
+            v = warp_reduce_fr(v);
+            if (lane == 0) st_elem(&out[k], v);
+        }
+        if (lane == 0) *ticket = 0;     // self-reset for the next launch on this stream
+    }
+}
+
+// ------------------------------------------------------------------ eq pyramid
+constexpr int EQ_SMALL_LOG = 10;
+
+// levels of size 1 .. 2^kmax inside one CTA
+__global__ void __launch_bounds__(1024) k_eq_small(Fr* pyr, const Fr* tau, uint32_t nv, uint32_t kmax) {
+    if (threadIdx.x == 0) st_elem(&pyr[1], Fr::one());
+    __syncthreads();
+    for (uint32_t k = 0; k < kmax; k++) {
+        size_t s = (size_t)1 << k;
+        Fr t = ldg_elem(&tau[nv - 1 - k]);
+        for (size_t b = threadIdx.x; b < s; b += blockDim.x) {
+            Fr v = pyr[s + b];
+            Fr hi = Fr::mul(v, t);
+            st_elem(&pyr[2 * s + 2 * b], Fr::sub(v, hi));
+            st_elem(&pyr[2 * s + 2 * b + 1], hi);
+        }
+        __syncthreads();
+    }
+}
+// out[2b] = in[b] (1 - t), out[2b+1] = in[b] t     (one multiplication per input)
+__global__ void __launch_bounds__(256) k_eq_double(const Fr* __restrict__ in, Fr* __restrict__ out, size_t s, const Fr* __restrict__ tau) {
+    Fr t = ldg_elem(tau);
+    for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < s; b += (size_t)gridDim.x * blockDim.x) {
+        Fr v = ldg_elem(&in[b]);
+        Fr hi = Fr::mul(v, t);
+        st_elem(&out[2 * b], Fr::sub(v, hi));
+        st_elem(&out[2 * b + 1], hi);
+    }
+}
+__global__ void __launch_bounds__(256) k_eq_double_scaled3(const Fr* __restrict__ in, Fr* __restrict__ out3, size_t s,
+                                                           const Fr* __restrict__ tau, const Fr* __restrict__ rabc) {
+    Fr t = ldg_elem(tau);
+    Fr omt = Fr::sub(Fr::one(), t);
+    Fr c0[3], c1[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { Fr r = ldg_elem(&rabc[k]); c0[k] = Fr::mul(r, omt); c1[k] = Fr::mul(r, t); }
+    for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < s; b += (size_t)gridDim.x * blockDim.x) {
+        Fr v = ldg_elem(&in[b]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            st_elem(&out3[(size_t)k * 2 * s + 2 * b], Fr::mul(v, c0[k]));
+            st_elem(&out3[(size_t)k * 2 * s + 2 * b + 1], Fr::mul(v, c1[k]));
+        }
+    }
+}
+
+void launch_eq_pyramid(Fr* pyr, const Fr* tau_dev, uint32_t nv, cudaStream_t stream) {
+    if (nv == 0) return;
+    uint32_t top = nv - 1;                              // largest level: size 2^(nv-1)
+    uint32_t kmax = top < (uint32_t)EQ_SMALL_LOG ? top : (uint32_t)EQ_SMALL_LOG;
+    SB_LAUNCH(k_eq_small, 1, 1024, 0, stream, pyr, tau_dev, nv, kmax);
+    for (uint32_t k = kmax; k < top; k++) {
+        size_t s = (size_t)1 << k;
+        SB_LAUNCH(k_eq_double, grid_for(s, 256, 8), 256, 0, stream, pyr + s, pyr + 2 * s, s, tau_dev + (nv - 1 - k));
+    }
+}
+void launch_eq_full(Fr* out, const Fr* pyr, const Fr* tau_dev, uint32_t nv, cudaStream_t stream) {
+    size_t s = (size_t)1 << (nv - 1);
+    SB_LAUNCH(k_eq_double, grid_for(s, 256, 8), 256, 0, stream, pyr + s, out, s, tau_dev);
+}
+void launch_eq_full_scaled3(Fr* out3, const Fr* pyr, const Fr* tau_dev, const Fr* rabc_dev, uint32_t nv, cudaStream_t stream) {
+    size_t s = (size_t)1 << (nv - 1);
+    SB_LAUNCH(k_eq_double_scaled3, grid_for(s, 256, 8), 256, 0, stream, pyr + s, out3, s, tau_dev, rabc_dev);
+}
+
+// ------------------------------------------------------------------ segmented sparse product
+__global__ void __launch_bounds__(128) k_segsum(Fr* __restrict__ out, Fr* __restrict__ partials, const SegItem* __restrict__ items,
+                                                uint32_t n_items, const Fr* __restrict__ val, const uint32_t* __restrict__ idx,
+                                                const Fr* __restrict__ x) {
+    for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += gridDim.x * blockDim.x) {
+        SegItem item = items[it];
+        Fr acc = Fr::zero();
+        for (uint32_t e = item.start; e < item.start + item.len; e++) {
+            uint32_t g = __ldg(&idx[e]);
+            Fr xv = ldg_elem(&x[g & ~SEG_UNIT_FLAG]);
+            if (g & SEG_UNIT_FLAG) acc = Fr::add(acc, xv);
+            else acc = Fr::add(acc, Fr::mul(ldg_elem(&val[e]), xv));
+        }
+        if (item.out & 0x80000000u) st_elem(&partials[item.out & 0x7fffffffu], acc);
+        else st_elem(&out[item.out], acc);
+    }
+}
+// one CTA per long segment: sum its partial slots
+__global__ void __launch_bounds__(256) k_seg_fixup(Fr* __restrict__ out, const Fr* __restrict__ partials, const SegFixup* __restrict__ fix) {
+    __shared__ Fr sh[32];
+    SegFixup f = fix[blockIdx.x];
+    Fr acc = Fr::zero();
+    for (uint32_t i = threadIdx.x; i < f.pcount; i += blockDim.x) acc = Fr::add(acc, ldg_elem(&partials[f.pstart + i]));
+    acc = warp_reduce_fr(acc);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (lane == 0) sh[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        Fr v = lane < nwarps ? sh[lane] : Fr::zero();
+        v = warp_reduce_fr(v);
+        if (lane == 0) st_elem(&out[f.seg], v);
+    }
+}
+void launch_segsum(Fr* out, Fr* partials, const SegItem* items, uint32_t n_items, const SegFixup* fix, uint32_t n_fix,
+                   const Fr* val, const uint32_t* idx, const Fr* x, cudaStream_t stream) {
+    if (n_items) SB_LAUNCH(k_segsum, grid_for(n_items, 128, 16), 128, 0, stream, out, partials, items, n_items, val, idx, x);
+    if (n_fix) SB_LAUNCH(k_seg_fixup, (int)n_fix, 256, 0, stream, out, partials, fix);
+}
+
+// ------------------------------------------------------------------ sumcheck rounds
+// KIND 1: S(t) = sum_b E[b] (A(t,b) B(t,b) - C(t,b))   (3 tables + eq suffix weights)
+// KIND 2: S(t) = sum_b M(t,b) Z(t,b)                   (2 tables; C, E unused)
+// FOLD: tables are first folded with r (fix the lowest variable), the folded halves are written out
+// for the next round, and the evaluation runs on the folded values still in registers.
+template <int KIND, bool FOLD>
+__global__ void __launch_bounds__(256, 2)
+k_sc_round(const Fr* __restrict__ A, const Fr* __restrict__ B, const Fr* __restrict__ C, Fr* __restrict__ Ao, Fr* __restrict__ Bo,
+           Fr* __restrict__ Co, const Fr* __restrict__ E, const Fr* __restrict__ r_ptr, size_t h /* pairs after the fold */,
+           Fr* out3, Fr* block_partials, unsigned int* ticket) {
+    Fr acc[3];
+    acc[0] = Fr::zero(); acc[1] = Fr::zero(); acc[2] = Fr::zero();
+    Fr r;
+    if (FOLD) r = ldg_elem(r_ptr);
+    for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < h; b += (size_t)gridDim.x * blockDim.x) {
+        Fr a0, a1, b0, b1, c0, c1;
+        if (FOLD) {
+            Fr x0 = ldg_elem(&A[4 * b]), x1 = ldg_elem(&A[4 * b + 1]), x2 = ldg_elem(&A[4 * b + 2]), x3 = ldg_elem(&A[4 * b + 3]);
+            a0 = Fr::add(x0, Fr::mul(r, Fr::sub(x1, x0)));
+            a1 = Fr::add(x2, Fr::mul(r, Fr::sub(x3, x2)));
+            st_elem(&Ao[2 * b], a0); st_elem(&Ao[2 * b + 1], a1);
+            x0 = ldg_elem(&B[4 * b]); x1 = ldg_elem(&B[4 * b + 1]); x2 = ldg_elem(&B[4 * b + 2]); x3 = ldg_elem(&B[4 * b + 3]);
+            b0 = Fr::add(x0, Fr::mul(r, Fr::sub(x1, x0)));
+            b1 = Fr::add(x2, Fr::mul(r, Fr::sub(x3, x2)));
+            st_elem(&Bo[2 * b], b0); st_elem(&Bo[2 * b + 1], b1);
+            if (KIND == 1) {
+                x0 = ldg_elem(&C[4 * b]); x1 = ldg_elem(&C[4 * b + 1]); x2 = ldg_elem(&C[4 * b + 2]); x3 = ldg_elem(&C[4 * b + 3]);
+                c0 = Fr::add(x0, Fr::mul(r, Fr::sub(x1, x0)));
+                c1 = Fr::add(x2, Fr::mul(r, Fr::sub(x3, x2)));
+                st_elem(&Co[2 * b], c0); st_elem(&Co[2 * b + 1], c1);
+            }
+        } else {
+            a0 = ldg_elem(&A[2 * b]); a1 = ldg_elem(&A[2 * b + 1]);
+            b0 = ldg_elem(&B[2 * b]); b1 = ldg_elem(&B[2 * b + 1]);
+            if (KIND == 1) { c0 = ldg_elem(&C[2 * b]); c1 = ldg_elem(&C[2 * b + 1]); }
+        }
+        // t = 2: T(2) = 2 T1 - T0
+        Fr a2 = Fr::sub(Fr::dbl(a1), a0), b2 = Fr::sub(Fr::dbl(b1), b0);
+        if (KIND == 1) {
+            Fr c2 = Fr::sub(Fr::dbl(c1), c0);
+            Fr e = ldg_elem(&E[b]);
+            acc[0] = Fr::add(acc[0], Fr::mul(e, Fr::sub(Fr::mul(a0, b0), c0)));
+            acc[1] = Fr::add(acc[1], Fr::mul(e, Fr::sub(Fr::mul(a1, b1), c1)));
+            acc[2] = Fr::add(acc[2], Fr::mul(e, Fr::sub(Fr::mul(a2, b2), c2)));
+        } else {
+            acc[0] = Fr::add(acc[0], Fr::mul(a0, b0));
+            acc[1] = Fr::add(acc[1], Fr::mul(a1, b1));
+            acc[2] = Fr::add(acc[2], Fr::mul(a2, b2));
+        }
+    }
+    reduce_finish<3>(acc, out3, block_partials, ticket);
+}
+
+template <int KIND>
+static void launch_sc_round(const Fr* A, const Fr* B, const Fr* C, Fr* Ao, Fr* Bo, Fr* Co, const Fr* E, const Fr* r_dev,
+                            size_t m_in, Fr* out3, const RoundWs& ws, cudaStream_t stream) {
+    bool fold = r_dev != nullptr;
+    size_t h = fold ? m_in / 4 : m_in / 2;
+    int grid = grid_for(h, 256, 2);
+    if (grid > ws.max_grid) grid = ws.max_grid;
+    if (fold) SB_LAUNCH((k_sc_round<KIND, true>), grid, 256, 0, stream, A, B, C, Ao, Bo, Co, E, r_dev, h, out3, ws.block_partials, ws.ticket);
+    else SB_LAUNCH((k_sc_round<KIND, false>), grid, 256, 0, stream, A, B, C, Ao, Bo, Co, E, r_dev, h, out3, ws.block_partials, ws.ticket);
+}
+void launch_sc1_round(const Fr* A, const Fr* B, const Fr* C, Fr* Ao, Fr* Bo, Fr* Co, const Fr* E, const Fr* r_dev,
+                      size_t m_in, Fr* out3, const RoundWs& ws, cudaStream_t stream) {
+    launch_sc_round<1>(A, B, C, Ao, Bo, Co, E, r_dev, m_in, out3, ws, stream);
+}
+void launch_sc2_round(const Fr* M, const Fr* Z, Fr* Mo, Fr* Zo, const Fr* r_dev, size_t m_in, Fr* out3,
+                      const RoundWs& ws, cudaStream_t stream) {
+    launch_sc_round<2>(M, Z, nullptr, Mo, Zo, nullptr, nullptr, r_dev, m_in, out3, ws, stream);
+}
+
+__global__ void k_final_fold3(const Fr* A, const Fr* B, const Fr* C, int ntab, const Fr* r_ptr, Fr* out) {
+    int k = threadIdx.x;
+    if (k >= ntab) return;
+    const Fr* T = k == 0 ? A : k == 1 ? B : C;
+    Fr r = *r_ptr, x0 = T[0], x1 = T[1];
+    out[k] = Fr::add(x0, Fr::mul(r, Fr::sub(x1, x0)));
+}
+void launch_final_fold3(const Fr* A, const Fr* B, const Fr* C, int ntab, const Fr* r_dev, Fr* out, cudaStream_t stream) {
+    SB_LAUNCH(k_final_fold3, 1, 32, 0, stream, A, B, C, ntab, r_dev, out);
+}
+
+// ------------------------------------------------------------------ opening fold
+__global__ void __launch_bounds__(256) k_open_fold(const Fr* __restrict__ in, Fr* __restrict__ r_out, Fr* __restrict__ q_out,
+                                                   const Fr* __restrict__ p_ptr, size_t half) {
+    Fr p = ldg_elem(p_ptr);
+    for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < half; b += (size_t)gridDim.x * blockDim.x) {
+        Fr x0 = ldg_elem(&in[2 * b]), x1 = ldg_elem(&in[2 * b + 1]);
+        Fr q = Fr::sub(x1, x0);
+        st_elem(&q_out[b], q);
+        st_elem(&r_out[b], Fr::add(x0, Fr::mul(p, q)));
+    }
+}
+void launch_open_fold(const Fr* in, Fr* r_out, Fr* q_out, const Fr* p_dev, size_t half, cudaStream_t stream) {
+    SB_LAUNCH(k_open_fold, grid_for(half, 256, 8), 256, 0, stream, in, r_out, q_out, p_dev, half);
+}
+
+// ------------------------------------------------------------------ self-test / microbenchmarks
+template <class F>
+__global__ void k_binop(int op, const F* a, const F* b, F* out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        F x = a[i], y = b[i], o;
+        if (op == 0) o = F::add(x, y);
+        else if (op == 1) o = F::sub(x, y);
+        else if (op == 2) o = F::mul(x, y);
+        else o = F::mul_portable(x, y);
+        out[i] = o;
+    }
+}
+void launch_fr_binop(int op, const Fr* a, const Fr* b, Fr* out, size_t n, cudaStream_t stream) {
+    SB_LAUNCH(k_binop<Fr>, grid_for(n, 256, 4), 256, 0, stream, op, a, b, out, n);
+}
+void launch_fq_binop(int op, const Fq* a, const Fq* b, Fq* out, size_t n, cudaStream_t stream) {
+    SB_LAUNCH(k_binop<Fq>, grid_for(n, 256, 4), 256, 0, stream, op, a, b, out, n);
+}
+template <class F>
+__global__ void __launch_bounds__(256) k_mul_bench(F* inout, size_t n, int iters) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = inout[i], y = x, z = F::add(x, F::one());
+    for (int it = 0; it < iters; it++) { x = F::mul(x, y); z = F::mul(z, y); }   // two independent chains
+    inout[i] = F::add(x, z);
+}
+void launch_fr_mul_bench(Fr* inout, size_t n_threads, int iters, cudaStream_t stream) {
+    SB_LAUNCH(k_mul_bench<Fr>, (int)((n_threads + 255) / 256), 256, 0, stream, inout, n_threads, iters);
+}
+void launch_fq_mul_bench(Fq* inout, size_t n_threads, int iters, cudaStream_t stream) {
+    SB_LAUNCH(k_mul_bench<Fq>, (int)((n_threads + 255) / 256), 256, 0, stream, inout, n_threads, iters);
+}

@@ -1,0 +1,324 @@
+// msm.cu -- bucket-method MSM over pre-shifted fixed bases (G1 over Fq, G2 over Fq2), fixed-base
+// scalar multiplication and batched XYZZ -> affine conversion.  See msm.cuh for the design.
+// Integer-pipe bound (Fq Montgomery products); bases are gathered with 128-bit loads.
+#include "msm.cuh"
+
+// ------------------------------------------------------------------ window geometry
+int msm_window_bits(size_t m) {
+    int lg = 0;
+    while (((size_t)1 << lg) < m) lg++;
+    int c = lg - 3;
+    if (c < 4) c = 4;
+    if (c > 16) c = 16;
+    return c;
+}
+
+// ------------------------------------------------------------------ digits + counting sort
+constexpr uint32_t CODE_NONE = 0xffffffffu;
+
+__global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict__ scalars, size_t m, int c, int W,
+                                                    uint32_t* __restrict__ codes, uint32_t* __restrict__ counts) {
+    const uint32_t B = 1u << (c - 1);
+    const uint32_t mask = (1u << c) - 1;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x) {
+        Fr s = ldg_elem(&scalars[i]).to_canonical();          // "into_repr" (commit.rs:20-21, open.rs:46)
+        uint32_t limb[9];
+#pragma unroll
+        for (int k = 0; k < 8; k++) limb[k] = s.l[k];
+        limb[8] = 0;
+        uint32_t carry = 0;
+        for (int w = 0; w < W; w++) {
+            int bit = w * c;
+            uint32_t d = 0;
+            if (bit < 256) {
+                int lo = bit >> 5, sh = bit & 31;
+                uint64_t v = (uint64_t)limb[lo] | ((uint64_t)limb[lo + 1] << 32);
+                d = (uint32_t)(v >> sh) & mask;
+            }
+            d += carry;
+            uint32_t code;
+            if (d > B) {                       // negative digit d - 2^c, borrow one from the next window
+                uint32_t nd = (1u << c) - d; carry = 1;
+                code = nd ? (((uint32_t)w * B + nd - 1) | 0x80000000u) : CODE_NONE;
+            }
+            else { carry = 0; code = d ? ((uint32_t)w * B + d - 1) : CODE_NONE; }
+            codes[(size_t)w * m + i] = code;
+            if (code != CODE_NONE) atomicAdd(&counts[code & 0x7fffffffu], 1u);
+        }
+    }
+}
+
+// exclusive scan of `total` counters by one CTA; offsets[total] = grand total; cursors = copy of offsets
+__global__ void __launch_bounds__(1024) k_scan_exclusive(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
+                                                         uint32_t* __restrict__ cursors, uint32_t total) {
+    __shared__ uint32_t sh[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t chunk = (total + 1023) / 1024;
+    const uint32_t beg = tid * chunk, end = min(beg + chunk, total);
+    uint32_t sum = 0;
+    for (uint32_t i = beg; i < end; i++) sum += counts[i];
+    sh[tid] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024; off <<= 1) {
+        uint32_t v = tid >= off ? sh[tid - off] : 0;
+        __syncthreads();
+        sh[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = sh[tid] - sum;
+    for (uint32_t i = beg; i < end; i++) { offsets[i] = run; cursors[i] = run; run += counts[i]; }
+    if (tid == 1023) offsets[total] = sh[1023];
+}
+
+__global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __restrict__ codes, size_t total, uint32_t* __restrict__ cursors,
+                                                     uint32_t* __restrict__ sorted) {
+    for (size_t f = blockIdx.x * (size_t)blockDim.x + threadIdx.x; f < total; f += (size_t)gridDim.x * blockDim.x) {
+        uint32_t code = codes[f];
+        if (code == CODE_NONE) continue;
+        uint32_t pos = atomicAdd(&cursors[code & 0x7fffffffu], 1u);
+        sorted[pos] = (uint32_t)f | (code & 0x80000000u);      // f = w * m + i indexes the pre-shifted table
+    }
+}
+
+// ------------------------------------------------------------------ bucket accumulation
+template <class F>
+__global__ void __launch_bounds__(128) k_bucket_accum(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
+                                                      const uint32_t* __restrict__ offsets, uint32_t nkeys, XyzzPt<F>* __restrict__ buckets) {
+    uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= nkeys) return;
+    uint32_t beg = offsets[key], end = offsets[key + 1];
+    XyzzPt<F> acc = XyzzPt<F>::inf();
+    for (uint32_t e = beg; e < end; e++) {
+        uint32_t ent = __ldg(&sorted[e]);
+        AffinePt<F> p = ldg_elem(&tab[ent & 0x7fffffffu]);
+        if (ent & 0x80000000u) p.y = F::neg(p.y);
+        acc = XyzzPt<F>::add_mixed(acc, p);
+    }
+    st_elem(&buckets[key], acc);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_bucket_merge(const XyzzPt<F>* __restrict__ buckets, int W, uint32_t B, XyzzPt<F>* __restrict__ merged) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    XyzzPt<F> acc = ldg_elem(&buckets[b]);
+    for (int w = 1; w < W; w++) acc = XyzzPt<F>::add(acc, ldg_elem(&buckets[(size_t)w * B + b]));
+    st_elem(&merged[b], acc);
+}
+
+template <class F>
+__device__ XyzzPt<F> mul_small(const XyzzPt<F>& p, uint32_t k) {
+    XyzzPt<F> acc = XyzzPt<F>::inf();
+    for (int bit = 31 - __clz(k | 1); bit >= 0; bit--) {
+        acc = XyzzPt<F>::dbl(acc);
+        if ((k >> bit) & 1) acc = XyzzPt<F>::add(acc, p);
+    }
+    return k ? acc : XyzzPt<F>::inf();
+}
+
+constexpr int RED_THREADS = 64;
+// tree-sum RED_THREADS points held one per thread; result valid in thread 0
+template <class F>
+__device__ XyzzPt<F> block_tree_sum(XyzzPt<F> v, XyzzPt<F>* sh) {
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int stride = RED_THREADS / 2; stride > 0; stride >>= 1) {
+        if ((int)threadIdx.x < stride) sh[threadIdx.x] = XyzzPt<F>::add(sh[threadIdx.x], sh[threadIdx.x + stride]);
+        __syncthreads();
+    }
+    return sh[0];
+}
+// stage 1: thread t owns merged buckets [t L, (t+1) L): sum_b (b+1) M_b = running sums + (t L) * (sum of M_b)
+template <class F>
+__global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce1(const XyzzPt<F>* __restrict__ merged, uint32_t B, uint32_t L,
+                                                                XyzzPt<F>* __restrict__ block_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    XyzzPt<F>* sh = reinterpret_cast<XyzzPt<F>*>(smem_raw);
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t lo = (uint64_t)t * L;
+    XyzzPt<F> total = XyzzPt<F>::inf();
+    if (lo < B) {
+        uint32_t hi = (uint32_t)min((uint64_t)B, lo + L);
+        XyzzPt<F> run = XyzzPt<F>::inf(), sum = XyzzPt<F>::inf();
+        for (uint32_t b = hi; b-- > (uint32_t)lo;) {
+            run = XyzzPt<F>::add(run, ldg_elem(&merged[b]));
+            sum = XyzzPt<F>::add(sum, run);
+        }
+        total = XyzzPt<F>::add(sum, mul_small(run, (uint32_t)lo));
+    }
+    XyzzPt<F> r = block_tree_sum(total, sh);
+    if (threadIdx.x == 0) st_elem(&block_out[blockIdx.x], r);
+}
+template <class F>
+__global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce2(const XyzzPt<F>* __restrict__ block_out, uint32_t nblocks, XyzzPt<F>* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    XyzzPt<F>* sh = reinterpret_cast<XyzzPt<F>*>(smem_raw);
+    XyzzPt<F> acc = XyzzPt<F>::inf();
+    for (uint32_t i = threadIdx.x; i < nblocks; i += blockDim.x) acc = XyzzPt<F>::add(acc, block_out[i]);
+    XyzzPt<F> r = block_tree_sum(acc, sh);
+    if (threadIdx.x == 0) st_elem(out, r);
+}
+
+// ------------------------------------------------------------------ base expansion / affine conversion
+template <class F>
+__global__ void __launch_bounds__(128) k_preshift(const AffinePt<F>* __restrict__ bases, size_t i0, size_t cnt, int c, int W,
+                                                  XyzzPt<F>* __restrict__ tmp) {
+    size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (j >= cnt) return;
+    XyzzPt<F> p = XyzzPt<F>::from_affine(ldg_elem(&bases[i0 + j]));
+    st_elem(&tmp[j], p);
+    for (int w = 1; w < W; w++) {
+        for (int k = 0; k < c; k++) p = XyzzPt<F>::dbl(p);
+        st_elem(&tmp[(size_t)w * cnt + j], p);
+    }
+}
+
+constexpr int BTA_K = 8;
+// flat element f of `in` goes to out[(f / cnt) * m + i0 + (f % cnt)]
+template <class F>
+__global__ void __launch_bounds__(128) k_batch_to_affine(const XyzzPt<F>* __restrict__ in, AffinePt<F>* __restrict__ out, size_t n,
+                                                         size_t cnt, size_t m, size_t i0) {
+    size_t base = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * BTA_K;
+    if (base >= n) return;
+    F pre[BTA_K];
+    F acc = F::one();
+#pragma unroll 1
+    for (int k = 0; k < BTA_K; k++) {
+        pre[k] = acc;
+        size_t f = base + k;
+        if (f < n) {
+            F zzz = ldg_elem(&in[f].ZZZ);
+            if (!zzz.is_zero()) acc = F::mul(acc, zzz);
+        }
+    }
+    F inv = F::inv(acc);
+#pragma unroll 1
+    for (int k = BTA_K - 1; k >= 0; k--) {
+        size_t f = base + k;
+        if (f >= n) continue;
+        XyzzPt<F> p = ldg_elem(&in[f]);
+        AffinePt<F> a;
+        if (p.ZZZ.is_zero()) {
+            a = AffinePt<F>::inf();
+        } else {
+            F zi3 = F::mul(inv, pre[k]);
+            inv = F::mul(inv, p.ZZZ);
+            F zi2 = F::mul(F::sqr(zi3), F::sqr(p.ZZ));
+            a.x = F::mul(p.X, zi2);
+            a.y = F::mul(p.Y, zi3);
+        }
+        st_elem(&out[(f / cnt) * m + i0 + (f % cnt)], a);
+    }
+}
+
+template <class F>
+void batch_to_affine(const XyzzPt<F>* in_dev, AffinePt<F>* out_dev, size_t n, cudaStream_t stream) {
+    if (!n) return;
+    size_t threads = (n + BTA_K - 1) / BTA_K;
+    SB_LAUNCH((k_batch_to_affine<F>), (int)((threads + 127) / 128), 128, 0, stream, in_dev, out_dev, n, n, n, (size_t)0);
+}
+
+template <class F>
+void msm_prepare(const AffinePt<F>* bases_dev, size_t m, MsmBases<F>& out, cudaStream_t stream) {
+    out.m = m; out.c = msm_window_bits(m); out.W = msm_num_windows(out.c);
+    out.tab.alloc((size_t)out.W * m, stream);
+    const size_t chunk = m < ((size_t)1 << 16) ? m : ((size_t)1 << 16);
+    DevBuf<XyzzPt<F>> tmp((size_t)out.W * chunk, stream);
+    for (size_t i0 = 0; i0 < m; i0 += chunk) {
+        size_t cnt = m - i0 < chunk ? m - i0 : chunk;
+        SB_LAUNCH((k_preshift<F>), (int)((cnt + 127) / 128), 128, 0, stream, bases_dev, i0, cnt, out.c, out.W, tmp.get());
+        size_t n = (size_t)out.W * cnt;
+        size_t threads = (n + BTA_K - 1) / BTA_K;
+        SB_LAUNCH((k_batch_to_affine<F>), (int)((threads + 127) / 128), 128, 0, stream, tmp.get(), out.tab.get(), n, cnt, m, i0);
+    }
+}
+
+template <class F>
+void msm_run(const MsmBases<F>& bases, const Fr* scalars_dev, size_t m, XyzzPt<F>* out_dev, cudaStream_t stream) {
+    SB_REQUIRE(m == bases.m, "msm: scalar count does not match the prepared bases");
+    const int c = bases.c, W = bases.W;
+    const uint32_t B = 1u << (c - 1);
+    const uint32_t nkeys = (uint32_t)W * B;
+    const size_t total = (size_t)W * m;
+    SB_REQUIRE(total < ((size_t)1 << 31), "msm: too many (window, point) pairs for 31-bit table indices");
+    DevBuf<uint32_t> codes(total, stream), sorted(total, stream);
+    DevBuf<uint32_t> counts(nkeys, stream), offsets(nkeys + 1, stream), cursors(nkeys, stream);
+    DevBuf<XyzzPt<F>> buckets(nkeys, stream), merged(B, stream);
+    SB_CUDA(cudaMemsetAsync(counts.get(), 0, counts.bytes(), stream));
+    SB_LAUNCH(k_msm_digits, grid_for(m, 256, 8), 256, 0, stream, scalars_dev, m, c, W, codes.get(), counts.get());
+    SB_LAUNCH(k_scan_exclusive, 1, 1024, 0, stream, counts.get(), offsets.get(), cursors.get(), nkeys);
+    SB_LAUNCH(k_msm_scatter, grid_for(total, 256, 8), 256, 0, stream, codes.get(), total, cursors.get(), sorted.get());
+    SB_LAUNCH((k_bucket_accum<F>), (int)((nkeys + 127) / 128), 128, 0, stream, bases.tab.get(), sorted.get(), offsets.get(), nkeys, buckets.get());
+    SB_LAUNCH((k_bucket_merge<F>), (int)((B + 127) / 128), 128, 0, stream, buckets.get(), W, B, merged.get());
+    const uint32_t L = B >= 8 * RED_THREADS ? 8 : 1;
+    const uint32_t nthreads = (B + L - 1) / L;
+    const uint32_t nblocks = (nthreads + RED_THREADS - 1) / RED_THREADS;
+    DevBuf<XyzzPt<F>> block_out(nblocks, stream);
+    const size_t smem = RED_THREADS * sizeof(XyzzPt<F>);
+    SB_LAUNCH((k_bucket_reduce1<F>), (int)nblocks, RED_THREADS, smem, stream, merged.get(), B, L, block_out.get());
+    SB_LAUNCH((k_bucket_reduce2<F>), 1, RED_THREADS, smem, stream, block_out.get(), nblocks, out_dev);
+}
+
+// ------------------------------------------------------------------ fixed-base multiplication (keygen)
+constexpr int FB_W = 8;                       // window bits
+constexpr int FB_NWIN = 32;                   // 32 * 8 = 256 >= 255
+
+template <class F>
+__global__ void k_fb_window_bases(AffinePt<F> g, XyzzPt<F>* __restrict__ wb) {
+    int win = threadIdx.x;
+    if (win >= FB_NWIN) return;
+    XyzzPt<F> p = XyzzPt<F>::from_affine(g);
+    for (int k = 0; k < win * FB_W; k++) p = XyzzPt<F>::dbl(p);
+    wb[win] = p;
+}
+template <class F>
+__global__ void __launch_bounds__(128) k_fb_table(const XyzzPt<F>* __restrict__ wb, XyzzPt<F>* __restrict__ tab) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= FB_NWIN * (1u << FB_W)) return;
+    uint32_t win = t >> FB_W, k = t & ((1u << FB_W) - 1);
+    tab[t] = mul_small(wb[win], k);
+}
+template <class F>
+__global__ void __launch_bounds__(128) k_fixed_base(const AffinePt<F>* __restrict__ tab, const Fr* __restrict__ scalars, size_t n,
+                                                    XyzzPt<F>* __restrict__ out) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr s = ldg_elem(&scalars[i]).to_canonical();
+    XyzzPt<F> acc = XyzzPt<F>::inf();
+#pragma unroll
+    for (int limb = 0; limb < 8; limb++) {
+        uint32_t v = s.l[limb];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t d = (v >> (8 * k)) & 0xffu;
+            if (d) acc = XyzzPt<F>::add_mixed(acc, ldg_elem(&tab[(uint32_t)(limb * 4 + k) * 256u + d]));
+        }
+    }
+    st_elem(&out[i], acc);
+}
+
+template <class F>
+void fixed_base_mul(const AffinePt<F>& g_host, const Fr* scalars_dev, size_t n, AffinePt<F>* out_dev, cudaStream_t stream) {
+    const size_t tab_n = (size_t)FB_NWIN << FB_W;
+    DevBuf<XyzzPt<F>> wb(FB_NWIN, stream), tabx(tab_n, stream);
+    DevBuf<AffinePt<F>> tab(tab_n, stream);
+    SB_LAUNCH((k_fb_window_bases<F>), 1, 32, 0, stream, g_host, wb.get());
+    SB_LAUNCH((k_fb_table<F>), (int)((tab_n + 127) / 128), 128, 0, stream, wb.get(), tabx.get());
+    batch_to_affine<F>(tabx.get(), tab.get(), tab_n, stream);
+    const size_t chunk = (size_t)1 << 22;
+    DevBuf<XyzzPt<F>> tmp(n < chunk ? n : chunk, stream);
+    for (size_t i0 = 0; i0 < n; i0 += chunk) {
+        size_t cnt = n - i0 < chunk ? n - i0 : chunk;
+        SB_LAUNCH((k_fixed_base<F>), (int)((cnt + 127) / 128), 128, 0, stream, tab.get(), scalars_dev + i0, cnt, tmp.get());
+        batch_to_affine<F>(tmp.get(), out_dev + i0, cnt, stream);
+    }
+}
+
+template void msm_prepare<Fq>(const AffinePt<Fq>*, size_t, MsmBases<Fq>&, cudaStream_t);
+template void msm_prepare<Fq2>(const AffinePt<Fq2>*, size_t, MsmBases<Fq2>&, cudaStream_t);
+template void msm_run<Fq>(const MsmBases<Fq>&, const Fr*, size_t, XyzzPt<Fq>*, cudaStream_t);
+template void msm_run<Fq2>(const MsmBases<Fq2>&, const Fr*, size_t, XyzzPt<Fq2>*, cudaStream_t);
+template void fixed_base_mul<Fq>(const AffinePt<Fq>&, const Fr*, size_t, AffinePt<Fq>*, cudaStream_t);
+template void fixed_base_mul<Fq2>(const AffinePt<Fq2>&, const Fr*, size_t, AffinePt<Fq2>*, cudaStream_t);
+template void batch_to_affine<Fq>(const XyzzPt<Fq>*, AffinePt<Fq>*, size_t, cudaStream_t);
+template void batch_to_affine<Fq2>(const XyzzPt<Fq2>*, AffinePt<Fq2>*, size_t, cudaStream_t);

@@ -1,0 +1,267 @@
+#!/usr/bin/env python3
+"""Generator for csrc/fp_gen.cuh: fully unrolled Montgomery multiplication / add / sub in PTX carry
+chains (mad.lo.cc / madc.hi.cc pairs, which ptxas fuses into IMAD.WIDE.U32 with carry predicates)
+for the two BLS12-381 prime fields in 32-bit limbs (Fr: 8 limbs, Fq: 12 limbs).
+
+The instruction stream is produced ONCE as an abstract list and rendered twice: as PTX text for the
+header, and through a bit-exact 32-bit-register + carry-flag emulator (`emulate`) that
+tests/test_field_gen.py runs against Python big integers -- so the sequence nvcc compiles is the
+sequence that was verified on the CPU.
+
+Scheme (per row i of b):   T = E + 2^32 * O   (E: even-offset accumulator, O: odd-offset accumulator)
+    E += sum_{j even} a[j] b_i 2^(32 j)      one carry chain over N limbs (64-bit products abut)
+    O += sum_{j odd}  a[j] b_i 2^(32 (j-1))  one carry chain
+    m  = E[0] * (-p^-1 mod 2^32);  E += (p_even) m;  O += (p_odd) m        => E[0] == 0
+    shift right by one limb: the arrays swap roles, the old E is consumed two limbs further up.
+Bounds: p < 2^(32N-1) so T < 2p after every row and no carry ever leaves the odd accumulator.
+"""
+import sys
+
+FIELDS = {
+    "fr": dict(N=8, p=0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001),
+    "fq": dict(N=12, p=0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab),
+}
+M32 = 0xFFFFFFFF
+
+
+def limbs(v, n):
+    return [(v >> (32 * i)) & M32 for i in range(n)]
+
+
+def gen_mul(N, p):
+    """abstract instruction list computing r = a*b*2^(-32N) mod p (inputs < p)"""
+    P = limbs(p, N)
+    inv = (-pow(p, -1, 1 << 32)) & M32
+    ins = []
+    X = ["x%d" % i for i in range(N)]   # offset-0 accumulator at the start
+    Y = ["y%d" % i for i in range(N)]   # offset-1 accumulator
+    a = ["a%d" % i for i in range(N)]
+    b = ["b%d" % i for i in range(N)]
+
+    def chain_mad(dst, src_mul, k, first_has_carry_in=False, addend=None, last_cc=True):
+        """dst[2t], dst[2t+1] (+)= src_mul[t] * k along one carry chain.  addend: list of N operands
+        (defaults to dst itself)."""
+        add = addend if addend is not None else dst
+        for t in range(N // 2):
+            lo = ("madc.lo.cc" if (t > 0 or first_has_carry_in) else "mad.lo.cc")
+            ins.append((lo, dst[2 * t], src_mul[t], k, add[2 * t]))
+            hi = "madc.hi.cc" if (last_cc or t < N // 2 - 1) else "madc.hi"
+            ins.append((hi, dst[2 * t + 1], src_mul[t], k, add[2 * t + 1]))
+
+    a_even = [a[j] for j in range(0, N, 2)]
+    a_odd = [a[j] for j in range(1, N, 2)]
+    # modulus limbs enter the mad chains as REGISTER operands fed from __constant__ memory: with
+    # immediates ptxas strength-reduces the special limbs (Fr: 0x00000001, 0xffffffff) into IADD3
+    # forms, which breaks the lo/hi pairing of the whole chain (179 instead of 128 IMAD per Fr mul).
+    p_even = ["p%d" % j for j in range(0, N, 2)]
+    p_odd = ["p%d" % j for j in range(1, N, 2)]
+
+    for i in range(N):
+        if i == 0:
+            for t in range(N // 2):
+                ins.append(("mul.lo", X[2 * t], a_even[t], b[0]))
+                ins.append(("mul.hi", X[2 * t + 1], a_even[t], b[0]))
+                ins.append(("mul.lo", Y[2 * t], a_odd[t], b[0]))
+                ins.append(("mul.hi", Y[2 * t + 1], a_odd[t], b[0]))
+            E, O = X, Y
+        else:
+            # previous row left: X = offset-0 array with X[0] == 0, Y = offset-1 array.
+            # new offset-0 array E = Y (+ X[1] into limb 0), new offset-1 array O = X >> 64 (+ odd products)
+            ins.append(("add.cc", Y[0], Y[0], X[1]))
+            shifted = [X[j + 2] for j in range(N - 2)] + ["0", "0"]
+            chain_mad(X, a_odd, b[i], first_has_carry_in=True, addend=shifted, last_cc=False)
+            chain_mad(Y, a_even, b[i])
+            ins.append(("addc", X[N - 1], X[N - 1], "0"))
+            E, O = Y, X
+        ins.append(("mul.lo", "m", E[0], "pinv"))
+        chain_mad(O, p_odd, "m", last_cc=False)
+        chain_mad(E, p_even, "m")
+        ins.append(("addc", O[N - 1], O[N - 1], "0"))
+        X, Y = E, O          # X: offset 0 with X[0] == 0; Y: offset 1
+    # merge: T = (X >> 32) + Y
+    r = ["r%d" % i for i in range(N)]
+    for k in range(N):
+        src = X[k + 1] if k + 1 < N else "0"
+        op = "add.cc" if k == 0 else ("addc.cc" if k < N - 1 else "addc")
+        ins.append((op, r[k], Y[k], src))
+    gen_final_sub(ins, N, P, r)
+    return ins
+
+
+def gen_final_sub(ins, N, P, r):
+    """r = r >= p ? r - p : r  (r < 2p)"""
+    s = ["s%d" % i for i in range(N)]
+    for k in range(N):
+        op = "sub.cc" if k == 0 else "subc.cc"
+        ins.append((op, s[k], r[k], hex(P[k])))
+    ins.append(("subc", "bw", "0", "0"))          # bw = 0xffffffff iff borrow (r < p)
+    for k in range(N):
+        ins.append(("selnz", r[k], r[k], s[k], "bw"))   # r = bw != 0 ? r : s
+
+
+def gen_add(N, p):
+    P = limbs(p, N); ins = []
+    r = ["r%d" % i for i in range(N)]
+    for k in range(N):
+        op = "add.cc" if k == 0 else ("addc.cc" if k < N - 1 else "addc")
+        ins.append((op, r[k], "a%d" % k, "b%d" % k))
+    gen_final_sub(ins, N, P, r)      # a + b < 2p < 2^(32N): no carry out
+    return ins
+
+
+def gen_sub(N, p):
+    P = limbs(p, N); ins = []
+    r = ["r%d" % i for i in range(N)]
+    for k in range(N):
+        op = "sub.cc" if k == 0 else "subc.cc"
+        ins.append((op, r[k], "a%d" % k, "b%d" % k))
+    ins.append(("subc", "bw", "0", "0"))
+    # add back p & mask
+    for k in range(N):
+        ins.append(("and", "s%d" % k, "bw", hex(P[k])))
+    for k in range(N):
+        op = "add.cc" if k == 0 else "addc.cc"      # the top carry is the intended wrap-around
+        ins.append((op, r[k], r[k], "s%d" % k))
+    return ins
+
+
+# ------------------------------------------------------------------ emulator
+def emulate(ins, env, strict=True):
+    """Execute the abstract stream on 32-bit registers with one carry flag (PTX CC.CF semantics)."""
+    cf = 0
+
+    def val(x):
+        if x.startswith("0x"):
+            return int(x, 16)
+        if x == "0":
+            return 0
+        return env[x]
+    for t in ins:
+        op = t[0]
+        if op in ("mul.lo", "mul.hi"):
+            pr = val(t[2]) * val(t[3])
+            env[t[1]] = (pr & M32) if op == "mul.lo" else (pr >> 32)
+        elif op in ("mad.lo.cc", "madc.lo.cc", "madc.hi.cc", "madc.hi", "mad.hi.cc"):
+            pr = val(t[2]) * val(t[3])
+            part = (pr & M32) if ".lo" in op else (pr >> 32)
+            s = part + val(t[4]) + (cf if op.startswith("madc") else 0)
+            env[t[1]] = s & M32
+            if op.endswith(".cc"):
+                cf = s >> 32
+            elif strict:
+                assert s >> 32 == 0, ("dropped carry", t)
+        elif op in ("add.cc", "addc.cc", "addc"):
+            s = val(t[2]) + val(t[3]) + (cf if op.startswith("addc") else 0)
+            env[t[1]] = s & M32
+            if op.endswith(".cc"):
+                cf = s >> 32
+            elif strict:
+                assert s >> 32 == 0, ("dropped carry", t)
+        elif op in ("sub.cc", "subc.cc", "subc"):
+            s = val(t[2]) - val(t[3]) - (cf if op.startswith("subc") else 0)
+            env[t[1]] = s & M32
+            if op.endswith(".cc"):
+                cf = 1 if s < 0 else 0
+        elif op == "selnz":
+            env[t[1]] = val(t[2]) if val(t[4]) != 0 else val(t[3])
+        elif op == "and":
+            env[t[1]] = val(t[2]) & val(t[3])
+        else:
+            raise ValueError(op)
+    return env
+
+
+def run_emulated(kind, field, a, b):
+    f = FIELDS[field]; N = f["N"]
+    ins = {"mul": gen_mul, "add": gen_add, "sub": gen_sub}[kind](N, f["p"])
+    env = {}
+    for i, (x, y) in enumerate(zip(limbs(a, N), limbs(b, N))):
+        env["a%d" % i] = x; env["b%d" % i] = y
+    for i, x in enumerate(limbs(f["p"], N)):
+        env["p%d" % i] = x
+    env["pinv"] = (-pow(f["p"], -1, 1 << 32)) & M32
+    emulate(ins, env)
+    return sum(env["r%d" % i] << (32 * i) for i in range(N))
+
+
+# ------------------------------------------------------------------ PTX rendering
+def render(name, ins, N, modc=None):
+    regs = set()
+    for t in ins:
+        for x in t[1:]:
+            if not (x.startswith("0x") or x == "0"):
+                regs.add(x)
+    inputs = ["a%d" % i for i in range(N)] + ["b%d" % i for i in range(N)]
+    if modc:
+        inputs += ["p%d" % i for i in range(N)] + ["pinv"]
+    outputs = ["r%d" % i for i in range(N)]
+    temps = sorted(regs - set(inputs) - set(outputs))
+    opmap = {}
+    for i, r in enumerate(outputs):
+        opmap[r] = "%%%d" % i
+    for i, r in enumerate(inputs):
+        opmap[r] = "%%%d" % (N + i)
+
+    def o(x):
+        if x.startswith("0x") or x == "0":
+            return x if x != "0" else "0"
+        return opmap.get(x, x)
+    lines = []
+    lines.append("    \"{\\n\\t\"")
+    lines.append("    \".reg .u32 %s;\\n\\t\"" % ", ".join(temps))
+    lines.append("    \".reg .pred pz;\\n\\t\"")
+    for t in ins:
+        op = t[0]
+        if op in ("mul.lo", "mul.hi"):
+            s = "%s.u32 %s, %s, %s;" % (op, o(t[1]), o(t[2]), o(t[3]))
+        elif op.startswith("mad"):
+            s = "%s.u32 %s, %s, %s, %s;" % (op, o(t[1]), o(t[2]), o(t[3]), o(t[4]))
+        elif op.startswith("add") or op.startswith("sub"):
+            s = "%s.u32 %s, %s, %s;" % (op, o(t[1]), o(t[2]), o(t[3]))
+        elif op == "and":
+            s = "and.b32 %s, %s, %s;" % (o(t[1]), o(t[2]), o(t[3]))
+        elif op == "selnz":
+            s = "setp.ne.u32 pz, %s, 0; selp.u32 %s, %s, %s, pz;" % (o(t[4]), o(t[1]), o(t[2]), o(t[3]))
+        else:
+            raise ValueError(op)
+        lines.append("    \"%s\\n\\t\"" % s)
+    lines.append("    \"}\"")
+    outs = ", ".join("\"=&r\"(r[%d])" % i for i in range(N))
+    ins_ = ", ".join(["\"r\"(a[%d])" % i for i in range(N)] + ["\"r\"(b[%d])" % i for i in range(N)] +
+                     (["\"r\"(%s[%d])" % (modc, i) for i in range(N + 1)] if modc else []))
+    body = "\n".join(lines)
+    return ("__device__ __forceinline__ void %s(uint32_t* __restrict__ r, const uint32_t* a, const uint32_t* b) {\n"
+            "  asm(\n%s\n    : %s\n    : %s);\n}\n" % (name, body, outs, ins_))
+
+
+def main(out_path):
+    parts = ["// GENERATED by tools/gen_field.py -- do not edit.  Unrolled PTX carry-chain field arithmetic\n"
+             "// (32-bit limbs, Montgomery radix 2^(32 N)) for BLS12-381 Fr (N=8) and Fq (N=12).\n"
+             "// The same instruction streams are verified against big integers by tests/test_field_gen.py.\n"
+             "#pragma once\n#include <cstdint>\n"]
+    for fname, f in FIELDS.items():
+        N = f["N"]; p = f["p"]; R = 1 << (32 * N)
+        def arr(v):
+            return "{" + ", ".join("0x%08xu" % x for x in limbs(v, N)) + "}"
+        U = fname.upper()
+        parts.append("#define %s_LIMBS %d" % (U, N))
+        parts.append("#define %s_MOD_INIT %s" % (U, arr(p)))
+        parts.append("#define %s_R1_INIT %s   /* R mod p: Montgomery one */" % (U, arr(R % p)))
+        parts.append("#define %s_R2_INIT %s   /* R^2 mod p */" % (U, arr(R * R % p)))
+        parts.append("#define %s_INV32 0x%08xu   /* -p^-1 mod 2^32 */\n" % (U, (-pow(p, -1, 1 << 32)) & M32))
+    parts.append("#if defined(__CUDACC__)\n")
+    for fname, f in FIELDS.items():
+        N = f["N"]
+        # outputs may alias inputs at the call site: the wrappers in fp.cuh copy through temporaries
+        parts.append("// modulus limbs followed by -p^-1 mod 2^32; deliberately not const (see gen_field.py)\n"
+                     "static __device__ __constant__ uint32_t %s_MOD_C[%d] = {%s, 0x%08xu};\n"
+                     % (fname.upper(), N + 1, ", ".join("0x%08xu" % x for x in limbs(f["p"], N)), (-pow(f["p"], -1, 1 << 32)) & M32))
+        parts.append(render("%s_mul_ptx" % fname, gen_mul(N, f["p"]), N, modc="%s_MOD_C" % fname.upper()))
+        parts.append(render("%s_add_ptx" % fname, gen_add(N, f["p"]), N))
+        parts.append(render("%s_sub_ptx" % fname, gen_sub(N, f["p"]), N))
+    parts.append("#endif  // __CUDACC__\n")
+    open(out_path, "w").write("\n".join(parts))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else "fp_gen.cuh")

@@ -1,0 +1,356 @@
+"""GPU parity tests: every stage of the CUDA path against the CPU oracle, through the C ABI.
+
+Bar: bit-exact (all arithmetic is exact field / group arithmetic).  The oracle follows the reference
+literally (log_n separate eq tables, 2 log_n + 3 sumcheck tables, duplicated-scalar G2 MSMs), so these
+tests also validate the algebraic rewrites the CUDA path uses.
+"""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FR_MOD = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+FQ_MOD = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import r1cs_spartan_b200 as m
+    return m
+
+
+def _edge_and_random(mod, n, seed):
+    rnd = random.Random(seed)
+    edge = [0, 1, 2, mod - 1, mod - 2, (mod - 1) // 2, (1 << 32) - 1, 1 << 32, (1 << 64) - 1, 1 << 255 if mod > (1 << 255) else 1 << 200]
+    edge = [e % mod for e in edge]
+    vals = edge + [rnd.randrange(mod) for _ in range(n - len(edge))]
+    return vals
+
+
+# ---------------------------------------------------------------- field arithmetic (K0)
+@pytest.mark.parametrize("field", ["fr", "fq"])
+def test_field_ops_match_oracle(sb, oracle, gpu_ctx, field):
+    mod = FR_MOD if field == "fr" else FQ_MOD
+    n = 4096
+    a = _edge_and_random(mod, n, 1); b = list(reversed(_edge_and_random(mod, n, 2)))
+    to_m = oracle.fr_from_ints if field == "fr" else oracle.fq_from_ints
+    binop = oracle.fr_binop if field == "fr" else oracle.fq_binop
+    A, B = to_m(a), to_m(b)
+    for op in ("add", "sub", "mul"):
+        got = gpu_ctx.field_binop(field, op, A, B)
+        assert np.array_equal(got, binop(op, A, B)), (field, op)
+    # the PTX carry-chain product against the portable 64-bit-accumulator product on the device itself
+    assert np.array_equal(gpu_ctx.field_binop(field, "mul", A, B), gpu_ctx.field_binop(field, "mul_portable", A, B))
+
+
+# ---------------------------------------------------------------- eq table (K2)
+@pytest.mark.parametrize("dim", [1, 2, 5, 9, 12])
+def test_eq_table_is_product_of_reference_tables(sb, oracle, gpu_ctx, dim):
+    t = oracle.fr_rand(1000 + dim, dim)
+    got = sb.eq_extension(t, ctx=gpu_ctx)
+    ref = oracle.eq_extension(t)          # (dim, 2^dim, 4): the reference's dim separate tables
+    prod = ref[0]
+    for i in range(1, dim):
+        prod = oracle.fr_binop("mul", prod, ref[i])
+    assert np.array_equal(got, prod)
+
+
+def test_eq_table_boolean_point_is_indicator(sb, oracle, gpu_ctx):
+    # reference test eq::functionality_test (eq.rs:30-46): t = 0b101101001 over 9 variables
+    tbits = 0b101101001
+    t = oracle.fr_from_ints([(tbits >> i) & 1 for i in range(9)])
+    got = sb.eq_extension(t, ctx=gpu_ctx)
+    ints = oracle.fr_to_ints(got)
+    assert ints[tbits] == 1 and sum(ints) == 1
+
+
+# ---------------------------------------------------------------- sparse products (K1, K5)
+def _random_csr(oracle, log_n, nnz, seed, unit_fraction=0.5):
+    rnd = random.Random(seed)
+    n = 1 << log_n
+    cells = set()
+    while len(cells) < nnz:
+        cells.add((rnd.randrange(n), rnd.randrange(n)))
+    rows = [[] for _ in range(n)]
+    for (x, y) in sorted(cells):
+        rows[x].append(y)
+    row_ptr = np.zeros(n + 1, dtype=np.uint64)
+    col = []
+    for x in range(n):
+        row_ptr[x + 1] = row_ptr[x] + len(rows[x])
+        col += rows[x]
+    vals = oracle.fr_rand(seed + 7, nnz)
+    one = oracle.fr_from_ints([1])[0]
+    for e in range(nnz):
+        if rnd.random() < unit_fraction:
+            vals[e] = one
+    return row_ptr, np.array(col, dtype=np.uint32), vals
+
+
+@pytest.mark.parametrize("log_n,nnz", [(3, 10), (6, 512), (8, 3000)])
+def test_sum_over_y_and_eval_on_x_random_matrices(sb, oracle, gpu_ctx, log_n, nnz):
+    mats = [_random_csr(oracle, log_n, nnz, 10 * log_n + k) for k in range(3)]
+    pk = sb.MLProofForR1CS.index(*mats, ctx=gpu_ctx)
+    ocs = oracle.R1CS.from_csr(log_n, mats)
+    z = oracle.fr_rand(5, 1 << log_n)
+    got = pk.sum_over_y(z)
+    for k in range(3):
+        assert np.array_equal(got[k], ocs.sum_over_y(k, z)), k
+    r_x = oracle.fr_rand(6, log_n)
+    for k in range(3):
+        assert np.array_equal(pk.eval_on_x(r_x, which=k), ocs.eval_on_x(k, r_x)), k
+    r_abc = oracle.fr_rand(8, 3)
+    comb = None
+    for k in range(3):
+        term = oracle.fr_binop("mul", ocs.eval_on_x(k, r_x), np.repeat(r_abc[k:k + 1], 1 << log_n, axis=0))
+        comb = term if comb is None else oracle.fr_binop("add", comb, term)
+    assert np.array_equal(pk.eval_on_x(r_x, r_abc=r_abc), comb)
+
+
+def test_eval_on_x_boolean_point_returns_matrix_row(sb, oracle, gpu_ctx):
+    # reference test r1cs_reader::test_eval_on_x_sanity (r1cs_reader.rs:128-145): x = 0b110010, LSB-first point
+    log_n = 6
+    mats = [_random_csr(oracle, log_n, 1 << 9, 77 + k, unit_fraction=0.0) for k in range(3)]
+    pk = sb.MLProofForR1CS.index(*mats, ctx=gpu_ctx)
+    x = 0b110010
+    point = oracle.fr_from_ints([(x >> i) & 1 for i in range(log_n)])
+    got = pk.eval_on_x(point, which=0)
+    row_ptr, col, val = mats[0]
+    expect = np.zeros((1 << log_n, 4), dtype=np.uint64)
+    for e in range(int(row_ptr[x]), int(row_ptr[x + 1])):
+        expect[col[e]] = val[e]
+    assert np.array_equal(got, expect)
+
+
+def test_synthetic_circuit_long_row_and_column(sb, oracle, gpu_ctx):
+    # the benchmark circuit has one ~n-entry row (A, B) and an ~n/2-entry column 0 (B): exercises the split path
+    log_n = 10
+    cs = sb.SyntheticR1CS(32, (1 << log_n) - 32, 0, 4242)
+    pk = sb.MLProofForR1CS.index(*cs.mats, ctx=gpu_ctx)
+    ocs = oracle.R1CS.from_csr(log_n, cs.mats)
+    z = np.concatenate([cs.v, cs.w])
+    assert ocs.is_satisfied(z)
+    got = pk.sum_over_y(z)
+    for k in range(3):
+        assert np.array_equal(got[k], ocs.sum_over_y(k, z))
+    r_x = oracle.fr_rand(9, log_n)
+    for k in range(3):
+        assert np.array_equal(pk.eval_on_x(r_x, which=k), ocs.eval_on_x(k, r_x))
+
+
+# ---------------------------------------------------------------- keygen / MSM / commitment (K7-K9)
+@pytest.fixture(scope="module")
+def small_pp(sb, oracle, gpu_ctx):
+    nv = 6
+    g, h = oracle.generators()
+    t = oracle.fr_rand(31337, nv)
+    return nv, g, h, t, sb.MLPolyCommit.keygen(nv, g, h, t, keep_all_levels=True, ctx=gpu_ctx), oracle.PP.keygen_with(nv, g, h, t)
+
+
+def test_keygen_matches_oracle(sb, oracle, small_pp):
+    nv, g, h, t, pp, opp = small_pp
+    for level in range(nv):
+        assert np.array_equal(pp.export(1, level), opp.g1(level)), ("g1", level)
+        assert np.array_equal(pp.export(2, level), opp.g2(level)), ("g2", level)
+    assert np.array_equal(pp.g_mask_random(), opp.g_mask())
+
+
+def test_pp_load_equals_keygen(sb, oracle, gpu_ctx, small_pp):
+    nv, g, h, t, pp, opp = small_pp
+    pp2 = sb.MLPolyCommit.load(nv, opp.g1(0), [opp.g2(i) for i in range(nv)], h, ctx=gpu_ctx)
+    z = oracle.fr_rand(3, 1 << nv)
+    point = oracle.fr_rand(4, nv)
+    assert np.array_equal(sb.MLPolyCommit.commit(pp2, z)[1], sb.MLPolyCommit.commit(pp, z)[1])
+    e1, (_, p1) = sb.MLPolyCommit.open(pp2, z, point)
+    e2, (_, p2) = sb.MLPolyCommit.open(pp, z, point)
+    assert np.array_equal(e1, e2) and np.array_equal(p1, p2)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 33, 1000])
+def test_msm_matches_oracle(sb, oracle, gpu_ctx, n):
+    g, h = oracle.generators()
+    ks = oracle.fr_rand(50 + n, n)
+    b1 = np.stack([oracle.g1_mul(g, ks[i]) for i in range(n)])
+    b2 = np.stack([oracle.g2_mul(h, ks[i]) for i in range(n)])
+    s = oracle.fr_rand(60 + n, n)
+    assert np.array_equal(sb.multi_scalar_mul(1, b1, s, ctx=gpu_ctx), oracle.msm_g1(b1, s))
+    assert np.array_equal(sb.multi_scalar_mul(2, b2, s, ctx=gpu_ctx), oracle.msm_g2(b2, s))
+
+
+def test_msm_structured_scalars(sb, oracle, gpu_ctx):
+    # zero / one / minus-one / repeated scalars and repeated bases: the exceptional cases of the group law
+    g, _ = oracle.generators()
+    n = 64
+    ks = oracle.fr_rand(5, n)
+    bases = np.stack([oracle.g1_mul(g, ks[i % 4]) for i in range(n)])       # only 4 distinct bases
+    vals = [0, 1, FR_MOD - 1, 2, 5, 5, 5, 5] * (n // 8)
+    s = oracle.fr_from_ints(vals)
+    assert np.array_equal(sb.multi_scalar_mul(1, bases, s, ctx=gpu_ctx), oracle.msm_g1(bases, s))
+    zeros = oracle.fr_from_ints([0] * n)
+    assert not sb.multi_scalar_mul(1, bases, zeros, ctx=gpu_ctx).any()       # infinity = all-zero encoding
+
+
+def test_commit_and_open_match_oracle(sb, oracle, small_pp):
+    nv, g, h, t, pp, opp = small_pp
+    z = oracle.fr_rand(71, 1 << nv)
+    point = oracle.fr_rand(72, nv)
+    got_nv, com = sb.MLPolyCommit.commit(pp, z)
+    assert got_nv == nv and np.array_equal(com, opp.commit(z))
+    # reference test commit::commit_test (commit.rs:54-66): commit == g * f(t)
+    assert np.array_equal(com, oracle.g1_mul(g, oracle.mle_eval(z, t)))
+    ev, (hh, proofs) = sb.MLPolyCommit.open(pp, z, point)
+    oev, oproofs = opp.open(z, point)
+    assert np.array_equal(ev, oev) and np.array_equal(proofs, oproofs) and np.array_equal(hh, h)
+
+
+def test_open_at_padded_public_point(sb, oracle, small_pp):
+    # prover_second_round opens at (r_v, 0, .., 0) (prover.rs:152): zero coordinates make r' = even
+    nv, g, h, t, pp, opp = small_pp
+    z = oracle.fr_rand(81, 1 << nv)
+    point = np.zeros((nv, 4), dtype=np.uint64)
+    point[:2] = oracle.fr_rand(82, 2)
+    ev, (_, proofs) = sb.MLPolyCommit.open(pp, z, point)
+    oev, oproofs = opp.open(z, point)
+    assert np.array_equal(ev, oev) and np.array_equal(proofs, oproofs)
+
+
+# ---------------------------------------------------------------- AHP rounds with explicit verifier messages
+def test_interactive_rounds_match_literal_sumcheck(sb, oracle, gpu_ctx, small_pp):
+    # the shape of reference test ahp::tests::test_small (ahp/tests.rs:8-75) with caller-chosen challenges
+    nv, g, h, t, pp, opp = small_pp
+    log_n, log_v = nv, 2
+    cs = sb.SyntheticR1CS(1 << log_v, (1 << log_n) - (1 << log_v), 1, 555)
+    pk = sb.MLProofForR1CS.index(*cs.mats, ctx=gpu_ctx)
+    ocs = oracle.R1CS.from_csr(log_n, cs.mats)
+    z = np.concatenate([cs.v, cs.w])
+    P = sb.MLProofForR1CS
+    st = P.prover_init(pk, cs.v, cs.w)
+    st, m1 = P.prover_first_round(st, pp)
+    assert np.array_equal(m1["commitment"][1], opp.commit(z))
+    r_v = oracle.fr_rand(1, log_v)
+    st, m2 = P.prover_second_round(st, r_v, pp)
+    pt = np.zeros((log_n, 4), dtype=np.uint64); pt[:log_v] = r_v
+    oev, oproofs = opp.open(z, pt)
+    assert np.array_equal(m2["z_rv_0"], oev) and np.array_equal(m2["proof_for_z_rv_0"][1], oproofs)
+    tor = oracle.fr_rand(2, log_n)
+    st, m3 = P.prover_third_round(st, tor)
+    assert m3["ml_index_info"] == (log_n + 2, log_n)
+    az, bz, cz = st.export_abc()
+    oabc = [ocs.sum_over_y(k, z) for k in range(3)]
+    assert all(np.array_equal(x, y) for x, y in zip((az, bz, cz), oabc))
+    # literal first sumcheck: products [Az, Bz, eq_0..] and [-Cz, eq_0..]
+    chal = oracle.fr_rand(3, log_n)
+    eq = oracle.eq_extension(tor)
+    ncz = oracle.fr_binop("sub", np.zeros_like(cz), oabc[2])
+    tables = np.stack([oabc[0], oabc[1], ncz] + [eq[i] for i in range(log_n)])
+    eq_idx = list(range(3, 3 + log_n))
+    lit = oracle.sumcheck_prove(tables, [[0, 1] + eq_idx, [2] + eq_idx], chal)
+    vm = None
+    for j in range(log_n):
+        st, evals = P.prove_first_sumcheck_round(st, vm)
+        assert np.array_equal(evals, lit[j]), j
+        vm = chal[j]
+    st, m4 = P.prove_fourth_round(st, vm)
+    for k, name in enumerate(("va", "vb", "vc")):
+        assert np.array_equal(m4[name], oracle.mle_eval(oabc[k], chal))
+    r_abc = oracle.fr_rand(4, 3)
+    st, m5 = P.prove_fifth_round(st, r_abc[0], r_abc[1], r_abc[2])
+    assert m5["index_info"] == (2, log_n)
+    tabs = []
+    for k in range(3):
+        tabs.append(oracle.fr_binop("mul", ocs.eval_on_x(k, chal), np.repeat(r_abc[k:k + 1], 1 << log_n, axis=0)))
+    tables2 = np.stack(tabs + [z])
+    chal2 = oracle.fr_rand(5, log_n)
+    lit2 = oracle.sumcheck_prove(tables2, [[0, 3], [1, 3], [2, 3]], chal2)
+    vm = None
+    for j in range(log_n):
+        st, evals = P.prove_second_sumcheck_round(st, vm)
+        assert np.array_equal(evals, lit2[j]), j
+        vm = chal2[j]
+    m6 = P.prove_sixth_round(st, vm, pp)
+    oev, oproofs = opp.open(z, chal2)
+    assert np.array_equal(m6["z_ry"], oev) and np.array_equal(m6["proof_for_z_ry"][1], oproofs)
+
+
+# ---------------------------------------------------------------- the non-interactive argument
+def _prove_both(sb, oracle, ctx, log_n, num_public, density, seed):
+    cs = sb.SyntheticR1CS(num_public, (1 << log_n) - num_public, density, seed)
+    g, h = oracle.generators()
+    t = oracle.fr_rand(seed ^ 0xABCDEF, log_n)
+    pp = sb.MLPolyCommit.keygen(log_n, g, h, t, ctx=ctx)
+    pk = sb.MLArgumentForR1CS.index(*cs.mats, ctx=ctx)
+    proof, tr = sb.MLArgumentForR1CS.prove(pk, cs.v, cs.w, pp, trace=True)
+    ocs = oracle.R1CS.from_csr(log_n, cs.mats)
+    opp = oracle.PP.keygen_with(log_n, g, h, t)
+    oproof, otr = oracle.prove(ocs, opp, cs.v, cs.w)
+    return proof, tr, oproof, otr
+
+
+@pytest.mark.parametrize("log_n,num_public,density", [(3, 4, 0), (4, 4, 0), (6, 8, 30), (8, 32, 0), (10, 32, 0), (11, 32, 127)])
+def test_prove_bytes_and_trace_match_oracle(sb, oracle, gpu_ctx, log_n, num_public, density):
+    proof, tr, oproof, otr = _prove_both(sb, oracle, gpu_ctx, log_n, num_public, density, 0x5EED0000 + log_n)
+    assert len(proof) == len(oproof)
+    # intermediates first, so that a mismatch is reported at the earliest stage
+    assert np.array_equal(tr.commitment, np.frombuffer(otr.blob("commitment"), dtype=np.uint64))
+    assert np.array_equal(tr.r_v, otr.fr("r_v"))
+    assert np.array_equal(tr.z_rv_0, otr.fr("z_rv_0")[0])
+    assert np.array_equal(tr.open1_proofs.reshape(-1), np.frombuffer(otr.blob("open1_proofs"), dtype=np.uint64))
+    assert np.array_equal(tr.tor, otr.fr("tor"))
+    assert np.array_equal(tr.az, otr.fr("az")) and np.array_equal(tr.bz, otr.fr("bz")) and np.array_equal(tr.cz, otr.fr("cz"))
+    assert np.array_equal(tr.sc1_evals.reshape(-1, 4), otr.fr("sc1_evals"))
+    assert np.array_equal(tr.r_x, otr.fr("r_x"))
+    assert np.array_equal(tr.vabc, otr.fr("vabc"))
+    assert np.array_equal(tr.r_abc, otr.fr("r_abc"))
+    assert np.array_equal(tr.sc2_evals.reshape(-1, 4), otr.fr("sc2_evals"))
+    assert np.array_equal(tr.r_y, otr.fr("r_y"))
+    assert np.array_equal(tr.z_ry, otr.fr("z_ry")[0])
+    assert np.array_equal(tr.open2_proofs.reshape(-1), np.frombuffer(otr.blob("open2_proofs"), dtype=np.uint64))
+    assert proof == oproof
+
+
+def test_prove_is_deterministic_and_handles_are_reusable(sb, oracle, gpu_ctx):
+    log_n = 7
+    cs = sb.SyntheticR1CS(32, (1 << log_n) - 32, 0, 1)
+    g, h = oracle.generators()
+    pp = sb.MLPolyCommit.keygen(log_n, g, h, oracle.fr_rand(2, log_n), ctx=gpu_ctx)
+    pk = sb.MLArgumentForR1CS.index(*cs.mats, ctx=gpu_ctx)
+    p1 = sb.MLArgumentForR1CS.prove(pk, cs.v, cs.w, pp)
+    p2 = sb.MLArgumentForR1CS.prove(pk, cs.v, cs.w, pp)
+    assert p1 == p2
+    # a different witness gives a different proof with the same handles
+    w2 = cs.w.copy(); w2[0] = oracle.fr_from_ints([12345])[0]
+    assert sb.MLArgumentForR1CS.prove(pk, cs.v, w2, pp) != p1
+
+
+def test_proof_size_formula(sb):
+    L = sb.load_library()
+    # proof sizes derived from the reference's struct layout
+    assert [L.sb_proof_size(l) for l in (8, 12, 16, 20, 24)] == [5720, 9880, 15064, 21272, 28504]
+
+
+# ---------------------------------------------------------------- error behaviour (reference: Error::InvalidArgument)
+def test_invalid_arguments(sb, oracle, gpu_ctx):
+    log_n = 4
+    cs = sb.SyntheticR1CS(4, 12, 0, 9)
+    pk = sb.MLArgumentForR1CS.index(*cs.mats, ctx=gpu_ctx)
+    g, h = oracle.generators()
+    pp = sb.MLPolyCommit.keygen(log_n, g, h, oracle.fr_rand(2, log_n), ctx=gpu_ctx)
+    with pytest.raises(sb.InvalidArgument):      # |v| + |w| != n  (prover.rs:117-119)
+        sb.MLArgumentForR1CS.prove(pk, cs.v, cs.w[:-1], pp)
+    with pytest.raises(sb.InvalidArgument):      # |v| not a power of two (prover.rs:114-116)
+        sb.MLArgumentForR1CS.prove(pk, np.concatenate([cs.v, cs.w[:1]])[:3], np.concatenate([cs.v[3:], cs.w]), pp)
+    rp, col, val = cs.mats[0]
+    bad_col = col.copy(); bad_col[0] = 1 << log_n
+    with pytest.raises(sb.InvalidArgument):      # sparse index out of bound (r1cs_reader.rs:55-62)
+        sb.MLArgumentForR1CS.index((rp, bad_col, val), cs.mats[1], cs.mats[2], ctx=gpu_ctx)
+    with pytest.raises(sb.InvalidArgument):      # not a power of two (indexer.rs:49)
+        m3 = (rp[:4].copy(), col[:int(rp[3])], val[:int(rp[3])])
+        sb.MLArgumentForR1CS.index(m3, m3, m3, ctx=gpu_ctx)
+    pp5 = sb.MLPolyCommit.keygen(5, g, h, oracle.fr_rand(3, 5), ctx=gpu_ctx)
+    with pytest.raises(sb.InvalidArgument):      # parameter size mismatch
+        sb.MLArgumentForR1CS.prove(pk, cs.v, cs.w, pp5)
+    st = sb.MLProofForR1CS.prover_init(pk, cs.v, cs.w)
+    with pytest.raises(sb.InvalidArgument):      # rounds out of order
+        sb.MLProofForR1CS.prover_third_round(st, oracle.fr_rand(1, log_n))
