@@ -41,6 +41,7 @@ typedef struct sb_ctx sb_ctx;
 typedef struct sb_index sb_index;     /* reference: IndexPK, src/ahp/indexer.rs:11-17 */
 typedef struct sb_pp sb_pp;           /* reference: PublicParameter, src/commitment/data_structures.rs:10-17 */
 typedef struct sb_prover sb_prover;   /* reference: Prover*State, src/ahp/prover.rs:25-64 */
+typedef struct sb_witness sb_witness; /* z = v || w kept in HBM between proofs (no reference counterpart) */
 
 /* One R1CS matrix in CSR form: row_ptr[n+1], col[nnz] (< n), val[nnz] (Fr).  The Rust shim flattens
  * ark_relations::r1cs::Matrix = Vec<Vec<(F, usize)>> into this (tuple layout is unspecified in Rust). */
@@ -151,8 +152,19 @@ const char* sb_phase_name(int i);          /* NULL past the last phase */
 sb_status sb_prove(sb_ctx* ctx, const sb_index* idx, const sb_pp* pp, const void* v, size_t nv_len, const void* w, size_t nw_len,
                    uint8_t* proof, size_t* len, sb_trace* trace);
 size_t sb_proof_size(uint32_t log_n);
+/* Same, with the witness already resident in HBM (bench.py's device-resident arm). */
+sb_status sb_witness_upload(sb_ctx* ctx, const sb_index* idx, const void* v, size_t nv_len, const void* w, size_t nw_len, sb_witness** out);
+void sb_witness_destroy(sb_witness* w);
+sb_status sb_prove_resident(sb_ctx* ctx, const sb_index* idx, const sb_pp* pp, const sb_witness* w, uint8_t* proof, size_t* len, sb_trace* trace);
 
 /* ---- self-test / measurement hooks ------------------------------------------------------------- */
+/* bytes this library copied host->device / device->host so far in this process */
+void sb_copy_counters(uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* per-kernel CUDA-event timing on the launching stream: enable, run, then read a JSON object
+ * {"kernel": {"launches": n, "ms": t}, ...}; the report call synchronizes and clears the records.
+ * Returns the size needed for the full report (including the terminating NUL). */
+void sb_prof_enable(int on);
+size_t sb_prof_report(char* buf, size_t cap);
 /* out = a op b elementwise on the device.  field: 0 = Fr, 1 = Fq.  op: 0 add, 1 sub, 2 mul, 3 mul (portable path) */
 sb_status sb_field_binop(sb_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
 /* integer-pipe microbenchmark: n_threads threads x 2 chains x iters Montgomery products; returns

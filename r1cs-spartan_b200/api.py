@@ -30,6 +30,7 @@ EXPORTS = [
     "sb_prover_first_sumcheck_round", "sb_prover_fourth_round", "sb_prover_fifth_round",
     "sb_prover_second_sumcheck_round", "sb_prover_sixth_round", "sb_prover_export_abc", "sb_phase_name", "sb_prove",
     "sb_proof_size", "sb_field_binop", "sb_mul_bench", "sb_kernel_bench",
+    "sb_witness_upload", "sb_witness_destroy", "sb_prove_resident", "sb_copy_counters", "sb_prof_enable", "sb_prof_report",
 ]
 
 
@@ -72,6 +73,8 @@ def load_library():
         L.sb_launch_count.restype = C.c_uint64
         L.sb_proof_size.restype = C.c_size_t
         L.sb_proof_size.argtypes = [C.c_uint32]
+        L.sb_prof_report.restype = C.c_size_t
+        L.sb_copy_counters.restype = None
         _lib = L
     return _lib
 
@@ -130,6 +133,22 @@ class Context:
     # ---- measurement hooks
     def launch_count(self):
         return int(load_library().sb_launch_count())
+
+    def copy_counters(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        load_library().sb_copy_counters(C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
+    def prof_enable(self, on=True):
+        load_library().sb_prof_enable(C.c_int(1 if on else 0))
+
+    def prof_report(self):
+        """{"kernel": {"launches": n, "ms": t}} measured with CUDA events on the launching stream."""
+        import json
+        L = load_library()
+        buf = C.create_string_buffer(1 << 16)
+        L.sb_prof_report(buf, C.c_size_t(len(buf)))
+        return json.loads(buf.value.decode() or "{}")
 
     def field_binop(self, field, op, a, b):
         words = 4 if field == "fr" else 6
@@ -406,6 +425,27 @@ class MLProofForR1CS:
         return {"z_ry": ev, "proof_for_z_ry": (pp.h_point, proofs)}
 
 
+class Witness:
+    """z = v || w uploaded once and kept in HBM (bench.py's device-resident arm)."""
+
+    def __init__(self, pk, v, w):
+        v = _fr(v); w = np.ascontiguousarray(w, dtype=np.uint64).reshape(-1, 4)
+        self.ctx, self.log_v = pk.ctx, max(v.shape[0].bit_length() - 1, 0)
+        self.h = C.c_void_p()
+        pk.ctx.check(load_library().sb_witness_upload(pk.ctx.h, pk.h, _p(v), C.c_size_t(v.shape[0]), _p(w), C.c_size_t(w.shape[0]), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            load_library().sb_witness_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ProveTrace:
     """Every intermediate the parity tests compare (see sb_trace in the C header)."""
 
@@ -439,17 +479,23 @@ class MLArgumentForR1CS:
         return MLProofForR1CS.index(matrix_a, matrix_b, matrix_c, ctx)
 
     @staticmethod
-    def prove(pk, v, w, pp, trace=False):
-        """lib.rs:58-146.  Returns the serialized Proof bytes (and a ProveTrace when trace=True)."""
+    def prove(pk, v, w, pp, trace=False, witness=None):
+        """lib.rs:58-146.  Returns the serialized Proof bytes (and a ProveTrace when trace=True).
+        witness: a Witness already resident in HBM (then v, w are ignored)."""
         L = load_library()
-        v = _fr(v); w = np.ascontiguousarray(w, dtype=np.uint64).reshape(-1, 4)
         cap = L.sb_proof_size(pk.log_n)
         buf = np.empty(cap, dtype=np.uint8)
         ln = C.c_size_t(cap)
-        tr = ProveTrace(pk.log_n, max(v.shape[0].bit_length() - 1, 0)) if trace else None
-        ts = tr.struct() if tr else None
-        st = L.sb_prove(pk.ctx.h, pk.h, pp.h, _p(v), C.c_size_t(v.shape[0]), _p(w), C.c_size_t(w.shape[0]), _p(buf), C.byref(ln),
-                        C.byref(ts) if tr else None)
+        if witness is not None:
+            tr = ProveTrace(pk.log_n, witness.log_v) if trace else None
+            ts = tr.struct() if tr else None
+            st = L.sb_prove_resident(pk.ctx.h, pk.h, pp.h, witness.h, _p(buf), C.byref(ln), C.byref(ts) if tr else None)
+        else:
+            v = _fr(v); w = np.ascontiguousarray(w, dtype=np.uint64).reshape(-1, 4)
+            tr = ProveTrace(pk.log_n, max(v.shape[0].bit_length() - 1, 0)) if trace else None
+            ts = tr.struct() if tr else None
+            st = L.sb_prove(pk.ctx.h, pk.h, pp.h, _p(v), C.c_size_t(v.shape[0]), _p(w), C.c_size_t(w.shape[0]), _p(buf), C.byref(ln),
+                            C.byref(ts) if tr else None)
         pk.ctx.check(st)
         proof = buf[:ln.value].tobytes()
         if tr:

@@ -36,14 +36,24 @@ struct SbError : std::runtime_error {
 // B200: 148 SMs.  Streaming kernels run as persistent grids of SB_SMS * k CTAs with grid-stride loops.
 constexpr int SB_SMS = 148;
 
-// Counter of kernels this library launched (bench.py reports it as gpu_launches).
+// Counter of kernels this library launched (bench.py reports it as gpu_launches), host<->device byte
+// counters, and the optional per-kernel CUDA-event profiler (sb_prof_enable / sb_prof_report).
 extern unsigned long long g_sb_launches;
-#define SB_LAUNCH(kernel, grid, block, smem, stream, ...)            \
-    do {                                                             \
-        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);  \
-        g_sb_launches++;                                             \
-        SB_CUDA(cudaGetLastError());                                 \
+extern unsigned long long g_sb_h2d_bytes, g_sb_d2h_bytes;
+extern bool g_sb_prof_on;
+void sb_prof_begin(const char* name, cudaStream_t stream);
+void sb_prof_end(cudaStream_t stream);
+#define SB_LAUNCH_NAMED(name, kernel, grid, block, smem, stream, ...)  \
+    do {                                                               \
+        if (g_sb_prof_on) sb_prof_begin(name, stream);                 \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
+        if (g_sb_prof_on) sb_prof_end(stream);                         \
+        g_sb_launches++;                                               \
+        SB_CUDA(cudaGetLastError());                                   \
     } while (0)
+#define SB_LAUNCH(kernel, grid, block, smem, stream, ...) SB_LAUNCH_NAMED(#kernel, kernel, grid, block, smem, stream, __VA_ARGS__)
+// kernel names for the two instantiations of the group templates
+#define SB_KNAME(F, base) (sizeof(F) == sizeof(Fq) ? base "<Fq>" : base "<Fq2>")
 
 // RAII device allocation on a stream-ordered pool.
 template <class T>

@@ -3,7 +3,49 @@
 // (no step of this path is a dense contraction).
 #include "kernels_fr.cuh"
 
+#include <map>
+#include <string>
+#include <vector>
+
 unsigned long long g_sb_launches = 0;
+unsigned long long g_sb_h2d_bytes = 0, g_sb_d2h_bytes = 0;
+bool g_sb_prof_on = false;
+
+// ------------------------------------------------------------------ per-kernel CUDA-event profiler
+namespace {
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+}  // namespace
+void sb_prof_begin(const char* name, cudaStream_t stream) {
+    ProfRec r{name, prof_event(), prof_event()};
+    cudaEventRecord(r.e0, stream);
+    g_prof_recs.push_back(r);
+}
+void sb_prof_end(cudaStream_t stream) { cudaEventRecord(g_prof_recs.back().e1, stream); }
+// JSON object {"kernel": {"launches": n, "ms": total}, ...}; clears the records
+std::string sb_prof_collect() {
+    std::map<std::string, std::pair<int, double>> acc;
+    for (auto& r : g_prof_recs) {
+        cudaEventSynchronize(r.e1);
+        float ms = 0; cudaEventElapsedTime(&ms, r.e0, r.e1);
+        auto& a = acc[r.name]; a.first++; a.second += ms;
+        g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1);
+    }
+    g_prof_recs.clear();
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : acc) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %d, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += buf; first = false;
+    }
+    return out + "}";
+}
 
 // ------------------------------------------------------------------ helpers
 template <class T>
@@ -244,8 +286,8 @@ static void launch_sc_round(const Fr* A, const Fr* B, const Fr* C, Fr* Ao, Fr* B
     size_t h = fold ? m_in / 4 : m_in / 2;
     int grid = grid_for(h, 256, 2);
     if (grid > ws.max_grid) grid = ws.max_grid;
-    if (fold) SB_LAUNCH((k_sc_round<KIND, true>), grid, 256, 0, stream, A, B, C, Ao, Bo, Co, E, r_dev, h, out3, ws.block_partials, ws.ticket);
-    else SB_LAUNCH((k_sc_round<KIND, false>), grid, 256, 0, stream, A, B, C, Ao, Bo, Co, E, r_dev, h, out3, ws.block_partials, ws.ticket);
+    if (fold) SB_LAUNCH_NAMED(KIND == 1 ? "k_sc_round<sc1,fold>" : "k_sc_round<sc2,fold>", (k_sc_round<KIND, true>), grid, 256, 0, stream, A, B, C, Ao, Bo, Co, E, r_dev, h, out3, ws.block_partials, ws.ticket);
+    else SB_LAUNCH_NAMED(KIND == 1 ? "k_sc_round<sc1,first>" : "k_sc_round<sc2,first>", (k_sc_round<KIND, false>), grid, 256, 0, stream, A, B, C, Ao, Bo, Co, E, r_dev, h, out3, ws.block_partials, ws.ticket);
 }
 void launch_sc1_round(const Fr* A, const Fr* B, const Fr* C, Fr* Ao, Fr* Bo, Fr* Co, const Fr* E, const Fr* r_dev,
                       size_t m_in, Fr* out3, const RoundWs& ws, cudaStream_t stream) {

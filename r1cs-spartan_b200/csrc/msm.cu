@@ -39,9 +39,9 @@ __global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict__ scala
             uint32_t code;
             if (d > B) {                       // negative digit d - 2^c, borrow one from the next window
                 uint32_t nd = (1u << c) - d; carry = 1;
-                code = nd ? (((uint32_t)w * B + nd - 1) | 0x80000000u) : CODE_NONE;
+                code = nd ? ((nd - 1) | 0x80000000u) : CODE_NONE;
             }
-            else { carry = 0; code = d ? ((uint32_t)w * B + d - 1) : CODE_NONE; }
+            else { carry = 0; code = d ? (d - 1) : CODE_NONE; }
             codes[(size_t)w * m + i] = code;
             if (code != CODE_NONE) atomicAdd(&counts[code & 0x7fffffffu], 1u);
         }
@@ -81,29 +81,62 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __restrict_
 }
 
 // ------------------------------------------------------------------ bucket accumulation
-template <class F>
-__global__ void __launch_bounds__(128) k_bucket_accum(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
-                                                      const uint32_t* __restrict__ offsets, uint32_t nkeys, XyzzPt<F>* __restrict__ buckets) {
-    uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
-    if (key >= nkeys) return;
-    uint32_t beg = offsets[key], end = offsets[key + 1];
-    XyzzPt<F> acc = XyzzPt<F>::inf();
-    for (uint32_t e = beg; e < end; e++) {
-        uint32_t ent = __ldg(&sorted[e]);
-        AffinePt<F> p = ldg_elem(&tab[ent & 0x7fffffffu]);
-        if (ent & 0x80000000u) p.y = F::neg(p.y);
-        acc = XyzzPt<F>::add_mixed(acc, p);
+// Bucket b's entries (all windows: the bases are pre-shifted) are one contiguous run of `sorted`.
+// Runs can be extremely uneven -- the top window only sees the few high bits of a 255-bit scalar, so
+// all of its digits fall into a handful of buckets -- so the work item is not a bucket but a CHUNK of at
+// most S consecutive entries of one run.  Level 1 turns chunks of base indices into partial sums (mixed
+// additions); every further level sums chunks of the previous level's partial sums, until each bucket
+// is down to one point.  Work per thread is bounded by S at every level whatever the scalars are.
+
+// chunk_start = exclusive scan of ceil(len_b / S) over the runs seg_off[b] .. seg_off[b+1]; one CTA
+__global__ void __launch_bounds__(1024) k_chunk_plan(const uint32_t* __restrict__ seg_off, uint32_t nseg, uint32_t S,
+                                                     uint32_t* __restrict__ chunk_start) {
+    __shared__ uint32_t sh[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (nseg + 1023) / 1024;
+    const uint32_t beg = tid * per, end = min(beg + per, nseg);
+    uint32_t sum = 0;
+    for (uint32_t i = beg; i < end; i++) sum += (seg_off[i + 1] - seg_off[i] + S - 1) / S;
+    sh[tid] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024; off <<= 1) {
+        uint32_t v = tid >= off ? sh[tid - off] : 0;
+        __syncthreads();
+        sh[tid] += v;
+        __syncthreads();
     }
-    st_elem(&buckets[key], acc);
+    uint32_t run = sh[tid] - sum;
+    for (uint32_t i = beg; i < end; i++) { chunk_start[i] = run; run += (seg_off[i + 1] - seg_off[i] + S - 1) / S; }
+    if (tid == 1023) chunk_start[nseg] = sh[1023];
 }
 
-template <class F>
-__global__ void __launch_bounds__(128) k_bucket_merge(const XyzzPt<F>* __restrict__ buckets, int W, uint32_t B, XyzzPt<F>* __restrict__ merged) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    XyzzPt<F> acc = ldg_elem(&buckets[b]);
-    for (int w = 1; w < W; w++) acc = XyzzPt<F>::add(acc, ldg_elem(&buckets[(size_t)w * B + b]));
-    st_elem(&merged[b], acc);
+// one thread per chunk: out[p] = sum of the chunk's elements
+template <class F, bool MIXED>
+__global__ void __launch_bounds__(128) k_seg_accum(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
+                                                   const XyzzPt<F>* __restrict__ in_pts, const uint32_t* __restrict__ seg_off,
+                                                   const uint32_t* __restrict__ chunk_start, uint32_t nseg, uint32_t S,
+                                                   XyzzPt<F>* __restrict__ out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= chunk_start[nseg]) return;
+    uint32_t lo = 0, hi = nseg;                 // last b with chunk_start[b] <= p (skips empty runs)
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&chunk_start[mid]) <= p) lo = mid; else hi = mid;
+    }
+    uint32_t beg = seg_off[lo] + (p - chunk_start[lo]) * S;
+    uint32_t end = min(beg + S, seg_off[lo + 1]);
+    XyzzPt<F> acc = XyzzPt<F>::inf();
+    for (uint32_t e = beg; e < end; e++) {
+        if (MIXED) {
+            uint32_t ent = __ldg(&sorted[e]);
+            AffinePt<F> q = ldg_elem(&tab[ent & 0x7fffffffu]);
+            if (ent & 0x80000000u) q.y = F::neg(q.y);
+            acc = XyzzPt<F>::add_mixed(acc, q);
+        } else {
+            acc = XyzzPt<F>::add(acc, ldg_elem(&in_pts[e]));
+        }
+    }
+    st_elem(&out[p], acc);
 }
 
 template <class F>
@@ -130,8 +163,8 @@ __device__ XyzzPt<F> block_tree_sum(XyzzPt<F> v, XyzzPt<F>* sh) {
 }
 // stage 1: thread t owns merged buckets [t L, (t+1) L): sum_b (b+1) M_b = running sums + (t L) * (sum of M_b)
 template <class F>
-__global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce1(const XyzzPt<F>* __restrict__ merged, uint32_t B, uint32_t L,
-                                                                XyzzPt<F>* __restrict__ block_out) {
+__global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce1(const XyzzPt<F>* __restrict__ pts, const uint32_t* __restrict__ off,
+                                                                uint32_t B, uint32_t L, XyzzPt<F>* __restrict__ block_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     XyzzPt<F>* sh = reinterpret_cast<XyzzPt<F>*>(smem_raw);
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -141,7 +174,8 @@ __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce1(const XyzzPt<F>*
         uint32_t hi = (uint32_t)min((uint64_t)B, lo + L);
         XyzzPt<F> run = XyzzPt<F>::inf(), sum = XyzzPt<F>::inf();
         for (uint32_t b = hi; b-- > (uint32_t)lo;) {
-            run = XyzzPt<F>::add(run, ldg_elem(&merged[b]));
+            uint32_t o = __ldg(&off[b]);
+            if (__ldg(&off[b + 1]) > o) run = XyzzPt<F>::add(run, ldg_elem(&pts[o]));
             sum = XyzzPt<F>::add(sum, run);
         }
         total = XyzzPt<F>::add(sum, mul_small(run, (uint32_t)lo));
@@ -215,7 +249,7 @@ template <class F>
 void batch_to_affine(const XyzzPt<F>* in_dev, AffinePt<F>* out_dev, size_t n, cudaStream_t stream) {
     if (!n) return;
     size_t threads = (n + BTA_K - 1) / BTA_K;
-    SB_LAUNCH((k_batch_to_affine<F>), (int)((threads + 127) / 128), 128, 0, stream, in_dev, out_dev, n, n, n, (size_t)0);
+    SB_LAUNCH_NAMED(SB_KNAME(F, "k_batch_to_affine"), (k_batch_to_affine<F>), (int)((threads + 127) / 128), 128, 0, stream, in_dev, out_dev, n, n, n, (size_t)0);
 }
 
 template <class F>
@@ -226,10 +260,10 @@ void msm_prepare(const AffinePt<F>* bases_dev, size_t m, MsmBases<F>& out, cudaS
     DevBuf<XyzzPt<F>> tmp((size_t)out.W * chunk, stream);
     for (size_t i0 = 0; i0 < m; i0 += chunk) {
         size_t cnt = m - i0 < chunk ? m - i0 : chunk;
-        SB_LAUNCH((k_preshift<F>), (int)((cnt + 127) / 128), 128, 0, stream, bases_dev, i0, cnt, out.c, out.W, tmp.get());
+        SB_LAUNCH_NAMED(SB_KNAME(F, "k_preshift"), (k_preshift<F>), (int)((cnt + 127) / 128), 128, 0, stream, bases_dev, i0, cnt, out.c, out.W, tmp.get());
         size_t n = (size_t)out.W * cnt;
         size_t threads = (n + BTA_K - 1) / BTA_K;
-        SB_LAUNCH((k_batch_to_affine<F>), (int)((threads + 127) / 128), 128, 0, stream, tmp.get(), out.tab.get(), n, cnt, m, i0);
+        SB_LAUNCH_NAMED(SB_KNAME(F, "k_batch_to_affine"), (k_batch_to_affine<F>), (int)((threads + 127) / 128), 128, 0, stream, tmp.get(), out.tab.get(), n, cnt, m, i0);
     }
 }
 
@@ -238,25 +272,48 @@ void msm_run(const MsmBases<F>& bases, const Fr* scalars_dev, size_t m, XyzzPt<F
     SB_REQUIRE(m == bases.m, "msm: scalar count does not match the prepared bases");
     const int c = bases.c, W = bases.W;
     const uint32_t B = 1u << (c - 1);
-    const uint32_t nkeys = (uint32_t)W * B;
-    const size_t total = (size_t)W * m;
+    const size_t total = (size_t)W * m;                       // upper bound on the number of entries
     SB_REQUIRE(total < ((size_t)1 << 31), "msm: too many (window, point) pairs for 31-bit table indices");
     DevBuf<uint32_t> codes(total, stream), sorted(total, stream);
-    DevBuf<uint32_t> counts(nkeys, stream), offsets(nkeys + 1, stream), cursors(nkeys, stream);
-    DevBuf<XyzzPt<F>> buckets(nkeys, stream), merged(B, stream);
+    DevBuf<uint32_t> counts(B, stream), offsets(B + 1, stream), cursors(B, stream);
     SB_CUDA(cudaMemsetAsync(counts.get(), 0, counts.bytes(), stream));
     SB_LAUNCH(k_msm_digits, grid_for(m, 256, 8), 256, 0, stream, scalars_dev, m, c, W, codes.get(), counts.get());
-    SB_LAUNCH(k_scan_exclusive, 1, 1024, 0, stream, counts.get(), offsets.get(), cursors.get(), nkeys);
+    SB_LAUNCH(k_scan_exclusive, 1, 1024, 0, stream, counts.get(), offsets.get(), cursors.get(), B);
     SB_LAUNCH(k_msm_scatter, grid_for(total, 256, 8), 256, 0, stream, codes.get(), total, cursors.get(), sorted.get());
-    SB_LAUNCH((k_bucket_accum<F>), (int)((nkeys + 127) / 128), 128, 0, stream, bases.tab.get(), sorted.get(), offsets.get(), nkeys, buckets.get());
-    SB_LAUNCH((k_bucket_merge<F>), (int)((B + 127) / 128), 128, 0, stream, buckets.get(), W, B, merged.get());
+    // chunked multi-level accumulation
+    const uint32_t S = total >= ((size_t)1 << 21) ? 32 : total >= ((size_t)1 << 18) ? 16 : total >= ((size_t)1 << 15) ? 8 : 4;
+    size_t bound1 = total / S + B + 1;
+    size_t bound2 = bound1 / S + B + 1;
+    DevBuf<XyzzPt<F>> ptsA(bound1, stream), ptsB(bound2, stream);
+    DevBuf<uint32_t> planA(B + 1, stream), planB(B + 1, stream);
+    const uint32_t* seg = offsets.get();
+    const XyzzPt<F>* in_pts = nullptr;
+    size_t elems = total, maxlen = total;
+    int level = 0;
+    const XyzzPt<F>* last_pts = nullptr; const uint32_t* last_plan = nullptr;
+    while (true) {
+        uint32_t* plan = (level % 2 == 0) ? planA.get() : planB.get();
+        XyzzPt<F>* outp = (level % 2 == 0) ? ptsA.get() : ptsB.get();
+        size_t items = elems / S + B + 1;
+        SB_LAUNCH(k_chunk_plan, 1, 1024, 0, stream, seg, B, S, plan);
+        if (level == 0)
+            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_mixed"), (k_seg_accum<F, true>), (int)((items + 127) / 128), 128, 0, stream,
+                            bases.tab.get(), sorted.get(), in_pts, seg, plan, B, S, outp);
+        else
+            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, false>), (int)((items + 127) / 128), 128, 0, stream,
+                            bases.tab.get(), sorted.get(), in_pts, seg, plan, B, S, outp);
+        last_pts = outp; last_plan = plan;
+        maxlen = (maxlen + S - 1) / S;
+        if (maxlen <= 1) break;
+        seg = plan; in_pts = outp; elems = items; level++;
+    }
     const uint32_t L = B >= 8 * RED_THREADS ? 8 : 1;
     const uint32_t nthreads = (B + L - 1) / L;
     const uint32_t nblocks = (nthreads + RED_THREADS - 1) / RED_THREADS;
     DevBuf<XyzzPt<F>> block_out(nblocks, stream);
     const size_t smem = RED_THREADS * sizeof(XyzzPt<F>);
-    SB_LAUNCH((k_bucket_reduce1<F>), (int)nblocks, RED_THREADS, smem, stream, merged.get(), B, L, block_out.get());
-    SB_LAUNCH((k_bucket_reduce2<F>), 1, RED_THREADS, smem, stream, block_out.get(), nblocks, out_dev);
+    SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce1"), (k_bucket_reduce1<F>), (int)nblocks, RED_THREADS, smem, stream, last_pts, last_plan, B, L, block_out.get());
+    SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce2"), (k_bucket_reduce2<F>), 1, RED_THREADS, smem, stream, block_out.get(), nblocks, out_dev);
 }
 
 // ------------------------------------------------------------------ fixed-base multiplication (keygen)
@@ -302,14 +359,14 @@ void fixed_base_mul(const AffinePt<F>& g_host, const Fr* scalars_dev, size_t n, 
     const size_t tab_n = (size_t)FB_NWIN << FB_W;
     DevBuf<XyzzPt<F>> wb(FB_NWIN, stream), tabx(tab_n, stream);
     DevBuf<AffinePt<F>> tab(tab_n, stream);
-    SB_LAUNCH((k_fb_window_bases<F>), 1, 32, 0, stream, g_host, wb.get());
-    SB_LAUNCH((k_fb_table<F>), (int)((tab_n + 127) / 128), 128, 0, stream, wb.get(), tabx.get());
+    SB_LAUNCH_NAMED(SB_KNAME(F, "k_fb_window_bases"), (k_fb_window_bases<F>), 1, 32, 0, stream, g_host, wb.get());
+    SB_LAUNCH_NAMED(SB_KNAME(F, "k_fb_table"), (k_fb_table<F>), (int)((tab_n + 127) / 128), 128, 0, stream, wb.get(), tabx.get());
     batch_to_affine<F>(tabx.get(), tab.get(), tab_n, stream);
     const size_t chunk = (size_t)1 << 22;
     DevBuf<XyzzPt<F>> tmp(n < chunk ? n : chunk, stream);
     for (size_t i0 = 0; i0 < n; i0 += chunk) {
         size_t cnt = n - i0 < chunk ? n - i0 : chunk;
-        SB_LAUNCH((k_fixed_base<F>), (int)((cnt + 127) / 128), 128, 0, stream, tab.get(), scalars_dev + i0, cnt, tmp.get());
+        SB_LAUNCH_NAMED(SB_KNAME(F, "k_fixed_base"), (k_fixed_base<F>), (int)((cnt + 127) / 128), 128, 0, stream, tab.get(), scalars_dev + i0, cnt, tmp.get());
         batch_to_affine<F>(tmp.get(), out_dev + i0, cnt, stream);
     }
 }

@@ -75,6 +75,14 @@ struct sb_pp {
     std::vector<G1Aff> g_mask;                    // vp.g_mask_random (keygen only)
 };
 
+// z = v || w resident in HBM (bench.py: the "inputs already resident" arm)
+struct sb_witness {
+    sb_ctx* ctx = nullptr;
+    size_t n = 0;
+    DevBuf<Fr> z;
+    std::vector<Fr> v_host;
+};
+
 enum ProverStage { ST_INIT, ST_R1, ST_R2, ST_R3, ST_SC1, ST_R4, ST_R5, ST_SC2, ST_DONE };
 
 struct sb_prover {
@@ -83,7 +91,8 @@ struct sb_prover {
     uint32_t log_n = 0, log_v = 0;
     size_t n = 0;
     ProverStage stage = ST_INIT;
-    DevBuf<Fr> z;
+    DevBuf<Fr> z_own;
+    const Fr* z = nullptr;    // z_own or a borrowed sb_witness table (never written)
     DevBuf<Fr> abc;           // Az | Bz | Cz (3n)
     DevBuf<Fr> pyr;           // eq suffix pyramid (n)
     DevBuf<Fr> ping, pong;    // folded tables: 3 * n/2 and 3 * n/4
@@ -105,11 +114,13 @@ static void ctx_sync(sb_ctx* c) { SB_CUDA(cudaStreamSynchronize(c->stream)); }
 static void h2d_fr(sb_ctx* c, int slot, const Fr* src, size_t count) {
     memcpy(c->h_mail.get() + slot, src, count * sizeof(Fr));
     SB_CUDA(cudaMemcpyAsync(c->d_mail.get() + slot, c->h_mail.get() + slot, count * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+    g_sb_h2d_bytes += count * sizeof(Fr);
 }
 static void d2h_fr(sb_ctx* c, int slot, Fr* dst, size_t count) {
     SB_CUDA(cudaMemcpyAsync(c->h_mail.get() + slot, c->d_mail.get() + slot, count * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
     ctx_sync(c);
     memcpy(dst, c->h_mail.get() + slot, count * sizeof(Fr));
+    g_sb_d2h_bytes += count * sizeof(Fr);
 }
 
 template <class F>
@@ -117,6 +128,7 @@ static AffinePt<F> fetch_affine(sb_ctx* c, const XyzzPt<F>* dev) {
     XyzzPt<F> h;
     SB_CUDA(cudaMemcpyAsync(&h, dev, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     ctx_sync(c);
+    g_sb_d2h_bytes += sizeof h;
     return xyzz_to_affine_host(h);
 }
 // many results at once: one D2H, one simultaneous inversion
@@ -125,6 +137,7 @@ static void fetch_affine_many(sb_ctx* c, const XyzzPt<F>* dev, size_t count, Aff
     std::vector<XyzzPt<F>> h(count);
     SB_CUDA(cudaMemcpyAsync(h.data(), dev, count * sizeof(XyzzPt<F>), cudaMemcpyDeviceToHost, c->stream));
     ctx_sync(c);
+    g_sb_d2h_bytes += count * sizeof(XyzzPt<F>);
     std::vector<F> pre(count);
     F acc = F::one();
     for (size_t i = 0; i < count; i++) { pre[i] = acc; if (!h[i].is_inf()) acc = F::mul(acc, h[i].ZZZ); }
@@ -385,10 +398,21 @@ static sb_prover* prover_init(sb_ctx* c, const sb_index* ix, const void* v, size
     std::unique_ptr<sb_prover> p(new sb_prover);
     p->ctx = c; p->idx = ix; p->log_n = ix->log_n; p->n = ix->n;
     p->log_v = 0; while (((size_t)1 << p->log_v) < nv_len) p->log_v++;
-    p->z.alloc(p->n, c->stream);
-    SB_CUDA(cudaMemcpyAsync(p->z.get(), v, nv_len * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
-    if (nw_len) SB_CUDA(cudaMemcpyAsync(p->z.get() + nv_len, w, nw_len * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+    p->z_own.alloc(p->n, c->stream);
+    SB_CUDA(cudaMemcpyAsync(p->z_own.get(), v, nv_len * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+    if (nw_len) SB_CUDA(cudaMemcpyAsync(p->z_own.get() + nv_len, w, nw_len * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+    g_sb_h2d_bytes += (nv_len + nw_len) * sizeof(Fr);
     ctx_sync(c);     // caller buffers are only borrowed for the duration of the call
+    p->z = p->z_own.get();
+    return p.release();
+}
+static sb_prover* prover_init_resident(sb_ctx* c, const sb_index* ix, const sb_witness* wt) {
+    SB_REQUIRE(wt->n == ix->n, "|v| + |w| != number of variables");
+    std::unique_ptr<sb_prover> p(new sb_prover);
+    p->ctx = c; p->idx = ix; p->log_n = ix->log_n; p->n = ix->n;
+    size_t nv_len = wt->v_host.size();
+    p->log_v = 0; while (((size_t)1 << p->log_v) < nv_len) p->log_v++;
+    p->z = wt->z.get();
     return p.release();
 }
 
@@ -402,7 +426,7 @@ static void prover_third_round(sb_prover* p, const Fr* tor) {
     p->abc.alloc(3 * n, st);
     SB_CUDA(cudaMemsetAsync(p->abc.get(), 0, 3 * n * sizeof(Fr), st));
     const SegPlan& pl = p->idx->rows;
-    launch_segsum(p->abc.get(), pl.partials.get(), pl.items.get(), pl.n_items, pl.fix.get(), pl.n_fix, pl.val.get(), pl.idx.get(), p->z.get(), st);
+    launch_segsum(p->abc.get(), pl.partials.get(), pl.items.get(), pl.n_items, pl.fix.get(), pl.n_fix, pl.val.get(), pl.idx.get(), p->z, st);
     p->ping.alloc(3 * (n / 2), st);
     p->pong.alloc(3 * std::max<size_t>(n / 4, 1), st);
     p->curA = p->abc.get(); p->curB = p->abc.get() + n; p->curC = p->abc.get() + 2 * n;
@@ -485,7 +509,7 @@ static void prover_fifth_round(sb_prover* p, const Fr* r_abc) {
     SB_CUDA(cudaMemsetAsync(p->mtab.get(), 0, n * sizeof(Fr), st));
     const SegPlan& pl = p->idx->cols;
     launch_segsum(p->mtab.get(), pl.partials.get(), pl.items.get(), pl.n_items, pl.fix.get(), pl.n_fix, pl.val.get(), pl.idx.get(), p->x3.get(), st);
-    p->curA = p->mtab.get(); p->curB = p->z.get(); p->curC = nullptr;
+    p->curA = p->mtab.get(); p->curB = p->z; p->curC = nullptr;
     p->cur_m = n; p->round = 0; p->into_ping = true;
     p->r_y.clear();
 }
@@ -757,7 +781,7 @@ sb_status sb_prover_first_round(sb_prover* p, const sb_pp* pp, void* out_commit)
     SB_REQUIRE(p && pp && out_commit, "null argument");
     SB_REQUIRE(p->stage == ST_INIT, "round called out of order");
     SB_REQUIRE(pp->nv == p->log_n, "public parameter size does not match the instance");
-    G1Aff r = commit_dev(p->ctx, pp, p->z.get());
+    G1Aff r = commit_dev(p->ctx, pp, p->z);
     memcpy(out_commit, &r, sizeof r);
     p->stage = ST_R1;
     SB_API_END
@@ -770,7 +794,7 @@ sb_status sb_prover_second_round(sb_prover* p, const sb_pp* pp, const void* r_v,
     std::vector<Fr> point(p->log_n, Fr::zero());          // r_v extended with zeros (prover.rs:152)
     if (p->log_v) memcpy(point.data(), r_v, p->log_v * sizeof(Fr));
     Fr ev; std::vector<G2Aff> pr(p->log_n);
-    open_dev(p->ctx, pp, p->z.get(), point.data(), &ev, pr.data(), p->open_r0, p->open_r1, p->open_q);
+    open_dev(p->ctx, pp, p->z, point.data(), &ev, pr.data(), p->open_r0, p->open_r1, p->open_q);
     memcpy(out_z_rv_0, &ev, sizeof ev);
     memcpy(out_proofs, pr.data(), pr.size() * sizeof(G2Aff));
     p->stage = ST_R2;
@@ -829,7 +853,7 @@ sb_status sb_prover_sixth_round(sb_prover* p, const sb_pp* pp, const void* last,
     SB_REQUIRE(pp->nv == p->log_n, "public parameter size does not match the instance");
     p->r_y.push_back(*static_cast<const Fr*>(last));
     Fr ev; std::vector<G2Aff> pr(p->log_n);
-    open_dev(p->ctx, pp, p->z.get(), p->r_y.data(), &ev, pr.data(), p->open_r0, p->open_r1, p->open_q);
+    open_dev(p->ctx, pp, p->z, p->r_y.data(), &ev, pr.data(), p->open_r0, p->open_r1, p->open_q);
     memcpy(out_z_ry, &ev, sizeof ev);
     memcpy(out_proofs, pr.data(), pr.size() * sizeof(G2Aff));
     p->stage = ST_DONE;
@@ -845,10 +869,13 @@ sb_status sb_prover_export_abc(sb_prover* p, void* az, void* bz, void* cz) {
     SB_API_END
 }
 
+}  // extern "C"
+
 // ---------------------------------------------------------------- MLArgumentForR1CS::prove (lib.rs:58-146)
-sb_status sb_prove(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const void* v, size_t nv_len, const void* w, size_t nw_len,
-                   uint8_t* proof, size_t* len, sb_trace* tr) {
-    SB_API_BEGIN(ctx)
+std::string sb_prof_collect();    // kernels_fr.cu
+
+static void prove_body(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const void* v, size_t nv_len, const void* w, size_t nw_len,
+                       const sb_witness* resident, uint8_t* proof, size_t* len, sb_trace* tr) {
     SB_REQUIRE(ctx && ix && pp && len, "null argument");
     SB_REQUIRE(pp->nv == ix->log_n, "public parameter size does not match the instance");
     const uint32_t ell = ix->log_n;
@@ -856,13 +883,14 @@ sb_status sb_prove(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const void*
     if (!proof || *len < need) { *len = need; throw SbError(SB_EINVAL, "proof buffer too small"); }
     double t_all = now_ms(), t0 = t_all;
     double ph[16] = {0};
-    std::unique_ptr<sb_prover> p(prover_init(ctx, ix, v, nv_len, w, nw_len));
+    std::unique_ptr<sb_prover> p(resident ? prover_init_resident(ctx, ix, resident) : prover_init(ctx, ix, v, nv_len, w, nw_len));
+    if (resident) { v = resident->v_host.data(); nv_len = resident->v_host.size(); }
     const Fr* vh = static_cast<const Fr*>(v);
     sbhost::Transcript fs = ix->fs_after_matrices;              // lib.rs:61-64, absorbed once at index time
     { Bytes b; sbhost::put_fr_vec(b, vh, nv_len); fs.feed(b); } // lib.rs:65
     ph[0] = now_ms() - t0; t0 = now_ms();
     // Prove 1
-    G1Aff com = commit_dev(ctx, pp, p->z.get());
+    G1Aff com = commit_dev(ctx, pp, p->z);
     Bytes pm1; sbhost::put_u64(pm1, ell); sbhost::put_g1(pm1, com);
     fs.feed(pm1);
     std::vector<Fr> r_v(p->log_v);
@@ -872,7 +900,7 @@ sb_status sb_prove(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const void*
     std::vector<Fr> point(ell, Fr::zero());
     std::copy(r_v.begin(), r_v.end(), point.begin());
     Fr z_rv_0; std::vector<G2Aff> pr1(ell);
-    open_dev(ctx, pp, p->z.get(), point.data(), &z_rv_0, pr1.data(), p->open_r0, p->open_r1, p->open_q);
+    open_dev(ctx, pp, p->z, point.data(), &z_rv_0, pr1.data(), p->open_r0, p->open_r1, p->open_q);
     Bytes pm2; sbhost::put_fr(pm2, z_rv_0); sbhost::put_g2(pm2, pp->h_host); sbhost::put_u64(pm2, ell);
     for (auto& q : pr1) sbhost::put_g2(pm2, q);
     fs.feed(pm2);
@@ -931,7 +959,7 @@ sb_status sb_prove(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const void*
     // Prove 6
     p->r_y.push_back(vm);
     Fr z_ry; std::vector<G2Aff> pr2(ell);
-    open_dev(ctx, pp, p->z.get(), p->r_y.data(), &z_ry, pr2.data(), p->open_r0, p->open_r1, p->open_q);
+    open_dev(ctx, pp, p->z, p->r_y.data(), &z_ry, pr2.data(), p->open_r0, p->open_r1, p->open_q);
     ph[8] = now_ms() - t0; t0 = now_ms();
     Bytes pm6; sbhost::put_fr(pm6, z_ry); sbhost::put_g2(pm6, pp->h_host); sbhost::put_u64(pm6, ell);
     for (auto& q : pr2) sbhost::put_g2(pm6, q);
@@ -957,8 +985,54 @@ sb_status sb_prove(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const void*
         if (tr->open1_proofs) memcpy(tr->open1_proofs, pr1.data(), ell * sizeof(G2Aff));
         if (tr->open2_proofs) memcpy(tr->open2_proofs, pr2.data(), ell * sizeof(G2Aff));
     }
+}
+
+extern "C" {
+sb_status sb_prove(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const void* v, size_t nv_len, const void* w, size_t nw_len,
+                   uint8_t* proof, size_t* len, sb_trace* tr) {
+    SB_API_BEGIN(ctx)
+    prove_body(ctx, ix, pp, v, nv_len, w, nw_len, nullptr, proof, len, tr);
     SB_API_END
 }
+sb_status sb_witness_upload(sb_ctx* ctx, const sb_index* ix, const void* v, size_t nv_len, const void* w, size_t nw_len, sb_witness** out) {
+    SB_API_BEGIN(ctx)
+    SB_REQUIRE(ctx && ix && v && out && (w || nw_len == 0), "null argument");
+    SB_REQUIRE(nv_len >= 1 && (nv_len & (nv_len - 1)) == 0, "public input should be power of two");
+    SB_REQUIRE(nv_len + nw_len == ix->n, "|v| + |w| != number of variables");
+    std::unique_ptr<sb_witness> wt(new sb_witness);
+    wt->ctx = ctx; wt->n = ix->n;
+    wt->v_host.assign(static_cast<const Fr*>(v), static_cast<const Fr*>(v) + nv_len);
+    wt->z.alloc(ix->n, ctx->stream);
+    SB_CUDA(cudaMemcpyAsync(wt->z.get(), v, nv_len * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    if (nw_len) SB_CUDA(cudaMemcpyAsync(wt->z.get() + nv_len, w, nw_len * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    ctx_sync(ctx);
+    *out = wt.release();
+    SB_API_END
+}
+void sb_witness_destroy(sb_witness* w) {
+    if (!w) return;
+    cudaSetDevice(w->ctx->device);
+    delete w;
+}
+sb_status sb_prove_resident(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const sb_witness* wt, uint8_t* proof, size_t* len, sb_trace* tr) {
+    SB_API_BEGIN(ctx)
+    SB_REQUIRE(wt, "null witness");
+    prove_body(ctx, ix, pp, nullptr, 0, nullptr, 0, wt, proof, len, tr);
+    SB_API_END
+}
+void sb_copy_counters(uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+    if (h2d_bytes) *h2d_bytes = g_sb_h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = g_sb_d2h_bytes;
+}
+void sb_prof_enable(int on) { g_sb_prof_on = on != 0; }
+size_t sb_prof_report(char* buf, size_t cap) {
+    std::string s = sb_prof_collect();
+    if (buf && cap) { size_t k = s.size() < cap - 1 ? s.size() : cap - 1; memcpy(buf, s.data(), k); buf[k] = 0; }
+    return s.size() + 1;
+}
+}  // extern "C"
+
+extern "C" {
 
 // ---------------------------------------------------------------- self-test / measurement hooks
 sb_status sb_field_binop(sb_ctx* ctx, int field, int op, const void* a, const void* b, void* outp, size_t n) {
