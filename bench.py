@@ -173,11 +173,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_log = []
+
     def timed(fn, steps):
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
+            ts = time.perf_counter()
             fn()
+            step_log.append(round(1e3 * (time.perf_counter() - ts), 3))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -186,28 +190,43 @@ def run_ours(args):
             dt = float(t.item())
         return dt
 
-    proofs = []
-    resident = lambda: proofs.append(sb.MLArgumentForR1CS.prove(pk, None, None, pp, witness=wit))
-    e2e = lambda: proofs.append(sb.MLArgumentForR1CS.prove(pk, cs.v, cs.w, pp))
+    proofs, phase_log = [], []
+
+    def resident():
+        pr, ph = sb.MLArgumentForR1CS.prove(pk, None, None, pp, witness=wit, trace="phases")
+        proofs.append(pr); phase_log.append(ph)
+
+    def e2e():
+        pr, ph = sb.MLArgumentForR1CS.prove(pk, cs.v, cs.w, pp, trace="phases")
+        proofs.append(pr); phase_log.append(ph)
     for _ in range(max(args.warmup, 3)):
         resident()
     e2e()
     # ---- timed region: K proofs with the witness resident in HBM
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("SB_NO_CLOCKS"):
         sampler.start()
-    ctx.prof_enable(True)
-    ctx.prof_report()
+    del phase_log[:]
     l0 = ctx.launch_count()
     dt = timed(resident, args.steps)
     launches = (ctx.launch_count() - l0) // args.steps
-    prof = ctx.prof_report()
-    ctx.prof_enable(False)
+    steps_resident = list(step_log); del step_log[:]
+    phases_resident = list(phase_log); del phase_log[:]
     # ---- e2e: host buffers in, proof bytes out
     h0, d0 = ctx.copy_counters()
     dt_e2e = timed(e2e, args.steps)
     h1, d1 = ctx.copy_counters()
+    steps_e2e = list(step_log); del step_log[:]
     clocks = sampler.stop() if rank == 0 else None
+    # ---- per-kernel split: the same K steps again with CUDA events around every launch and the MSMs of an
+    # opening serialised on one stream (concurrent streams would charge queueing time to the kernels)
+    ctx.set_serial_msm(True)
+    ctx.prof_enable(True)
+    ctx.prof_report()
+    dt_serial = timed(resident, args.steps)
+    prof = ctx.prof_report()
+    ctx.prof_enable(False)
+    ctx.set_serial_msm(False)
     assert all(p == proofs[0] for p in proofs), "proofs differ between steps"
     _, tr = sb.MLArgumentForR1CS.prove(pk, None, None, pp, trace=True, witness=wit)
 
@@ -270,6 +289,8 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "phases_ms": tr.phase_ms,
+        "step_ms": {"resident": steps_resident, "e2e": steps_e2e, "serialised_profiled_avg": 1e3 * dt_serial / args.steps},
+        "step_phases_ms": [{k: round(v, 2) for k, v in ph.items()} for ph in phases_resident],
         "kernels": kernels,
     }
     line.update(extra)

@@ -164,6 +164,9 @@ void sb_copy_counters(uint64_t* h2d_bytes, uint64_t* d2h_bytes);
  * {"kernel": {"launches": n, "ms": t}, ...}; the report call synchronizes and clears the records.
  * Returns the size needed for the full report (including the terminating NUL). */
 void sb_prof_enable(int on);
+/* on != 0: run the MSMs of an opening one after another on one stream (so that the per-kernel event
+ * times of sb_prof_report do not include time spent queued behind other streams); default off. */
+void sb_set_serial_msm(sb_ctx* ctx, int on);
 size_t sb_prof_report(char* buf, size_t cap);
 /* out = a op b elementwise on the device.  field: 0 = Fr, 1 = Fq.  op: 0 add, 1 sub, 2 mul, 3 mul (portable path) */
 sb_status sb_field_binop(sb_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);

@@ -31,6 +31,7 @@ EXPORTS = [
     "sb_prover_second_sumcheck_round", "sb_prover_sixth_round", "sb_prover_export_abc", "sb_phase_name", "sb_prove",
     "sb_proof_size", "sb_field_binop", "sb_mul_bench", "sb_kernel_bench",
     "sb_witness_upload", "sb_witness_destroy", "sb_prove_resident", "sb_copy_counters", "sb_prof_enable", "sb_prof_report",
+    "sb_set_serial_msm",
 ]
 
 
@@ -141,6 +142,9 @@ class Context:
 
     def prof_enable(self, on=True):
         load_library().sb_prof_enable(C.c_int(1 if on else 0))
+
+    def set_serial_msm(self, on=True):
+        load_library().sb_set_serial_msm(self.h, C.c_int(1 if on else 0))
 
     def prof_report(self):
         """{"kernel": {"launches": n, "ms": t}} measured with CUDA events on the launching stream."""
@@ -486,6 +490,19 @@ class MLArgumentForR1CS:
         cap = L.sb_proof_size(pk.log_n)
         buf = np.empty(cap, dtype=np.uint8)
         ln = C.c_size_t(cap)
+        if trace == "phases":          # per-phase wall times only, no intermediate is copied out
+            ts = TraceStruct()
+            if witness is not None:
+                st = L.sb_prove_resident(pk.ctx.h, pk.h, pp.h, witness.h, _p(buf), C.byref(ln), C.byref(ts))
+            else:
+                v = _fr(v); w = np.ascontiguousarray(w, dtype=np.uint64).reshape(-1, 4)
+                st = L.sb_prove(pk.ctx.h, pk.h, pp.h, _p(v), C.c_size_t(v.shape[0]), _p(w), C.c_size_t(w.shape[0]), _p(buf), C.byref(ln), C.byref(ts))
+            pk.ctx.check(st)
+            phases, i = {}, 0
+            while L.sb_phase_name(i):
+                phases[L.sb_phase_name(i).decode()] = ts.phase_ms[i]
+                i += 1
+            return buf[:ln.value].tobytes(), phases
         if witness is not None:
             tr = ProveTrace(pk.log_n, witness.log_v) if trace else None
             ts = tr.struct() if tr else None

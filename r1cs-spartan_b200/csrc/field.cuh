@@ -177,7 +177,14 @@ struct alignas(16) Fp {
 typedef Fp<FrParams> Fr;
 typedef Fp<FqParams> Fq;
 
-// Fq2 = Fq[u] / (u^2 + 1)
+// Fq2 = Fq[u] / (u^2 + 1).  mul/sqr are real (non-inlined) device functions: one G2 point addition is
+// ~14 of them, and with everything inlined its ~190 KB of straight-line code streams through the
+// instruction cache once per addition (ncu: `no_instruction` was the second largest stall reason).
+#if defined(__CUDACC__)
+#define SB_FQ2_FN __host__ __device__ __noinline__
+#else
+#define SB_FQ2_FN
+#endif
 struct alignas(16) Fq2 {
     Fq c0, c1;
     SB_HD static Fq2 zero() { Fq2 z; z.c0 = Fq::zero(); z.c1 = Fq::zero(); return z; }
@@ -189,12 +196,12 @@ struct alignas(16) Fq2 {
     SB_HD static Fq2 sub(const Fq2& a, const Fq2& b) { Fq2 o; o.c0 = Fq::sub(a.c0, b.c0); o.c1 = Fq::sub(a.c1, b.c1); return o; }
     SB_HD static Fq2 dbl(const Fq2& a) { return add(a, a); }
     SB_HD static Fq2 neg(const Fq2& a) { Fq2 o; o.c0 = Fq::neg(a.c0); o.c1 = Fq::neg(a.c1); return o; }
-    SB_HD static Fq2 mul(const Fq2& a, const Fq2& b) {
+    SB_FQ2_FN static Fq2 mul(const Fq2& a, const Fq2& b) {
         Fq v0 = Fq::mul(a.c0, b.c0), v1 = Fq::mul(a.c1, b.c1);
         Fq s = Fq::mul(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
         Fq2 o; o.c0 = Fq::sub(v0, v1); o.c1 = Fq::sub(Fq::sub(s, v0), v1); return o;
     }
-    SB_HD static Fq2 sqr(const Fq2& a) {
+    SB_FQ2_FN static Fq2 sqr(const Fq2& a) {
         Fq s = Fq::add(a.c0, a.c1), d = Fq::sub(a.c0, a.c1), m = Fq::mul(a.c0, a.c1);
         Fq2 o; o.c0 = Fq::mul(s, d); o.c1 = Fq::dbl(m); return o;
     }

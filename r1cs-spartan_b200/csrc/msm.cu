@@ -4,22 +4,31 @@
 #include "msm.cuh"
 
 // ------------------------------------------------------------------ window geometry
-int msm_window_bits(size_t m) {
+WinLayout msm_layout(size_t m) {
     int lg = 0;
     while (((size_t)1 << lg) < m) lg++;
     int c = lg - 3;
     if (c < 4) c = 4;
     if (c > 16) c = 16;
-    return c;
+    WinLayout L{};
+    L.c = c;
+    const int top = c - 1, rest = 255 - top;
+    const int wl = (rest + c - 1) / c;                 // lower windows
+    const int base = rest / wl, extra = rest % wl;     // widths: `extra` windows of base+1, the others base (>= c-1)
+    int s = 0;
+    for (int w = 0; w < wl; w++) { L.shift[w] = (uint16_t)s; s += base + (w < extra ? 1 : 0); }
+    L.shift[wl] = (uint16_t)s;                          // top window
+    L.shift[wl + 1] = 255;
+    L.W = wl + 1;
+    return L;
 }
 
 // ------------------------------------------------------------------ digits + counting sort
 constexpr uint32_t CODE_NONE = 0xffffffffu;
 
-__global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict__ scalars, size_t m, int c, int W,
+__global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict__ scalars, size_t m, WinLayout lay,
                                                     uint32_t* __restrict__ codes, uint32_t* __restrict__ counts) {
-    const uint32_t B = 1u << (c - 1);
-    const uint32_t mask = (1u << c) - 1;
+    const int W = lay.W;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x) {
         Fr s = ldg_elem(&scalars[i]).to_canonical();          // "into_repr" (commit.rs:20-21, open.rs:46)
         uint32_t limb[9];
@@ -28,20 +37,17 @@ __global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict__ scala
         limb[8] = 0;
         uint32_t carry = 0;
         for (int w = 0; w < W; w++) {
-            int bit = w * c;
-            uint32_t d = 0;
-            if (bit < 256) {
-                int lo = bit >> 5, sh = bit & 31;
-                uint64_t v = (uint64_t)limb[lo] | ((uint64_t)limb[lo + 1] << 32);
-                d = (uint32_t)(v >> sh) & mask;
-            }
-            d += carry;
+            const int bit = lay.shift[w], width = lay.shift[w + 1] - bit;
+            const int lo = bit >> 5, sh = bit & 31;
+            uint64_t v = (uint64_t)limb[lo] | ((uint64_t)limb[lo + 1] << 32);
+            uint32_t d = ((uint32_t)(v >> sh) & ((1u << width) - 1)) + carry;
             uint32_t code;
-            if (d > B) {                       // negative digit d - 2^c, borrow one from the next window
-                uint32_t nd = (1u << c) - d; carry = 1;
+            if (w + 1 < W && d > (1u << (width - 1))) {       // negative digit d - 2^width, borrow from the next window
+                uint32_t nd = (1u << width) - d; carry = 1;
                 code = nd ? ((nd - 1) | 0x80000000u) : CODE_NONE;
+            } else {                                           // the top window is never recoded (see WinLayout)
+                carry = 0; code = d ? (d - 1) : CODE_NONE;
             }
-            else { carry = 0; code = d ? (d - 1) : CODE_NONE; }
             codes[(size_t)w * m + i] = code;
             if (code != CODE_NONE) atomicAdd(&counts[code & 0x7fffffffu], 1u);
         }
@@ -50,15 +56,18 @@ __global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict__ scala
 
 // exclusive scan of `total` counters by one CTA; offsets[total] = grand total; cursors = copy of offsets
 __global__ void __launch_bounds__(1024) k_scan_exclusive(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
-                                                         uint32_t* __restrict__ cursors, uint32_t total) {
+                                                         uint32_t* __restrict__ cursors, uint32_t total, uint32_t* __restrict__ info) {
     __shared__ uint32_t sh[1024];
+    __shared__ uint32_t sh_max;
+    if (threadIdx.x == 0) sh_max = 0;
     const uint32_t tid = threadIdx.x;
     const uint32_t chunk = (total + 1023) / 1024;
     const uint32_t beg = tid * chunk, end = min(beg + chunk, total);
-    uint32_t sum = 0;
-    for (uint32_t i = beg; i < end; i++) sum += counts[i];
+    uint32_t sum = 0, mx = 0;
+    for (uint32_t i = beg; i < end; i++) { uint32_t cnt = counts[i]; sum += cnt; mx = max(mx, cnt); }
     sh[tid] = sum;
     __syncthreads();
+    atomicMax(&sh_max, mx);
     for (uint32_t off = 1; off < 1024; off <<= 1) {
         uint32_t v = tid >= off ? sh[tid - off] : 0;
         __syncthreads();
@@ -67,7 +76,7 @@ __global__ void __launch_bounds__(1024) k_scan_exclusive(const uint32_t* __restr
     }
     uint32_t run = sh[tid] - sum;
     for (uint32_t i = beg; i < end; i++) { offsets[i] = run; cursors[i] = run; run += counts[i]; }
-    if (tid == 1023) offsets[total] = sh[1023];
+    if (tid == 1023) { offsets[total] = sh[1023]; info[0] = sh[1023]; info[1] = sh_max; }
 }
 
 __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __restrict__ codes, size_t total, uint32_t* __restrict__ cursors,
@@ -195,14 +204,14 @@ __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce2(const XyzzPt<F>*
 
 // ------------------------------------------------------------------ base expansion / affine conversion
 template <class F>
-__global__ void __launch_bounds__(128) k_preshift(const AffinePt<F>* __restrict__ bases, size_t i0, size_t cnt, int c, int W,
+__global__ void __launch_bounds__(128) k_preshift(const AffinePt<F>* __restrict__ bases, size_t i0, size_t cnt, WinLayout lay,
                                                   XyzzPt<F>* __restrict__ tmp) {
     size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (j >= cnt) return;
     XyzzPt<F> p = XyzzPt<F>::from_affine(ldg_elem(&bases[i0 + j]));
     st_elem(&tmp[j], p);
-    for (int w = 1; w < W; w++) {
-        for (int k = 0; k < c; k++) p = XyzzPt<F>::dbl(p);
+    for (int w = 1; w < lay.W; w++) {
+        for (int k = lay.shift[w - 1]; k < lay.shift[w]; k++) p = XyzzPt<F>::dbl(p);
         st_elem(&tmp[(size_t)w * cnt + j], p);
     }
 }
@@ -254,66 +263,98 @@ void batch_to_affine(const XyzzPt<F>* in_dev, AffinePt<F>* out_dev, size_t n, cu
 
 template <class F>
 void msm_prepare(const AffinePt<F>* bases_dev, size_t m, MsmBases<F>& out, cudaStream_t stream) {
-    out.m = m; out.c = msm_window_bits(m); out.W = msm_num_windows(out.c);
-    out.tab.alloc((size_t)out.W * m, stream);
+    out.m = m; out.lay = msm_layout(m);
+    const int W = out.lay.W;
+    out.tab.alloc((size_t)W * m, stream);
     const size_t chunk = m < ((size_t)1 << 16) ? m : ((size_t)1 << 16);
-    DevBuf<XyzzPt<F>> tmp((size_t)out.W * chunk, stream);
+    DevBuf<XyzzPt<F>> tmp((size_t)W * chunk, stream);
     for (size_t i0 = 0; i0 < m; i0 += chunk) {
         size_t cnt = m - i0 < chunk ? m - i0 : chunk;
-        SB_LAUNCH_NAMED(SB_KNAME(F, "k_preshift"), (k_preshift<F>), (int)((cnt + 127) / 128), 128, 0, stream, bases_dev, i0, cnt, out.c, out.W, tmp.get());
-        size_t n = (size_t)out.W * cnt;
+        SB_LAUNCH_NAMED(SB_KNAME(F, "k_preshift"), (k_preshift<F>), (int)((cnt + 127) / 128), 128, 0, stream, bases_dev, i0, cnt, out.lay, tmp.get());
+        size_t n = (size_t)W * cnt;
         size_t threads = (n + BTA_K - 1) / BTA_K;
         SB_LAUNCH_NAMED(SB_KNAME(F, "k_batch_to_affine"), (k_batch_to_affine<F>), (int)((threads + 127) / 128), 128, 0, stream, tmp.get(), out.tab.get(), n, cnt, m, i0);
     }
 }
 
 template <class F>
-void msm_run(const MsmBases<F>& bases, const Fr* scalars_dev, size_t m, XyzzPt<F>* out_dev, cudaStream_t stream) {
+void msm_begin(MsmJob<F>& job) {
+    const MsmBases<F>& bases = *job.bases;
+    cudaStream_t stream = job.stream;
+    const size_t m = job.m;
     SB_REQUIRE(m == bases.m, "msm: scalar count does not match the prepared bases");
-    const int c = bases.c, W = bases.W;
-    const uint32_t B = 1u << (c - 1);
-    const size_t total = (size_t)W * m;                       // upper bound on the number of entries
+    const uint32_t B = 1u << (bases.lay.c - 1);
+    const size_t total = (size_t)bases.lay.W * m;             // upper bound on the number of entries
     SB_REQUIRE(total < ((size_t)1 << 31), "msm: too many (window, point) pairs for 31-bit table indices");
-    DevBuf<uint32_t> codes(total, stream), sorted(total, stream);
-    DevBuf<uint32_t> counts(B, stream), offsets(B + 1, stream), cursors(B, stream);
-    SB_CUDA(cudaMemsetAsync(counts.get(), 0, counts.bytes(), stream));
-    SB_LAUNCH(k_msm_digits, grid_for(m, 256, 8), 256, 0, stream, scalars_dev, m, c, W, codes.get(), counts.get());
-    SB_LAUNCH(k_scan_exclusive, 1, 1024, 0, stream, counts.get(), offsets.get(), cursors.get(), B);
-    SB_LAUNCH(k_msm_scatter, grid_for(total, 256, 8), 256, 0, stream, codes.get(), total, cursors.get(), sorted.get());
-    // chunked multi-level accumulation
-    const uint32_t S = total >= ((size_t)1 << 21) ? 32 : total >= ((size_t)1 << 18) ? 16 : total >= ((size_t)1 << 15) ? 8 : 4;
-    size_t bound1 = total / S + B + 1;
-    size_t bound2 = bound1 / S + B + 1;
-    DevBuf<XyzzPt<F>> ptsA(bound1, stream), ptsB(bound2, stream);
-    DevBuf<uint32_t> planA(B + 1, stream), planB(B + 1, stream);
-    const uint32_t* seg = offsets.get();
+    job.codes.alloc(total, stream); job.sorted.alloc(total, stream);
+    job.counts.alloc(B, stream); job.offsets.alloc(B + 1, stream); job.cursors.alloc(B, stream); job.info.alloc(2, stream);
+    SB_CUDA(cudaMemsetAsync(job.counts.get(), 0, job.counts.bytes(), stream));
+    SB_LAUNCH(k_msm_digits, grid_for(m, 256, 8), 256, 0, stream, job.scalars, m, bases.lay, job.codes.get(), job.counts.get());
+    SB_LAUNCH(k_scan_exclusive, 1, 1024, 0, stream, job.counts.get(), job.offsets.get(), job.cursors.get(), B, job.info.get());
+    SB_CUDA(cudaMemcpyAsync(job.info_host, job.info.get(), 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    SB_LAUNCH(k_msm_scatter, grid_for(total, 256, 8), 256, 0, stream, job.codes.get(), total, job.cursors.get(), job.sorted.get());
+}
+
+// Chunk size S and level count from the measured longest run: two levels (chunks of S, then at most S
+// partial sums per bucket) while the longest run is <= 2^12, more levels beyond (adversarial scalars).
+template <class F>
+void msm_finish(MsmJob<F>& job) {
+    const MsmBases<F>& bases = *job.bases;
+    cudaStream_t stream = job.stream;
+    const uint32_t B = 1u << (bases.lay.c - 1);
+    const size_t entries = job.info_host[0];
+    const size_t maxrun = job.info_host[1] ? job.info_host[1] : 1;
+    int levels = maxrun <= 1 ? 1 : maxrun <= (1u << 12) ? 2 : maxrun <= (1u << 18) ? 3 : 4;
+    uint32_t S = 1;
+    while (true) {                                             // smallest S with S^levels >= maxrun
+        size_t pw = 1;
+        for (int i = 0; i < levels; i++) pw *= S;
+        if (pw >= maxrun) break;
+        S++;
+    }
+    if (S < 2) S = 2;
+    const size_t bound1 = entries / S + B + 1;
+    const size_t bound2 = bound1 / S + B + 1;
+    job.ptsA.alloc(bound1, stream); job.ptsB.alloc(bound2, stream);
+    job.planA.alloc(B + 1, stream); job.planB.alloc(B + 1, stream);
+    const uint32_t* seg = job.offsets.get();
     const XyzzPt<F>* in_pts = nullptr;
-    size_t elems = total, maxlen = total;
+    size_t elems = entries, run = maxrun;
     int level = 0;
     const XyzzPt<F>* last_pts = nullptr; const uint32_t* last_plan = nullptr;
     while (true) {
-        uint32_t* plan = (level % 2 == 0) ? planA.get() : planB.get();
-        XyzzPt<F>* outp = (level % 2 == 0) ? ptsA.get() : ptsB.get();
+        uint32_t* plan = (level % 2 == 0) ? job.planA.get() : job.planB.get();
+        XyzzPt<F>* outp = (level % 2 == 0) ? job.ptsA.get() : job.ptsB.get();
         size_t items = elems / S + B + 1;
         SB_LAUNCH(k_chunk_plan, 1, 1024, 0, stream, seg, B, S, plan);
         if (level == 0)
             SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_mixed"), (k_seg_accum<F, true>), (int)((items + 127) / 128), 128, 0, stream,
-                            bases.tab.get(), sorted.get(), in_pts, seg, plan, B, S, outp);
+                            bases.tab.get(), job.sorted.get(), in_pts, seg, plan, B, S, outp);
         else
             SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, false>), (int)((items + 127) / 128), 128, 0, stream,
-                            bases.tab.get(), sorted.get(), in_pts, seg, plan, B, S, outp);
+                            bases.tab.get(), job.sorted.get(), in_pts, seg, plan, B, S, outp);
         last_pts = outp; last_plan = plan;
-        maxlen = (maxlen + S - 1) / S;
-        if (maxlen <= 1) break;
+        run = (run + S - 1) / S;
+        if (run <= 1) break;
         seg = plan; in_pts = outp; elems = items; level++;
     }
     const uint32_t L = B >= 8 * RED_THREADS ? 8 : 1;
     const uint32_t nthreads = (B + L - 1) / L;
     const uint32_t nblocks = (nthreads + RED_THREADS - 1) / RED_THREADS;
-    DevBuf<XyzzPt<F>> block_out(nblocks, stream);
+    job.block_out.alloc(nblocks, stream);
     const size_t smem = RED_THREADS * sizeof(XyzzPt<F>);
-    SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce1"), (k_bucket_reduce1<F>), (int)nblocks, RED_THREADS, smem, stream, last_pts, last_plan, B, L, block_out.get());
-    SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce2"), (k_bucket_reduce2<F>), 1, RED_THREADS, smem, stream, block_out.get(), nblocks, out_dev);
+    SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce1"), (k_bucket_reduce1<F>), (int)nblocks, RED_THREADS, smem, stream, last_pts, last_plan, B, L, job.block_out.get());
+    SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce2"), (k_bucket_reduce2<F>), 1, RED_THREADS, smem, stream, job.block_out.get(), nblocks, job.out);
+}
+
+template <class F>
+void msm_run(const MsmBases<F>& bases, const Fr* scalars_dev, size_t m, XyzzPt<F>* out_dev, cudaStream_t stream) {
+    static thread_local PinnedBuf<uint32_t> info(2);
+    MsmJob<F> job;
+    job.bases = &bases; job.scalars = scalars_dev; job.m = m; job.out = out_dev; job.stream = stream; job.info_host = info.get();
+    msm_begin(job);
+    SB_CUDA(cudaStreamSynchronize(stream));
+    msm_finish(job);
 }
 
 // ------------------------------------------------------------------ fixed-base multiplication (keygen)
@@ -373,6 +414,10 @@ void fixed_base_mul(const AffinePt<F>& g_host, const Fr* scalars_dev, size_t n, 
 
 template void msm_prepare<Fq>(const AffinePt<Fq>*, size_t, MsmBases<Fq>&, cudaStream_t);
 template void msm_prepare<Fq2>(const AffinePt<Fq2>*, size_t, MsmBases<Fq2>&, cudaStream_t);
+template void msm_begin<Fq>(MsmJob<Fq>&);
+template void msm_begin<Fq2>(MsmJob<Fq2>&);
+template void msm_finish<Fq>(MsmJob<Fq>&);
+template void msm_finish<Fq2>(MsmJob<Fq2>&);
 template void msm_run<Fq>(const MsmBases<Fq>&, const Fr*, size_t, XyzzPt<Fq>*, cudaStream_t);
 template void msm_run<Fq2>(const MsmBases<Fq2>&, const Fr*, size_t, XyzzPt<Fq2>*, cudaStream_t);
 template void fixed_base_mul<Fq>(const AffinePt<Fq>&, const Fr*, size_t, AffinePt<Fq>*, cudaStream_t);

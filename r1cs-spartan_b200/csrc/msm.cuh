@@ -14,16 +14,40 @@
 #pragma once
 #include "common.cuh"
 
+// Window layout of the 255-bit scalar: W windows, window w covers bits [shift[w], shift[w+1]).
+// Widths are c or c-1 and as even as possible, and the TOP window is c-1 bits wide: every window is
+// (nearly) fully populated, so signed digits spread evenly over the 2^(c-1) buckets, and the top
+// digit (at most 0.906 * 2^(c-1) + carry, because r < 0.906 * 2^255) needs no carry-out window.
+struct WinLayout {
+    int W;
+    int c;
+    uint16_t shift[72];
+};
+WinLayout msm_layout(size_t m);
+
 template <class F>
 struct MsmBases {
-    DevBuf<AffinePt<F>> tab;   // [W][m]: tab[w * m + i] = 2^(c w) * P_i
+    DevBuf<AffinePt<F>> tab;   // [W][m]: tab[w * m + i] = 2^(shift[w]) * P_i
     size_t m = 0;
-    int c = 0;                 // window bits
-    int W = 0;                 // number of windows (c * W >= 256)
+    WinLayout lay{};
 };
 
-int msm_window_bits(size_t m);
-inline int msm_num_windows(int c) { return 255 / c + 1; }
+// One MSM in flight: phase A (digits, counting sort, run statistics) and phase B (chunked accumulation,
+// bucket reduction) are separate so that a whole ladder of MSMs can be queued on several streams with a
+// single host synchronisation in between.
+template <class F>
+struct MsmJob {
+    const MsmBases<F>* bases = nullptr;
+    const Fr* scalars = nullptr;
+    size_t m = 0;
+    XyzzPt<F>* out = nullptr;
+    cudaStream_t stream = nullptr;
+    uint32_t* info_host = nullptr;     // pinned: [0] = number of entries, [1] = longest bucket run
+    DevBuf<uint32_t> codes, sorted, counts, offsets, cursors, info, planA, planB;
+    DevBuf<XyzzPt<F>> ptsA, ptsB, block_out;
+};
+template <class F> void msm_begin(MsmJob<F>& job);
+template <class F> void msm_finish(MsmJob<F>& job);   // job.stream must have been synchronised after msm_begin
 
 // expand affine bases (device) into their window multiples
 template <class F>

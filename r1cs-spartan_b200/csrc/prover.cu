@@ -30,6 +30,12 @@ struct sb_ctx {
     DevBuf<unsigned int> ticket;
     DevBuf<Fr> d_mail;                 // device scratch for scalars going in / results coming out
     PinnedBuf<Fr> h_mail;
+    // auxiliary streams: the ladder of G2 MSMs of one opening runs concurrently on these
+    static constexpr int NAUX = 8;
+    cudaStream_t aux[NAUX] = {};
+    cudaEvent_t ev_main = nullptr, ev_aux[NAUX] = {};
+    PinnedBuf<uint32_t> msm_info;      // 2 words per ladder level
+    bool serial_msm = false;           // profiling aid: keep every MSM on the main stream
     RoundWs ws{};
     static constexpr int MAIL = 256;
     // mailbox slots
@@ -364,6 +370,9 @@ static G1Aff commit_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev) {
 }
 
 // open.rs:19-58 with the halved MSMs: pi_i = MSM(powers_of_h[i+1], q_k), k = nv - i.
+// The fold/quotient chain runs first on the main stream (it is microseconds of work); the nv MSMs are
+// then independent and are spread over the auxiliary streams, largest first, so that the latency-bound
+// tails of the small ones hide behind the throughput-bound accumulation of the large ones.
 static void open_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev, const Fr* point_host, Fr* eval_out, G2Aff* proofs_out,
                      DevBuf<Fr>& r0, DevBuf<Fr>& r1, DevBuf<Fr>& q) {
     uint32_t nv = pp->nv;
@@ -373,18 +382,36 @@ static void open_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev, const Fr* poin
     h2d_fr(c, sb_ctx::SLOT_VEC2, point_host, nv);
     if (r0.n < n / 2) r0.alloc(n / 2, st);
     if (r1.n < std::max<size_t>(n / 4, 1)) r1.alloc(std::max<size_t>(n / 4, 1), st);
-    if (q.n < n / 2) q.alloc(n / 2, st);
+    if (q.n < n) q.alloc(n, st);                       // quotient pyramid: level with `half` entries lives at q + half
     DevBuf<G2Xyzz> res(nv, st);
     const Fr* cur = z_dev;
     for (uint32_t i = 0; i < nv; i++) {
-        uint32_t k = nv - i;
-        size_t half = (size_t)1 << (k - 1);
+        size_t half = (size_t)1 << (nv - i - 1);
         Fr* dst = (i % 2 == 0) ? r0.get() : r1.get();
-        launch_open_fold(cur, dst, q.get(), c->d_mail.get() + sb_ctx::SLOT_VEC2 + i, half, st);
-        msm_run<Fq2>(pp->g2[i + 1], q.get(), half, res.get() + i, st);
+        launch_open_fold(cur, dst, q.get() + half, c->d_mail.get() + sb_ctx::SLOT_VEC2 + i, half, st);
         cur = dst;
     }
     SB_CUDA(cudaMemcpyAsync(c->d_mail.get() + sb_ctx::SLOT_OUT, cur, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    SB_CUDA(cudaEventRecord(c->ev_main, st));
+    {
+        std::vector<MsmJob<Fq2>> jobs(nv);
+        const int na = (int)std::min<uint32_t>(nv, sb_ctx::NAUX);
+        for (int s = 0; s < na; s++) SB_CUDA(cudaStreamWaitEvent(c->aux[s], c->ev_main, 0));
+        for (uint32_t i = 0; i < nv; i++) {
+            size_t half = (size_t)1 << (nv - i - 1);
+            MsmJob<Fq2>& j = jobs[i];
+            j.bases = &pp->g2[i + 1]; j.scalars = q.get() + half; j.m = half; j.out = res.get() + i;
+            j.stream = c->serial_msm ? c->aux[0] : c->aux[i % sb_ctx::NAUX]; j.info_host = c->msm_info.get() + 2 * i;
+            msm_begin(j);
+        }
+        for (int s = 0; s < na; s++) SB_CUDA(cudaStreamSynchronize(c->aux[s]));
+        g_sb_d2h_bytes += 8 * nv;
+        for (uint32_t i = 0; i < nv; i++) msm_finish(jobs[i]);
+        for (int s = 0; s < na; s++) {
+            SB_CUDA(cudaEventRecord(c->ev_aux[s], c->aux[s]));
+            SB_CUDA(cudaStreamWaitEvent(st, c->ev_aux[s], 0));
+        }
+    }   // job buffers are released in stream order on their own streams
     fetch_affine_many<Fq2>(c, res.get(), nv, proofs_out);
     d2h_fr(c, sb_ctx::SLOT_OUT, eval_out, 1);
 }
@@ -593,6 +620,12 @@ sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
         SB_CUDA(cudaMemsetAsync(c->ticket.get(), 0, sizeof(unsigned int), c->stream));
         c->d_mail.alloc(sb_ctx::MAIL, c->stream);
         c->h_mail.alloc(sb_ctx::MAIL);
+        c->msm_info.alloc(2 * 64);
+        for (int i = 0; i < sb_ctx::NAUX; i++) {
+            SB_CUDA(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+            SB_CUDA(cudaEventCreateWithFlags(&c->ev_aux[i], cudaEventDisableTiming));
+        }
+        SB_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
         c->ws.block_partials = c->block_partials.get();
         c->ws.ticket = c->ticket.get();
         SB_CUDA(cudaStreamSynchronize(c->stream));
@@ -615,6 +648,11 @@ void sb_ctx_destroy(sb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->block_partials.release(); c->ticket.release(); c->d_mail.release(); c->h_mail.release();
     cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < sb_ctx::NAUX; i++) {
+        if (c->aux[i]) { cudaStreamSynchronize(c->aux[i]); cudaStreamDestroy(c->aux[i]); }
+        if (c->ev_aux[i]) cudaEventDestroy(c->ev_aux[i]);
+    }
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1025,6 +1063,7 @@ void sb_copy_counters(uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
     if (d2h_bytes) *d2h_bytes = g_sb_d2h_bytes;
 }
 void sb_prof_enable(int on) { g_sb_prof_on = on != 0; }
+void sb_set_serial_msm(sb_ctx* ctx, int on) { if (ctx) ctx->serial_msm = on != 0; }
 size_t sb_prof_report(char* buf, size_t cap) {
     std::string s = sb_prof_collect();
     if (buf && cap) { size_t k = s.size() < cap - 1 ? s.size() : cap - 1; memcpy(buf, s.data(), k); buf[k] = 0; }
