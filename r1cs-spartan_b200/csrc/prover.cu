@@ -23,8 +23,10 @@ struct sb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string last_error;
-    sb_comm comm{};                    // world <= 1: single GPU
-    bool sharded = false;
+    // hypercube sharding: rank/world (world = 2^glog); world == 1 is the single-GPU case
+    sb_comm comm{};
+    int rank = 0, world = 1, glog = 0;
+    bool sharded() const { return world > 1; }
     // per-round reduction workspace + mailbox
     DevBuf<Fr> block_partials;
     DevBuf<unsigned int> ticket;
@@ -44,6 +46,13 @@ struct sb_ctx {
     static constexpr int SLOT_RABC = 8;    // r_a, r_b, r_c
     static constexpr int SLOT_VEC = 16;    // tau / point vectors (<= 64 Fr)
     static constexpr int SLOT_VEC2 = 96;
+
+    // the one collective the sharded prover needs: every rank contributes `bytes` bytes
+    void allgather(const void* send, void* recv, size_t bytes) {
+        if (!sharded()) { memcpy(recv, send, bytes); return; }
+        int rc = comm.allgather(comm.user, send, recv, bytes);
+        if (rc != 0) throw SbError(SB_ECOMM, "allgather hook failed with code " + std::to_string(rc));
+    }
 };
 
 static std::string g_create_error;
@@ -58,25 +67,33 @@ struct SegPlan {
     size_t nnz = 0;
 };
 
+// Sharded contexts hold the plans of their own slice only: rows / columns [rank * nl, (rank + 1) * nl).
 struct sb_index {
     sb_ctx* ctx = nullptr;
-    uint32_t log_n = 0;
-    size_t n = 0;
-    SegPlan rows;      // segments k * n + row over [A; B; C], gathers z[col]
-    SegPlan cols;      // segments = columns, gathers X[k * n + row]
+    uint32_t log_n = 0, loc = 0;     // total variables, variables of the local slice (log_n - glog)
+    size_t n = 0, nl = 0;
+    SegPlan rows;      // segments k * nl + local row over [A; B; C], gathers z[col] (z is replicated)
+    SegPlan cols;      // segments = local column, gathers X[k * n + row] (X is replicated)
     sbhost::Transcript fs_after_matrices;   // lib.rs:61-64 absorbed once
     size_t nnz[3] = {0, 0, 0};
 };
 
+// One multilinear-commitment parameter set over `nv` variables, expanded for the MSM kernels.
+// In a sharded context `nv` is the LOCAL variable count: the slice of a PublicParameter owned by rank rho is
+// itself a PublicParameter over the low variables with generators scaled by eq(t_hi, rho) (powers[L][x] =
+// h^{eq(t[L..], x)} factors over the top bits), and `tail` is the parameter set over the top glog variables
+// that every rank keeps for the last glog levels of an opening.
 struct sb_pp {
     sb_ctx* ctx = nullptr;
-    uint32_t nv = 0;
-    MsmBases<Fq> g1;                              // powers_of_g[0]
-    std::vector<MsmBases<Fq2>> g2;                // g2[L] = powers_of_h[L] for L = 1..nv-1 (g2[0] unused), g2[nv] = {h}
-    G1Aff g_host; G2Aff h_host;
+    uint32_t nv = 0;            // variables handled by g1 / g2 below
+    uint32_t nv_total = 0;      // variables of the whole polynomial
+    MsmBases<Fq> g1;                              // powers_of_g[0] (slice)
+    std::vector<MsmBases<Fq2>> g2;                // g2[L] = powers_of_h[L] (slice) for L = 1..nv-1, g2[nv] = {last base}
+    std::unique_ptr<sb_pp> tail;
+    G1Aff g_host; G2Aff h_host;                   // the caller's generators (h goes into every opening proof)
     bool have_g = false;
-    // raw affine copies kept for export
-    std::vector<DevBuf<G1Aff>> raw_g1;            // per level (level 0 always)
+    // raw affine copies kept for export (single-GPU contexts only)
+    std::vector<DevBuf<G1Aff>> raw_g1;
     std::vector<DevBuf<G2Aff>> raw_g2;
     std::vector<G1Aff> g_mask;                    // vp.g_mask_random (keygen only)
 };
@@ -94,17 +111,20 @@ enum ProverStage { ST_INIT, ST_R1, ST_R2, ST_R3, ST_SC1, ST_R4, ST_R5, ST_SC2, S
 struct sb_prover {
     sb_ctx* ctx = nullptr;
     const sb_index* idx = nullptr;
-    uint32_t log_n = 0, log_v = 0;
-    size_t n = 0;
+    uint32_t log_n = 0, log_v = 0, loc = 0;
+    size_t n = 0, nl = 0;
     ProverStage stage = ST_INIT;
     DevBuf<Fr> z_own;
-    const Fr* z = nullptr;    // z_own or a borrowed sb_witness table (never written)
-    DevBuf<Fr> abc;           // Az | Bz | Cz (3n)
-    DevBuf<Fr> pyr;           // eq suffix pyramid (n)
-    DevBuf<Fr> ping, pong;    // folded tables: 3 * n/2 and 3 * n/4
-    DevBuf<Fr> x3;            // r_k * eq(r_x, .), 3n
-    DevBuf<Fr> mtab;          // M(y), n
+    const Fr* z = nullptr;    // full z (replicated); z_own or a borrowed sb_witness table (never written)
+    DevBuf<Fr> abc;           // local slices of Az | Bz | Cz (3 nl)
+    DevBuf<Fr> pyr;           // eq suffix pyramid over the local variables (nl), reused full-size (n) for eq(r_x, .)
+    DevBuf<Fr> ping, pong;    // folded tables: 3 * nl/2 and 3 * nl/4
+    DevBuf<Fr> x3;            // r_k * eq(r_x, .), 3n (replicated)
+    DevBuf<Fr> mtab;          // local slice of M(y), nl
     DevBuf<Fr> open_r0, open_r1, open_q;
+    // tail instance over the top glog variables (sharded only): gathered tables, pyramid, fold buffers
+    DevBuf<Fr> tail_tabs, tail_pyr, tail_ping, tail_pong;
+    bool in_tail = false;
     // sumcheck bookkeeping
     uint32_t round = 0;
     std::vector<Fr> tor, r_x, r_y;
@@ -129,21 +149,9 @@ static void d2h_fr(sb_ctx* c, int slot, Fr* dst, size_t count) {
     g_sb_d2h_bytes += count * sizeof(Fr);
 }
 
+// host: many XYZZ points -> affine with one simultaneous inversion
 template <class F>
-static AffinePt<F> fetch_affine(sb_ctx* c, const XyzzPt<F>* dev) {
-    XyzzPt<F> h;
-    SB_CUDA(cudaMemcpyAsync(&h, dev, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-    ctx_sync(c);
-    g_sb_d2h_bytes += sizeof h;
-    return xyzz_to_affine_host(h);
-}
-// many results at once: one D2H, one simultaneous inversion
-template <class F>
-static void fetch_affine_many(sb_ctx* c, const XyzzPt<F>* dev, size_t count, AffinePt<F>* out) {
-    std::vector<XyzzPt<F>> h(count);
-    SB_CUDA(cudaMemcpyAsync(h.data(), dev, count * sizeof(XyzzPt<F>), cudaMemcpyDeviceToHost, c->stream));
-    ctx_sync(c);
-    g_sb_d2h_bytes += count * sizeof(XyzzPt<F>);
+static void to_affine_many_host(const XyzzPt<F>* h, size_t count, AffinePt<F>* out) {
     std::vector<F> pre(count);
     F acc = F::one();
     for (size_t i = 0; i < count; i++) { pre[i] = acc; if (!h[i].is_inf()) acc = F::mul(acc, h[i].ZZZ); }
@@ -157,14 +165,35 @@ static void fetch_affine_many(sb_ctx* c, const XyzzPt<F>* dev, size_t count, Aff
         out[i].y = F::mul(h[i].Y, zi3);
     }
 }
+template <class F>
+static void fetch_xyzz(sb_ctx* c, const XyzzPt<F>* dev, size_t count, XyzzPt<F>* host) {
+    SB_CUDA(cudaMemcpyAsync(host, dev, count * sizeof(XyzzPt<F>), cudaMemcpyDeviceToHost, c->stream));
+    ctx_sync(c);
+    g_sb_d2h_bytes += count * sizeof(XyzzPt<F>);
+}
+template <class F>
+static AffinePt<F> fetch_affine(sb_ctx* c, const XyzzPt<F>* dev) {
+    XyzzPt<F> h; fetch_xyzz(c, dev, 1, &h);
+    return xyzz_to_affine_host(h);
+}
 
 static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// ====================================================================== index: plans + transcript prefix
-struct HostEntry { uint32_t seg; uint32_t gather; Fr val; };
+// eq_i(r) = (1 - r)(1 - tau) + r tau
+static Fr eq1(const Fr& tau, const Fr& r) {
+    Fr one = Fr::one();
+    return Fr::add(Fr::mul(Fr::sub(one, r), Fr::sub(one, tau)), Fr::mul(r, tau));
+}
+// eq(t_hi, rho) = prod_k (bit k of rho ? t_hi[k] : 1 - t_hi[k]): weight of slice rho in any eq table of t
+static Fr top_weight(const Fr* t_hi, int glog, int rho) {
+    Fr w = Fr::one();
+    for (int k = 0; k < glog; k++) w = Fr::mul(w, ((rho >> k) & 1) ? t_hi[k] : Fr::sub(Fr::one(), t_hi[k]));
+    return w;
+}
 
+// ====================================================================== index: plans + transcript prefix
 static void build_plan(sb_ctx* c, size_t nseg, const std::vector<uint64_t>& seg_ptr, const std::vector<uint32_t>& gather,
                        const std::vector<Fr>& val, SegPlan& plan) {
     size_t nnz = gather.size();
@@ -213,9 +242,12 @@ static void build_plan(sb_ctx* c, size_t nseg, const std::vector<uint64_t>& seg_
 
 static sb_index* index_create(sb_ctx* c, uint32_t log_n, const sb_csr* mats[3]) {
     SB_REQUIRE(log_n >= 1 && log_n <= 28, "log_n out of range (need 1 <= log_n <= 28)");
+    SB_REQUIRE((int)log_n > c->glog, "instance too small for this many ranks (need at least 2 rows per rank)");
     size_t n = (size_t)1 << log_n;
     std::unique_ptr<sb_index> ix(new sb_index);
     ix->ctx = c; ix->log_n = log_n; ix->n = n;
+    ix->loc = log_n - c->glog; ix->nl = n >> c->glog;
+    const size_t nl = ix->nl, lo = (size_t)c->rank * nl, hi = lo + nl;
     // validation (r1cs_reader.rs:36-70)
     for (int k = 0; k < 3; k++) {
         const sb_csr* m = mats[k];
@@ -226,7 +258,6 @@ static sb_index* index_create(sb_ctx* c, uint32_t log_n, const sb_csr* mats[3]) 
         SB_REQUIRE(ix->nnz[k] == 0 || (m->col && m->val), "null col/val");
         for (size_t e = 0; e < ix->nnz[k]; e++) SB_REQUIRE(m->col[e] < n, "sparse index out of bound");
     }
-    size_t total = ix->nnz[0] + ix->nnz[1] + ix->nnz[2];
     // transcript prefix: feed(matrix_a), feed(matrix_b), feed(matrix_c)  (lib.rs:61-64)
     {
         Bytes buf; buf.reserve(1 << 20);
@@ -243,29 +274,31 @@ static sb_index* index_create(sb_ctx* c, uint32_t log_n, const sb_csr* mats[3]) 
             ix->fs_after_matrices.feed(buf);
         }
     }
-    // row plan: segments k n + row
+    // row plan: segments k nl + (row - lo) for the rows of this rank's slice
     {
-        std::vector<uint64_t> seg_ptr(3 * n + 1);
-        std::vector<uint32_t> gather(total);
-        std::vector<Fr> val(total);
+        std::vector<uint64_t> seg_ptr(3 * nl + 1);
+        std::vector<uint32_t> gather;
+        std::vector<Fr> val;
         size_t o = 0;
         for (int k = 0; k < 3; k++) {
             const sb_csr* m = mats[k];
             const Fr* v = static_cast<const Fr*>(m->val);
-            for (size_t r = 0; r < n; r++) {
-                seg_ptr[k * n + r] = o;
-                for (uint64_t e = m->row_ptr[r]; e < m->row_ptr[r + 1]; e++) { gather[o] = m->col[e]; val[o] = v[e]; o++; }
+            for (size_t r = lo; r < hi; r++) {
+                seg_ptr[k * nl + (r - lo)] = o;
+                for (uint64_t e = m->row_ptr[r]; e < m->row_ptr[r + 1]; e++) { gather.push_back(m->col[e]); val.push_back(v[e]); o++; }
             }
         }
-        seg_ptr[3 * n] = o;
-        build_plan(c, 3 * n, seg_ptr, gather, val, ix->rows);
+        seg_ptr[3 * nl] = o;
+        build_plan(c, 3 * nl, seg_ptr, gather, val, ix->rows);
     }
-    // column plan: segment = column y, entries (k n + row, value) of all three matrices
+    // column plan: segment = column y - lo of this rank's slice, entries (k n + row, value) of all three matrices
     {
-        std::vector<uint64_t> seg_ptr(n + 1, 0);
-        for (int k = 0; k < 3; k++) for (size_t e = 0; e < ix->nnz[k]; e++) seg_ptr[mats[k]->col[e] + 1]++;
-        for (size_t y = 0; y < n; y++) seg_ptr[y + 1] += seg_ptr[y];
+        std::vector<uint64_t> seg_ptr(nl + 1, 0);
+        for (int k = 0; k < 3; k++)
+            for (size_t e = 0; e < ix->nnz[k]; e++) { size_t y = mats[k]->col[e]; if (y >= lo && y < hi) seg_ptr[y - lo + 1]++; }
+        for (size_t y = 0; y < nl; y++) seg_ptr[y + 1] += seg_ptr[y];
         std::vector<uint64_t> cur(seg_ptr.begin(), seg_ptr.end() - 1);
+        size_t total = seg_ptr[nl];
         std::vector<uint32_t> gather(total);
         std::vector<Fr> val(total);
         for (int k = 0; k < 3; k++) {
@@ -273,58 +306,79 @@ static sb_index* index_create(sb_ctx* c, uint32_t log_n, const sb_csr* mats[3]) 
             const Fr* v = static_cast<const Fr*>(m->val);
             for (size_t r = 0; r < n; r++)
                 for (uint64_t e = m->row_ptr[r]; e < m->row_ptr[r + 1]; e++) {
-                    uint64_t p = cur[m->col[e]]++;
-                    gather[p] = (uint32_t)(k * n + r); val[p] = v[e];
+                    size_t y = m->col[e];
+                    if (y < lo || y >= hi) continue;
+                    uint64_t q = cur[y - lo]++;
+                    gather[q] = (uint32_t)(k * n + r); val[q] = v[e];
                 }
         }
-        build_plan(c, n, seg_ptr, gather, val, ix->cols);
+        build_plan(c, nl, seg_ptr, gather, val, ix->cols);
     }
     return ix.release();
 }
 
 // ====================================================================== public parameters
-static void pp_prepare_from_raw(sb_ctx* c, sb_pp* pp, const G1Aff* g1_level0_dev, const std::vector<const G2Aff*>& g2_levels_dev /* index L */) {
+// expand device-resident affine levels into the MSM tables of one parameter set
+static void pp_prepare(sb_ctx* c, sb_pp* pp, const G1Aff* g1_level0_dev, const std::vector<const G2Aff*>& g2_levels_dev /* index L, 1..nv-1 */,
+                       const G2Aff& last_base) {
     uint32_t nv = pp->nv;
-    msm_prepare<Fq>(g1_level0_dev, (size_t)1 << nv, pp->g1, c->stream);
+    if (g1_level0_dev) msm_prepare<Fq>(g1_level0_dev, (size_t)1 << nv, pp->g1, c->stream);
     pp->g2.resize(nv + 1);
     for (uint32_t L = 1; L < nv; L++) msm_prepare<Fq2>(g2_levels_dev[L], (size_t)1 << (nv - L), pp->g2[L], c->stream);
     DevBuf<G2Aff> hdev(1, c->stream);
-    SB_CUDA(cudaMemcpyAsync(hdev.get(), &pp->h_host, sizeof(G2Aff), cudaMemcpyHostToDevice, c->stream));
+    SB_CUDA(cudaMemcpyAsync(hdev.get(), &last_base, sizeof(G2Aff), cudaMemcpyHostToDevice, c->stream));
     msm_prepare<Fq2>(hdev.get(), 1, pp->g2[nv], c->stream);
     ctx_sync(c);
 }
 
 static sb_pp* pp_load(sb_ctx* c, uint32_t nv, const void* g0, const void* const* hs, const void* h) {
     SB_REQUIRE(nv >= 1 && nv <= 28, "nv out of range");
+    SB_REQUIRE((int)nv > c->glog, "polynomial too small for this many ranks");
     SB_REQUIRE(g0 && hs && h, "null parameter array");
+    for (uint32_t L = 0; L < nv; L++) SB_REQUIRE(hs[L], "null powers_of_h level");
+    cudaStream_t st = c->stream;
+    const uint32_t loc = nv - c->glog;
+    const size_t rho = (size_t)c->rank;
     std::unique_ptr<sb_pp> pp(new sb_pp);
-    pp->ctx = c; pp->nv = nv;
+    pp->ctx = c; pp->nv = loc; pp->nv_total = nv;
     memcpy(&pp->h_host, h, sizeof(G2Aff));
-    size_t n = (size_t)1 << nv;
-    pp->raw_g1.resize(nv); pp->raw_g2.resize(nv);
-    pp->raw_g1[0].alloc(n, c->stream);
-    SB_CUDA(cudaMemcpyAsync(pp->raw_g1[0].get(), g0, n * sizeof(G1Aff), cudaMemcpyHostToDevice, c->stream));
-    std::vector<const G2Aff*> lv(nv, nullptr);
-    for (uint32_t L = 0; L < nv; L++) {
-        SB_REQUIRE(hs[L], "null powers_of_h level");
-        size_t sz = (size_t)1 << (nv - L);
-        pp->raw_g2[L].alloc(sz, c->stream);
-        SB_CUDA(cudaMemcpyAsync(pp->raw_g2[L].get(), hs[L], sz * sizeof(G2Aff), cudaMemcpyHostToDevice, c->stream));
+    pp->raw_g1.resize(loc); pp->raw_g2.resize(loc);
+    const size_t nl = (size_t)1 << loc;
+    pp->raw_g1[0].alloc(nl, st);
+    SB_CUDA(cudaMemcpyAsync(pp->raw_g1[0].get(), static_cast<const G1Aff*>(g0) + rho * nl, nl * sizeof(G1Aff), cudaMemcpyHostToDevice, st));
+    std::vector<const G2Aff*> lv(loc, nullptr);
+    for (uint32_t L = (c->sharded() ? 1 : 0); L < loc; L++) {
+        size_t sz = (size_t)1 << (loc - L);                    // slice of the global level L (global size 2^(nv-L))
+        pp->raw_g2[L].alloc(sz, st);
+        SB_CUDA(cudaMemcpyAsync(pp->raw_g2[L].get(), static_cast<const G2Aff*>(hs[L]) + rho * sz, sz * sizeof(G2Aff), cudaMemcpyHostToDevice, st));
         lv[L] = pp->raw_g2[L].get();
     }
-    pp_prepare_from_raw(c, pp.get(), pp->raw_g1[0].get(), lv);
+    // last local base: the rank's single element of global level `loc` (= h itself on one GPU)
+    G2Aff last = c->sharded() ? static_cast<const G2Aff*>(hs[loc])[rho] : pp->h_host;
+    pp_prepare(c, pp.get(), pp->raw_g1[0].get(), lv, last);
+    if (c->sharded()) {
+        const uint32_t g = (uint32_t)c->glog;
+        std::unique_ptr<sb_pp> tail(new sb_pp);
+        tail->ctx = c; tail->nv = g; tail->nv_total = g; tail->h_host = pp->h_host;
+        std::vector<DevBuf<G2Aff>> tmp(g);
+        std::vector<const G2Aff*> tl(g, nullptr);
+        for (uint32_t L = 1; L < g; L++) {
+            size_t sz = (size_t)1 << (g - L);
+            tmp[L].alloc(sz, st);
+            SB_CUDA(cudaMemcpyAsync(tmp[L].get(), hs[loc + L], sz * sizeof(G2Aff), cudaMemcpyHostToDevice, st));
+            tl[L] = tmp[L].get();
+        }
+        pp_prepare(c, tail.get(), nullptr, tl, pp->h_host);
+        pp->tail = std::move(tail);
+        for (auto& b : pp->raw_g2) b.release();
+    }
     return pp.release();
 }
 
-// setup.rs:27-105: powers_of_x[i][b] = x^{eq(t[i..], b)}; the scalars are exactly the levels of the eq
-// suffix pyramid of t (level of size 2^k covers t[nv-k..]).
-static sb_pp* pp_keygen(sb_ctx* c, uint32_t nv, const void* g, const void* h, const void* t, bool keep_all) {
-    SB_REQUIRE(nv >= 1 && nv <= 28, "nv out of range");
-    SB_REQUIRE(g && h && t, "null keygen argument");
-    std::unique_ptr<sb_pp> pp(new sb_pp);
-    pp->ctx = c; pp->nv = nv;
-    memcpy(&pp->g_host, g, sizeof(G1Aff)); memcpy(&pp->h_host, h, sizeof(G2Aff));
-    pp->have_g = true;
+// setup.rs:27-105 for one parameter set: powers_of_x[i][b] = x^{eq(t[i..], b)}; the scalars are exactly the
+// levels of the eq suffix pyramid of t (level of size 2^k covers t[nv-k..]).  `last_base` closes the ladder.
+static void pp_keygen_core(sb_ctx* c, sb_pp* pp, uint32_t nv, const G1Aff* g, const G2Aff& h, const Fr* t, bool keep_all, const G2Aff& last_base) {
+    pp->nv = nv;
     size_t n = (size_t)1 << nv;
     cudaStream_t st = c->stream;
     DevBuf<Fr> tdev(nv, st), pyr(n, st), full(n, st);
@@ -336,55 +390,99 @@ static sb_pp* pp_keygen(sb_ctx* c, uint32_t nv, const void* g, const void* h, co
     for (uint32_t L = 0; L < nv; L++) {
         size_t sz = (size_t)1 << (nv - L);
         const Fr* scal = L == 0 ? full.get() : pyr.get() + sz;
-        if (L == 0 || keep_all) {
+        if (g && (L == 0 || keep_all)) {
             pp->raw_g1[L].alloc(sz, st);
-            fixed_base_mul<Fq>(pp->g_host, scal, sz, pp->raw_g1[L].get(), st);
+            fixed_base_mul<Fq>(*g, scal, sz, pp->raw_g1[L].get(), st);
         }
         if (L >= 1 || keep_all) {
             pp->raw_g2[L].alloc(sz, st);
-            fixed_base_mul<Fq2>(pp->h_host, scal, sz, pp->raw_g2[L].get(), st);
+            fixed_base_mul<Fq2>(h, scal, sz, pp->raw_g2[L].get(), st);
             lv[L] = pp->raw_g2[L].get();
         }
     }
+    pp_prepare(c, pp, g ? pp->raw_g1[0].get() : nullptr, lv, last_base);
+    if (!keep_all) {   // the prover only ever reads the expanded tables
+        for (auto& b : pp->raw_g2) b.release();
+    }
+    ctx_sync(c);
+}
+
+static sb_pp* pp_keygen(sb_ctx* c, uint32_t nv, const void* g, const void* h, const void* t, bool keep_all) {
+    SB_REQUIRE(nv >= 1 && nv <= 28, "nv out of range");
+    SB_REQUIRE((int)nv > c->glog, "polynomial too small for this many ranks");
+    SB_REQUIRE(g && h && t, "null keygen argument");
+    SB_REQUIRE(!(keep_all && c->sharded()), "keep_all_levels is only available on a single-GPU context");
+    cudaStream_t st = c->stream;
+    std::unique_ptr<sb_pp> pp(new sb_pp);
+    pp->ctx = c; pp->nv_total = nv;
+    memcpy(&pp->g_host, g, sizeof(G1Aff)); memcpy(&pp->h_host, h, sizeof(G2Aff));
+    pp->have_g = true;
+    const Fr* tv = static_cast<const Fr*>(t);
     // vp.g_mask_random = g^{t_i}
     {
-        DevBuf<G1Aff> mask(nv, st);
+        DevBuf<Fr> tdev(nv, st); DevBuf<G1Aff> mask(nv, st);
+        SB_CUDA(cudaMemcpyAsync(tdev.get(), t, nv * sizeof(Fr), cudaMemcpyHostToDevice, st));
         fixed_base_mul<Fq>(pp->g_host, tdev.get(), nv, mask.get(), st);
         pp->g_mask.resize(nv);
         SB_CUDA(cudaMemcpyAsync(pp->g_mask.data(), mask.get(), nv * sizeof(G1Aff), cudaMemcpyDeviceToHost, st));
         ctx_sync(c);
     }
-    pp_prepare_from_raw(c, pp.get(), pp->raw_g1[0].get(), lv);
-    if (!keep_all) {   // the prover only ever reads the expanded tables
-        for (auto& b : pp->raw_g2) b.release();
+    if (!c->sharded()) {
+        pp_keygen_core(c, pp.get(), nv, &pp->g_host, pp->h_host, tv, keep_all, pp->h_host);
+        return pp.release();
     }
-    ctx_sync(c);
+    // slice of rank rho = parameter set over the low variables with generators scaled by eq(t_hi, rho)
+    const uint32_t loc = nv - c->glog;
+    Fr w = top_weight(tv + loc, c->glog, c->rank);
+    G1Aff g_rho; G2Aff h_rho;
+    {
+        DevBuf<Fr> wd(1, st); DevBuf<G1Aff> g1(1, st); DevBuf<G2Aff> h1(1, st);
+        SB_CUDA(cudaMemcpyAsync(wd.get(), &w, sizeof(Fr), cudaMemcpyHostToDevice, st));
+        fixed_base_mul<Fq>(pp->g_host, wd.get(), 1, g1.get(), st);
+        fixed_base_mul<Fq2>(pp->h_host, wd.get(), 1, h1.get(), st);
+        SB_CUDA(cudaMemcpyAsync(&g_rho, g1.get(), sizeof g_rho, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaMemcpyAsync(&h_rho, h1.get(), sizeof h_rho, cudaMemcpyDeviceToHost, st));
+        ctx_sync(c);
+    }
+    pp_keygen_core(c, pp.get(), loc, &g_rho, h_rho, tv, false, h_rho);
+    std::unique_ptr<sb_pp> tail(new sb_pp);
+    tail->ctx = c; tail->nv_total = (uint32_t)c->glog; tail->h_host = pp->h_host;
+    pp_keygen_core(c, tail.get(), (uint32_t)c->glog, nullptr, pp->h_host, tv + loc, false, pp->h_host);
+    pp->tail = std::move(tail);
     return pp.release();
 }
 
 // ====================================================================== commitment ops on device tables
-static G1Aff commit_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev) {
+// commit.rs:17-29.  Sharded: every rank sums its slice, the G partial sums are exchanged and added on the host.
+static G1Aff commit_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full) {
     DevBuf<G1Xyzz> out(1, c->stream);
-    msm_run<Fq>(pp->g1, z_dev, (size_t)1 << pp->nv, out.get(), c->stream);
-    return fetch_affine<Fq>(c, out.get());
+    const size_t nl = (size_t)1 << pp->nv;
+    msm_run<Fq>(pp->g1, z_dev_full + (size_t)c->rank * nl, nl, out.get(), c->stream);
+    G1Xyzz mine; fetch_xyzz(c, out.get(), 1, &mine);
+    if (!c->sharded()) return xyzz_to_affine_host(mine);
+    std::vector<G1Xyzz> all(c->world);
+    c->allgather(&mine, all.data(), sizeof(G1Xyzz));
+    G1Xyzz acc = all[0];
+    for (int r = 1; r < c->world; r++) acc = G1Xyzz::add(acc, all[r]);
+    return xyzz_to_affine_host(acc);
 }
 
-// open.rs:19-58 with the halved MSMs: pi_i = MSM(powers_of_h[i+1], q_k), k = nv - i.
+// open.rs:19-58 with the halved MSMs on one parameter set: pi_i = MSM(g2[i+1], q_k), k = nv - i.
 // The fold/quotient chain runs first on the main stream (it is microseconds of work); the nv MSMs are
 // then independent and are spread over the auxiliary streams, largest first, so that the latency-bound
 // tails of the small ones hide behind the throughput-bound accumulation of the large ones.
-static void open_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev, const Fr* point_host, Fr* eval_out, G2Aff* proofs_out,
-                     DevBuf<Fr>& r0, DevBuf<Fr>& r1, DevBuf<Fr>& q) {
+// Leaves the nv results (XYZZ) in res_dev and the fully folded value in the mailbox slot SLOT_OUT.
+static void open_partial(sb_ctx* c, const sb_pp* pp, const Fr* table_dev, const Fr* point_host, G2Xyzz* res_dev,
+                         DevBuf<Fr>& r0, DevBuf<Fr>& r1, DevBuf<Fr>& q) {
     uint32_t nv = pp->nv;
     size_t n = (size_t)1 << nv;
     cudaStream_t st = c->stream;
     SB_REQUIRE(nv <= 64, "nv too large for the mailbox");
     h2d_fr(c, sb_ctx::SLOT_VEC2, point_host, nv);
-    if (r0.n < n / 2) r0.alloc(n / 2, st);
+    if (r0.n < std::max<size_t>(n / 2, 1)) r0.alloc(std::max<size_t>(n / 2, 1), st);
     if (r1.n < std::max<size_t>(n / 4, 1)) r1.alloc(std::max<size_t>(n / 4, 1), st);
     if (q.n < n) q.alloc(n, st);                       // quotient pyramid: level with `half` entries lives at q + half
-    DevBuf<G2Xyzz> res(nv, st);
-    const Fr* cur = z_dev;
+    const Fr* cur = table_dev;
     for (uint32_t i = 0; i < nv; i++) {
         size_t half = (size_t)1 << (nv - i - 1);
         Fr* dst = (i % 2 == 0) ? r0.get() : r1.get();
@@ -393,38 +491,80 @@ static void open_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev, const Fr* poin
     }
     SB_CUDA(cudaMemcpyAsync(c->d_mail.get() + sb_ctx::SLOT_OUT, cur, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
     SB_CUDA(cudaEventRecord(c->ev_main, st));
-    {
-        std::vector<MsmJob<Fq2>> jobs(nv);
-        const int na = (int)std::min<uint32_t>(nv, sb_ctx::NAUX);
-        for (int s = 0; s < na; s++) SB_CUDA(cudaStreamWaitEvent(c->aux[s], c->ev_main, 0));
-        for (uint32_t i = 0; i < nv; i++) {
-            size_t half = (size_t)1 << (nv - i - 1);
-            MsmJob<Fq2>& j = jobs[i];
-            j.bases = &pp->g2[i + 1]; j.scalars = q.get() + half; j.m = half; j.out = res.get() + i;
-            j.stream = c->serial_msm ? c->aux[0] : c->aux[i % sb_ctx::NAUX]; j.info_host = c->msm_info.get() + 2 * i;
-            msm_begin(j);
+    std::vector<MsmJob<Fq2>> jobs(nv);
+    const int na = (int)std::min<uint32_t>(nv, sb_ctx::NAUX);
+    for (int s = 0; s < na; s++) SB_CUDA(cudaStreamWaitEvent(c->aux[s], c->ev_main, 0));
+    for (uint32_t i = 0; i < nv; i++) {
+        size_t half = (size_t)1 << (nv - i - 1);
+        MsmJob<Fq2>& j = jobs[i];
+        j.bases = &pp->g2[i + 1]; j.scalars = q.get() + half; j.m = half; j.out = res_dev + i;
+        j.stream = c->serial_msm ? c->aux[0] : c->aux[i % sb_ctx::NAUX]; j.info_host = c->msm_info.get() + 2 * i;
+        msm_begin(j);
+    }
+    for (int s = 0; s < na; s++) SB_CUDA(cudaStreamSynchronize(c->aux[s]));
+    g_sb_d2h_bytes += 8 * nv;
+    for (uint32_t i = 0; i < nv; i++) msm_finish(jobs[i]);
+    for (int s = 0; s < na; s++) {
+        SB_CUDA(cudaEventRecord(c->ev_aux[s], c->aux[s]));
+        SB_CUDA(cudaStreamWaitEvent(st, c->ev_aux[s], 0));
+    }
+}   // job buffers are released in stream order on their own streams
+
+// Full opening of the nv_total-variable polynomial z at `point`.  Sharded: each rank opens its slice over the
+// local variables with its slice of the parameters (partial sums per level + its folded value), one allgather
+// exchanges them, the per-level partial sums are added on the host, and the gathered folded values are the
+// table of the tail opening over the top glog variables, which every rank runs redundantly.
+static void open_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full, const Fr* point_host, Fr* eval_out, G2Aff* proofs_out,
+                     DevBuf<Fr>& r0, DevBuf<Fr>& r1, DevBuf<Fr>& q) {
+    const uint32_t loc = pp->nv, total = pp->nv_total;
+    const size_t nl = (size_t)1 << loc;
+    cudaStream_t st = c->stream;
+    DevBuf<G2Xyzz> res(total, st);
+    open_partial(c, pp, z_dev_full + (size_t)c->rank * nl, point_host, res.get(), r0, r1, q);
+    std::vector<G2Xyzz> pts(total);
+    if (!c->sharded()) {
+        fetch_xyzz(c, res.get(), total, pts.data());
+        d2h_fr(c, sb_ctx::SLOT_OUT, eval_out, 1);
+    } else {
+        const int G = c->world; const uint32_t g = (uint32_t)c->glog;
+        const size_t rec = loc * sizeof(G2Xyzz) + sizeof(Fr);
+        std::vector<uint8_t> mine(rec), all(rec * G);
+        fetch_xyzz(c, res.get(), loc, reinterpret_cast<G2Xyzz*>(mine.data()));
+        Fr folded; d2h_fr(c, sb_ctx::SLOT_OUT, &folded, 1);
+        memcpy(mine.data() + loc * sizeof(G2Xyzz), &folded, sizeof(Fr));
+        c->allgather(mine.data(), all.data(), rec);
+        std::vector<Fr> tail_tab(G);
+        for (uint32_t i = 0; i < loc; i++) {
+            G2Xyzz acc = G2Xyzz::inf();
+            for (int r = 0; r < G; r++) {
+                G2Xyzz part; memcpy(&part, all.data() + r * rec + i * sizeof(G2Xyzz), sizeof part);
+                acc = G2Xyzz::add(acc, part);
+            }
+            pts[i] = acc;
         }
-        for (int s = 0; s < na; s++) SB_CUDA(cudaStreamSynchronize(c->aux[s]));
-        g_sb_d2h_bytes += 8 * nv;
-        for (uint32_t i = 0; i < nv; i++) msm_finish(jobs[i]);
-        for (int s = 0; s < na; s++) {
-            SB_CUDA(cudaEventRecord(c->ev_aux[s], c->aux[s]));
-            SB_CUDA(cudaStreamWaitEvent(st, c->ev_aux[s], 0));
-        }
-    }   // job buffers are released in stream order on their own streams
-    fetch_affine_many<Fq2>(c, res.get(), nv, proofs_out);
-    d2h_fr(c, sb_ctx::SLOT_OUT, eval_out, 1);
+        for (int r = 0; r < G; r++) memcpy(&tail_tab[r], all.data() + r * rec + loc * sizeof(G2Xyzz), sizeof(Fr));
+        DevBuf<Fr> tt(G, st), t0, t1, tq;
+        SB_CUDA(cudaMemcpyAsync(tt.get(), tail_tab.data(), G * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        g_sb_h2d_bytes += G * sizeof(Fr);
+        open_partial(c, pp->tail.get(), tt.get(), point_host + loc, res.get() + loc, t0, t1, tq);
+        fetch_xyzz(c, res.get() + loc, g, pts.data() + loc);
+        d2h_fr(c, sb_ctx::SLOT_OUT, eval_out, 1);
+    }
+    to_affine_many_host(pts.data(), total, proofs_out);
 }
 
 // ====================================================================== prover rounds
+static void prover_setup_common(sb_prover* p, sb_ctx* c, const sb_index* ix, size_t nv_len) {
+    p->ctx = c; p->idx = ix; p->log_n = ix->log_n; p->n = ix->n; p->loc = ix->loc; p->nl = ix->nl;
+    p->log_v = 0; while (((size_t)1 << p->log_v) < nv_len) p->log_v++;
+}
 static sb_prover* prover_init(sb_ctx* c, const sb_index* ix, const void* v, size_t nv_len, const void* w, size_t nw_len) {
     // prover.rs:114-119
     SB_REQUIRE(nv_len >= 1 && (nv_len & (nv_len - 1)) == 0, "public input should be power of two");
     SB_REQUIRE(nv_len + nw_len == ix->n, "|v| + |w| != number of variables");
     SB_REQUIRE(v && (w || nw_len == 0), "null witness");
     std::unique_ptr<sb_prover> p(new sb_prover);
-    p->ctx = c; p->idx = ix; p->log_n = ix->log_n; p->n = ix->n;
-    p->log_v = 0; while (((size_t)1 << p->log_v) < nv_len) p->log_v++;
+    prover_setup_common(p.get(), c, ix, nv_len);
     p->z_own.alloc(p->n, c->stream);
     SB_CUDA(cudaMemcpyAsync(p->z_own.get(), v, nv_len * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
     if (nw_len) SB_CUDA(cudaMemcpyAsync(p->z_own.get() + nv_len, w, nw_len * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
@@ -436,66 +576,118 @@ static sb_prover* prover_init(sb_ctx* c, const sb_index* ix, const void* v, size
 static sb_prover* prover_init_resident(sb_ctx* c, const sb_index* ix, const sb_witness* wt) {
     SB_REQUIRE(wt->n == ix->n, "|v| + |w| != number of variables");
     std::unique_ptr<sb_prover> p(new sb_prover);
-    p->ctx = c; p->idx = ix; p->log_n = ix->log_n; p->n = ix->n;
-    size_t nv_len = wt->v_host.size();
-    p->log_v = 0; while (((size_t)1 << p->log_v) < nv_len) p->log_v++;
+    prover_setup_common(p.get(), c, ix, wt->v_host.size());
     p->z = wt->z.get();
     return p.release();
 }
 
+// (re)start a sumcheck on the local slices
+static void sc_reset(sb_prover* p, const Fr* A, const Fr* B, const Fr* C) {
+    p->curA = A; p->curB = B; p->curC = C;
+    p->cur_m = p->nl; p->round = 0; p->into_ping = true; p->in_tail = false;
+    p->prefix = Fr::one();
+}
+
 static void prover_third_round(sb_prover* p, const Fr* tor) {
     sb_ctx* c = p->ctx; cudaStream_t st = c->stream;
-    size_t n = p->n;
+    const size_t nl = p->nl;
     p->tor.assign(tor, tor + p->log_n);
     h2d_fr(c, sb_ctx::SLOT_VEC, tor, p->log_n);
-    p->pyr.alloc(n, st);
-    launch_eq_pyramid(p->pyr.get(), c->d_mail.get() + sb_ctx::SLOT_VEC, p->log_n, st);
-    p->abc.alloc(3 * n, st);
-    SB_CUDA(cudaMemsetAsync(p->abc.get(), 0, 3 * n * sizeof(Fr), st));
+    // eq suffix pyramid over the local variables tau[0..loc); the top glog factors are the scalar top_weight
+    if (p->pyr.n < p->n) p->pyr.alloc(p->n, st);
+    launch_eq_pyramid(p->pyr.get(), c->d_mail.get() + sb_ctx::SLOT_VEC, p->loc, st);
+    if (c->sharded()) {
+        const size_t G = (size_t)c->world;
+        p->tail_pyr.alloc(G, st); p->tail_tabs.alloc(3 * G, st);
+        p->tail_ping.alloc(3 * std::max<size_t>(G / 2, 1), st); p->tail_pong.alloc(3 * std::max<size_t>(G / 4, 1), st);
+        launch_eq_pyramid(p->tail_pyr.get(), c->d_mail.get() + sb_ctx::SLOT_VEC + p->loc, (uint32_t)c->glog, st);
+    }
+    p->abc.alloc(3 * nl, st);
+    SB_CUDA(cudaMemsetAsync(p->abc.get(), 0, 3 * nl * sizeof(Fr), st));
     const SegPlan& pl = p->idx->rows;
     launch_segsum(p->abc.get(), pl.partials.get(), pl.items.get(), pl.n_items, pl.fix.get(), pl.n_fix, pl.val.get(), pl.idx.get(), p->z, st);
-    p->ping.alloc(3 * (n / 2), st);
-    p->pong.alloc(3 * std::max<size_t>(n / 4, 1), st);
-    p->curA = p->abc.get(); p->curB = p->abc.get() + n; p->curC = p->abc.get() + 2 * n;
-    p->cur_m = n; p->round = 0; p->into_ping = true;
-    p->prefix = Fr::one();
+    p->ping.alloc(3 * std::max<size_t>(nl / 2, 1), st);
+    p->pong.alloc(3 * std::max<size_t>(nl / 4, 1), st);
+    sc_reset(p, p->abc.get(), p->abc.get() + nl, p->abc.get() + 2 * nl);
     p->r_x.clear();
 }
 
-// eq_i(r) = (1 - r)(1 - tau) + r tau
-static Fr eq1(const Fr& tau, const Fr& r) {
-    Fr one = Fr::one();
-    return Fr::add(Fr::mul(Fr::sub(one, r), Fr::sub(one, tau)), Fr::mul(r, tau));
+// One sumcheck round on the device, returning the GLOBAL S_j(0), S_j(1), S_j(2).
+//   kind 1: S_j(t) = sum_b E_{>j}(b) (A_j(t,b) B_j(t,b) - C_j(t,b));  kind 2: S_j(t) = sum_b M_j(t,b) Z_j(t,b).
+// Rounds j < loc run on the local slices (sharded: the G partial triples are exchanged and combined, kind 1
+// weighting slice rho by eq(tau_hi, rho)); at j == loc the slices have one entry left per table, which are
+// gathered into the G-entry tail tables that every rank finishes redundantly.
+static void sc_round_device(sb_prover* p, int kind, const Fr* v_msg, Fr* S) {
+    sb_ctx* c = p->ctx; cudaStream_t st = c->stream;
+    const uint32_t j = p->round;
+    const Fr* r_dev = nullptr;
+    if (v_msg) { h2d_fr(c, sb_ctx::SLOT_R, v_msg, 1); r_dev = c->d_mail.get() + sb_ctx::SLOT_R; }
+    Fr* out3 = c->d_mail.get() + sb_ctx::SLOT_OUT;
+    const int ntab = kind == 1 ? 3 : 2;
+    if (c->sharded() && !p->in_tail && j == p->loc) {
+        // last local fold (2 entries -> 1 per table), then gather the slices
+        launch_final_fold3(p->curA, p->curB, p->curC, ntab, r_dev, out3, st);
+        Fr mine[3], zero = Fr::zero();
+        mine[2] = zero;
+        d2h_fr(c, sb_ctx::SLOT_OUT, mine, ntab);
+        const int G = c->world;
+        std::vector<Fr> all(3 * G), tabs(3 * G, zero);
+        c->allgather(mine, all.data(), 3 * sizeof(Fr));
+        for (int r = 0; r < G; r++) for (int k = 0; k < 3; k++) tabs[k * G + r] = all[3 * r + k];
+        SB_CUDA(cudaMemcpyAsync(p->tail_tabs.get(), tabs.data(), 3 * G * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        g_sb_h2d_bytes += 3 * G * sizeof(Fr);
+        p->in_tail = true; p->into_ping = true;
+        p->curA = p->tail_tabs.get(); p->curB = p->tail_tabs.get() + G; p->curC = kind == 1 ? p->tail_tabs.get() + 2 * G : nullptr;
+        p->cur_m = (size_t)G;
+        const Fr* E = p->tail_pyr.get() + p->cur_m / 2;
+        if (kind == 1) launch_sc1_round(p->curA, p->curB, p->curC, nullptr, nullptr, nullptr, E, nullptr, p->cur_m, out3, c->ws, st);
+        else launch_sc2_round(p->curA, p->curB, nullptr, nullptr, nullptr, p->cur_m, out3, c->ws, st);
+        ctx_sync(c);                               // tabs (host) is read by the async copy above
+        d2h_fr(c, sb_ctx::SLOT_OUT, S, 3);
+        return;
+    }
+    const Fr* pyr = p->in_tail ? p->tail_pyr.get() : p->pyr.get();
+    if (!v_msg) {
+        if (kind == 1) launch_sc1_round(p->curA, p->curB, p->curC, nullptr, nullptr, nullptr, pyr + p->cur_m / 2, nullptr, p->cur_m, out3, c->ws, st);
+        else launch_sc2_round(p->curA, p->curB, nullptr, nullptr, nullptr, p->cur_m, out3, c->ws, st);
+    } else {
+        size_t mo = p->cur_m / 2;
+        Fr* base = p->in_tail ? (p->into_ping ? p->tail_ping.get() : p->tail_pong.get()) : (p->into_ping ? p->ping.get() : p->pong.get());
+        Fr* Ao = base; Fr* Bo = base + mo; Fr* Co = base + 2 * mo;
+        // after the fold the tables have mo entries -> mo/2 pairs weighted by the pyramid level of size mo/2
+        if (kind == 1) launch_sc1_round(p->curA, p->curB, p->curC, Ao, Bo, Co, pyr + std::max<size_t>(mo / 2, 1), r_dev, p->cur_m, out3, c->ws, st);
+        else launch_sc2_round(p->curA, p->curB, Ao, Bo, r_dev, p->cur_m, out3, c->ws, st);
+        p->curA = Ao; p->curB = Bo; p->curC = kind == 1 ? Co : nullptr; p->cur_m = mo; p->into_ping = !p->into_ping;
+    }
+    d2h_fr(c, sb_ctx::SLOT_OUT, S, 3);
+    if (c->sharded() && !p->in_tail) {
+        const int G = c->world;
+        std::vector<Fr> all(3 * G);
+        c->allgather(S, all.data(), 3 * sizeof(Fr));
+        for (int t = 0; t < 3; t++) S[t] = Fr::zero();
+        for (int r = 0; r < G; r++) {
+            if (kind == 1) {
+                Fr w = top_weight(p->tor.data() + p->loc, c->glog, r);
+                for (int t = 0; t < 3; t++) S[t] = Fr::add(S[t], Fr::mul(w, all[3 * r + t]));
+            } else {
+                for (int t = 0; t < 3; t++) S[t] = Fr::add(S[t], all[3 * r + t]);
+            }
+        }
+    }
 }
 
 // One round of the first sumcheck.  Device: S_j(0), S_j(1), S_j(2) (degree 2).  Host: the reference's
 // message is P_j(t) = [prod_{i<j} eq_i(r_i)] * eq_j(t) * S_j(t) at t = 0..log_n+2.
 static void prover_sc1_round(sb_prover* p, const Fr* v_msg, Fr* out_evals) {
-    sb_ctx* c = p->ctx; cudaStream_t st = c->stream;
     uint32_t j = p->round, ell = p->log_n;
     SB_REQUIRE(j < ell, "first sumcheck already finished");
     SB_REQUIRE((j == 0) == (v_msg == nullptr), "verifier message expected from the second round on, and only then");
-    const Fr* r_dev = nullptr;
     if (v_msg) {
         p->r_x.push_back(*v_msg);
         p->prefix = Fr::mul(p->prefix, eq1(p->tor[j - 1], *v_msg));
-        h2d_fr(c, sb_ctx::SLOT_R, v_msg, 1);
-        r_dev = c->d_mail.get() + sb_ctx::SLOT_R;
-    }
-    Fr* out3 = c->d_mail.get() + sb_ctx::SLOT_OUT;
-    if (!v_msg) {
-        launch_sc1_round(p->curA, p->curB, p->curC, nullptr, nullptr, nullptr, p->pyr.get() + (p->cur_m / 2), nullptr, p->cur_m, out3, c->ws, st);
-    } else {
-        size_t mo = p->cur_m / 2;
-        Fr* base = p->into_ping ? p->ping.get() : p->pong.get();
-        Fr* Ao = base; Fr* Bo = base + mo; Fr* Co = base + 2 * mo;
-        // after the fold the tables have mo entries -> mo/2 pairs weighted by the pyramid level of size mo/2
-        const Fr* E = p->pyr.get() + std::max<size_t>(mo / 2, 1);
-        launch_sc1_round(p->curA, p->curB, p->curC, Ao, Bo, Co, E, r_dev, p->cur_m, out3, c->ws, st);
-        p->curA = Ao; p->curB = Bo; p->curC = Co; p->cur_m = mo; p->into_ping = !p->into_ping;
     }
     Fr S[3];
-    d2h_fr(c, sb_ctx::SLOT_OUT, S, 3);
+    sc_round_device(p, 1, v_msg, S);
     // extend the quadratic S by finite differences and apply the linear factor eq_j(t) and the prefix
     const Fr one = Fr::one();
     Fr tau = p->tor[j];
@@ -514,51 +706,48 @@ static void prover_sc1_round(sb_prover* p, const Fr* v_msg, Fr* out_evals) {
     p->round++;
 }
 
-static void prover_fourth_round(sb_prover* p, const Fr* last, Fr* vabc) {
+// the last fold of the (already folded) tables IS eval_at(r)  (prover.rs:217-219)
+static void sc_final_fold(sb_prover* p, const Fr* last, int ntab, Fr* out) {
     sb_ctx* c = p->ctx; cudaStream_t st = c->stream;
-    SB_REQUIRE(p->round == p->log_n && p->cur_m == 2, "first sumcheck not finished");
-    p->r_x.push_back(*last);
+    SB_REQUIRE(p->round == p->log_n, "sumcheck not finished");
     h2d_fr(c, sb_ctx::SLOT_R, last, 1);
-    // the final fold of the (already folded) tables IS eval_at(r_x)  (prover.rs:217-219)
-    launch_final_fold3(p->curA, p->curB, p->curC, 3, c->d_mail.get() + sb_ctx::SLOT_R, c->d_mail.get() + sb_ctx::SLOT_OUT, st);
-    d2h_fr(c, sb_ctx::SLOT_OUT, vabc, 3);
+    if (c->sharded() && !p->in_tail) {
+        // log_n == loc cannot happen on a sharded context (glog >= 1), so the tables are the tail tables here
+        throw SbError(SB_EINTERNAL, "sharded sumcheck ended outside the tail phase");
+    }
+    SB_REQUIRE(p->cur_m == 2, "sumcheck tables not fully folded");
+    launch_final_fold3(p->curA, p->curB, p->curC, ntab, c->d_mail.get() + sb_ctx::SLOT_R, c->d_mail.get() + sb_ctx::SLOT_OUT, st);
+    d2h_fr(c, sb_ctx::SLOT_OUT, out, ntab);
+}
+
+static void prover_fourth_round(sb_prover* p, const Fr* last, Fr* vabc) {
+    p->r_x.push_back(*last);
+    sc_final_fold(p, last, 3, vabc);
 }
 
 static void prover_fifth_round(sb_prover* p, const Fr* r_abc) {
     sb_ctx* c = p->ctx; cudaStream_t st = c->stream;
-    size_t n = p->n;
+    const size_t n = p->n, nl = p->nl;
     h2d_fr(c, sb_ctx::SLOT_VEC, p->r_x.data(), p->log_n);
     h2d_fr(c, sb_ctx::SLOT_RABC, r_abc, 3);
+    // eq(r_x, .) over ALL variables (replicated on every rank), pre-scaled by r_a, r_b, r_c
     launch_eq_pyramid(p->pyr.get(), c->d_mail.get() + sb_ctx::SLOT_VEC, p->log_n, st);
     p->x3.alloc(3 * n, st);
     launch_eq_full_scaled3(p->x3.get(), p->pyr.get(), c->d_mail.get() + sb_ctx::SLOT_VEC, c->d_mail.get() + sb_ctx::SLOT_RABC, p->log_n, st);
-    p->mtab.alloc(n, st);
-    SB_CUDA(cudaMemsetAsync(p->mtab.get(), 0, n * sizeof(Fr), st));
+    p->mtab.alloc(nl, st);
+    SB_CUDA(cudaMemsetAsync(p->mtab.get(), 0, nl * sizeof(Fr), st));
     const SegPlan& pl = p->idx->cols;
     launch_segsum(p->mtab.get(), pl.partials.get(), pl.items.get(), pl.n_items, pl.fix.get(), pl.n_fix, pl.val.get(), pl.idx.get(), p->x3.get(), st);
-    p->curA = p->mtab.get(); p->curB = p->z; p->curC = nullptr;
-    p->cur_m = n; p->round = 0; p->into_ping = true;
+    sc_reset(p, p->mtab.get(), p->z + (size_t)c->rank * nl, nullptr);
     p->r_y.clear();
 }
 
 static void prover_sc2_round(sb_prover* p, const Fr* v_msg, Fr* out3_host) {
-    sb_ctx* c = p->ctx; cudaStream_t st = c->stream;
     uint32_t j = p->round;
     SB_REQUIRE(j < p->log_n, "second sumcheck already finished");
     SB_REQUIRE((j == 0) == (v_msg == nullptr), "verifier message expected from the second round on, and only then");
-    Fr* out3 = c->d_mail.get() + sb_ctx::SLOT_OUT;
-    if (!v_msg) {
-        launch_sc2_round(p->curA, p->curB, nullptr, nullptr, nullptr, p->cur_m, out3, c->ws, st);
-    } else {
-        p->r_y.push_back(*v_msg);
-        h2d_fr(c, sb_ctx::SLOT_R, v_msg, 1);
-        size_t mo = p->cur_m / 2;
-        Fr* base = p->into_ping ? p->ping.get() : p->pong.get();
-        Fr* Mo = base; Fr* Zo = base + mo;
-        launch_sc2_round(p->curA, p->curB, Mo, Zo, c->d_mail.get() + sb_ctx::SLOT_R, p->cur_m, out3, c->ws, st);
-        p->curA = Mo; p->curB = Zo; p->cur_m = mo; p->into_ping = !p->into_ping;
-    }
-    d2h_fr(c, sb_ctx::SLOT_OUT, out3_host, 3);
+    if (v_msg) p->r_y.push_back(*v_msg);
+    sc_round_device(p, 2, v_msg, out3_host);
     p->round++;
 }
 
@@ -607,7 +796,8 @@ sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
         if (comm && comm->world > 1) {
             if (!comm->allgather || comm->rank < 0 || comm->rank >= comm->world || (comm->world & (comm->world - 1)))
                 throw SbError(SB_EINVAL, "sharded context needs an allgather hook and a power-of-two world");
-            c->comm = *comm; c->sharded = true;
+            c->comm = *comm; c->rank = comm->rank; c->world = comm->world;
+            c->glog = 0; while ((1 << c->glog) < c->world) c->glog++;
         }
         SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         cudaMemPool_t pool;
@@ -686,6 +876,7 @@ sb_status sb_pp_keygen(sb_ctx* ctx, uint32_t nv, const void* g, const void* h, c
 sb_status sb_pp_export(sb_ctx* ctx, const sb_pp* pp, int group, uint32_t level, void* outp) {
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && pp && outp && level < pp->nv && (group == 1 || group == 2), "bad export request");
+    SB_REQUIRE(!ctx->sharded(), "export is only available on a single-GPU context");
     size_t sz = (size_t)1 << (pp->nv - level);
     if (group == 1) {
         SB_REQUIRE(pp->raw_g1[level].p, "G1 level not kept (keygen with keep_all_levels)");
@@ -699,8 +890,8 @@ sb_status sb_pp_export(sb_ctx* ctx, const sb_pp* pp, int group, uint32_t level, 
 }
 sb_status sb_pp_export_g_mask(sb_ctx* ctx, const sb_pp* pp, void* outp) {
     SB_API_BEGIN(ctx)
-    SB_REQUIRE(ctx && pp && outp && pp->g_mask.size() == pp->nv, "g_mask_random only exists after sb_pp_keygen");
-    memcpy(outp, pp->g_mask.data(), pp->nv * sizeof(G1Aff));
+    SB_REQUIRE(ctx && pp && outp && pp->g_mask.size() == pp->nv_total, "g_mask_random only exists after sb_pp_keygen");
+    memcpy(outp, pp->g_mask.data(), pp->nv_total * sizeof(G1Aff));
     SB_API_END
 }
 void sb_pp_destroy(sb_pp* pp) {
@@ -712,7 +903,7 @@ void sb_pp_destroy(sb_pp* pp) {
 sb_status sb_commit(sb_ctx* ctx, const sb_pp* pp, const void* z, void* out_g1) {
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && pp && z && out_g1, "null argument");
-    size_t n = (size_t)1 << pp->nv;
+    size_t n = (size_t)1 << pp->nv_total;
     DevBuf<Fr> zd(n, ctx->stream);
     SB_CUDA(cudaMemcpyAsync(zd.get(), z, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     G1Aff r = commit_dev(ctx, pp, zd.get());
@@ -722,10 +913,10 @@ sb_status sb_commit(sb_ctx* ctx, const sb_pp* pp, const void* z, void* out_g1) {
 sb_status sb_open(sb_ctx* ctx, const sb_pp* pp, const void* z, const void* point, void* out_eval, void* out_proofs) {
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && pp && z && point && out_eval && out_proofs, "null argument");
-    size_t n = (size_t)1 << pp->nv;
+    size_t n = (size_t)1 << pp->nv_total;
     DevBuf<Fr> zd(n, ctx->stream), r0, r1, q;
     SB_CUDA(cudaMemcpyAsync(zd.get(), z, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-    Fr ev; std::vector<G2Aff> pr(pp->nv);
+    Fr ev; std::vector<G2Aff> pr(pp->nv_total);
     open_dev(ctx, pp, zd.get(), static_cast<const Fr*>(point), &ev, pr.data(), r0, r1, q);
     memcpy(out_eval, &ev, sizeof ev);
     memcpy(out_proofs, pr.data(), pr.size() * sizeof(G2Aff));
@@ -734,6 +925,7 @@ sb_status sb_open(sb_ctx* ctx, const sb_pp* pp, const void* z, const void* point
 sb_status sb_msm(sb_ctx* ctx, int group, const void* bases, const void* scalars, size_t n, void* out_affine) {
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && bases && scalars && out_affine && n >= 1 && (group == 1 || group == 2), "bad msm request");
+    SB_REQUIRE(!ctx->sharded(), "sb_msm is only available on a single-GPU context");
     cudaStream_t st = ctx->stream;
     DevBuf<Fr> sd(n, st);
     SB_CUDA(cudaMemcpyAsync(sd.get(), scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
@@ -771,6 +963,7 @@ sb_status sb_eq_table(sb_ctx* ctx, const void* t, uint32_t dim, void* outp) {
 sb_status sb_sum_over_y(sb_ctx* ctx, const sb_index* ix, const void* z, void* az, void* bz, void* cz) {
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && ix && z, "null argument");
+    SB_REQUIRE(!ctx->sharded(), "sb_sum_over_y is only available on a single-GPU context");
     size_t n = ix->n; cudaStream_t st = ctx->stream;
     DevBuf<Fr> zd(n, st), out(3 * n, st);
     SB_CUDA(cudaMemcpyAsync(zd.get(), z, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
@@ -786,6 +979,7 @@ sb_status sb_eval_on_x(sb_ctx* ctx, const sb_index* ix, const void* r_x, const v
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && ix && r_x && outp, "null argument");
     SB_REQUIRE(r_abc || (which >= 0 && which < 3), "which must be 0, 1 or 2");
+    SB_REQUIRE(!ctx->sharded(), "sb_eval_on_x is only available on a single-GPU context");
     size_t n = ix->n; cudaStream_t st = ctx->stream;
     Fr rk[3];
     if (r_abc) memcpy(rk, r_abc, sizeof rk);
@@ -818,7 +1012,7 @@ sb_status sb_prover_first_round(sb_prover* p, const sb_pp* pp, void* out_commit)
     SB_API_BEGIN(p ? p->ctx : nullptr)
     SB_REQUIRE(p && pp && out_commit, "null argument");
     SB_REQUIRE(p->stage == ST_INIT, "round called out of order");
-    SB_REQUIRE(pp->nv == p->log_n, "public parameter size does not match the instance");
+    SB_REQUIRE(pp->nv_total == p->log_n, "public parameter size does not match the instance");
     G1Aff r = commit_dev(p->ctx, pp, p->z);
     memcpy(out_commit, &r, sizeof r);
     p->stage = ST_R1;
@@ -828,7 +1022,7 @@ sb_status sb_prover_second_round(sb_prover* p, const sb_pp* pp, const void* r_v,
     SB_API_BEGIN(p ? p->ctx : nullptr)
     SB_REQUIRE(p && pp && out_z_rv_0 && out_proofs && (r_v || p->log_v == 0), "null argument");
     SB_REQUIRE(p->stage == ST_R1, "round called out of order");
-    SB_REQUIRE(pp->nv == p->log_n, "public parameter size does not match the instance");
+    SB_REQUIRE(pp->nv_total == p->log_n, "public parameter size does not match the instance");
     std::vector<Fr> point(p->log_n, Fr::zero());          // r_v extended with zeros (prover.rs:152)
     if (p->log_v) memcpy(point.data(), r_v, p->log_v * sizeof(Fr));
     Fr ev; std::vector<G2Aff> pr(p->log_n);
@@ -888,7 +1082,7 @@ sb_status sb_prover_sixth_round(sb_prover* p, const sb_pp* pp, const void* last,
     SB_API_BEGIN(p ? p->ctx : nullptr)
     SB_REQUIRE(p && pp && last && out_z_ry && out_proofs, "null argument");
     SB_REQUIRE(p->stage == ST_SC2 && p->round == p->log_n, "round called out of order");
-    SB_REQUIRE(pp->nv == p->log_n, "public parameter size does not match the instance");
+    SB_REQUIRE(pp->nv_total == p->log_n, "public parameter size does not match the instance");
     p->r_y.push_back(*static_cast<const Fr*>(last));
     Fr ev; std::vector<G2Aff> pr(p->log_n);
     open_dev(p->ctx, pp, p->z, p->r_y.data(), &ev, pr.data(), p->open_r0, p->open_r1, p->open_q);
@@ -902,7 +1096,8 @@ sb_status sb_prover_export_abc(sb_prover* p, void* az, void* bz, void* cz) {
     SB_REQUIRE(p && p->abc.p, "Az/Bz/Cz exist only after the third round");
     void* dst[3] = {az, bz, cz};
     for (int k = 0; k < 3; k++)
-        if (dst[k]) SB_CUDA(cudaMemcpyAsync(dst[k], p->abc.get() + k * p->n, p->n * sizeof(Fr), cudaMemcpyDeviceToHost, p->ctx->stream));
+        if (dst[k])      // sharded: only this rank's slice is written, at its place in the full-size output
+            SB_CUDA(cudaMemcpyAsync(static_cast<Fr*>(dst[k]) + (size_t)p->ctx->rank * p->nl, p->abc.get() + k * p->nl, p->nl * sizeof(Fr), cudaMemcpyDeviceToHost, p->ctx->stream));
     ctx_sync(p->ctx);
     SB_API_END
 }
@@ -915,7 +1110,7 @@ std::string sb_prof_collect();    // kernels_fr.cu
 static void prove_body(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const void* v, size_t nv_len, const void* w, size_t nw_len,
                        const sb_witness* resident, uint8_t* proof, size_t* len, sb_trace* tr) {
     SB_REQUIRE(ctx && ix && pp && len, "null argument");
-    SB_REQUIRE(pp->nv == ix->log_n, "public parameter size does not match the instance");
+    SB_REQUIRE(pp->nv_total == ix->log_n, "public parameter size does not match the instance");
     const uint32_t ell = ix->log_n;
     const size_t need = sb_proof_size(ell);
     if (!proof || *len < need) { *len = need; throw SbError(SB_EINVAL, "proof buffer too small"); }
@@ -950,7 +1145,8 @@ static void prove_body(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const v
     if (tr && (tr->az || tr->bz || tr->cz)) {
         void* dst[3] = {tr->az, tr->bz, tr->cz};
         for (int k = 0; k < 3; k++)
-            if (dst[k]) SB_CUDA(cudaMemcpyAsync(dst[k], p->abc.get() + k * p->n, p->n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+            if (dst[k])  // sharded: only this rank's slice is written, at its place in the full-size output
+                SB_CUDA(cudaMemcpyAsync(static_cast<Fr*>(dst[k]) + (size_t)ctx->rank * p->nl, p->abc.get() + k * p->nl, p->nl * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
         ctx_sync(ctx);
     }
     Bytes pm3; sbhost::put_u64(pm3, ell + 2); sbhost::put_u64(pm3, ell);   // IndexInfo{max_multiplicands, num_variables}
