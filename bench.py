@@ -16,6 +16,8 @@ Timing: CUDA events on the library's stream are used for the per-kernel split; t
 host wall-clock bracketed by device synchronisation (every step ends with the proof bytes on the host,
 so the device is idle at both ends), max over ranks.
 """
+import os as _os
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before any CUDA initialisation (see api.load_library)
 import argparse
 import json
 import os

@@ -168,6 +168,8 @@ void sb_prof_enable(int on);
  * times of sb_prof_report do not include time spent queued behind other streams); default off. */
 void sb_set_serial_msm(sb_ctx* ctx, int on);
 size_t sb_prof_report(char* buf, size_t cap);
+/* same records as a timeline: JSON array [[kernel, start_ms, end_ms], ...] relative to the first launch */
+size_t sb_prof_timeline(char* buf, size_t cap);
 /* out = a op b elementwise on the device.  field: 0 = Fr, 1 = Fq.  op: 0 add, 1 sub, 2 mul, 3 mul (portable path) */
 sb_status sb_field_binop(sb_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
 /* integer-pipe microbenchmark: n_threads threads x 2 chains x iters Montgomery products; returns

@@ -31,7 +31,7 @@ EXPORTS = [
     "sb_prover_second_sumcheck_round", "sb_prover_sixth_round", "sb_prover_export_abc", "sb_phase_name", "sb_prove",
     "sb_proof_size", "sb_field_binop", "sb_mul_bench", "sb_kernel_bench",
     "sb_witness_upload", "sb_witness_destroy", "sb_prove_resident", "sb_copy_counters", "sb_prof_enable", "sb_prof_report",
-    "sb_set_serial_msm",
+    "sb_set_serial_msm", "sb_prof_timeline",
 ]
 
 
@@ -67,6 +67,9 @@ def load_library():
         if not os.path.exists(LIB_PATH):
             raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
                               "There is no CPU fallback." % LIB_PATH)
+        # one hardware work queue per ladder stream (the default of 8 aliases the 20+ streams of an opening onto
+        # shared queues and serialises them); only effective if set before the CUDA context is created
+        os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
         L = C.CDLL(LIB_PATH)
         L.sb_last_error.restype = C.c_char_p
         L.sb_last_error.argtypes = [C.c_void_p]
@@ -142,6 +145,15 @@ class Context:
 
     def prof_enable(self, on=True):
         load_library().sb_prof_enable(C.c_int(1 if on else 0))
+
+    def prof_timeline(self):
+        """[[kernel, start_ms, end_ms], ...] of the launches recorded since prof_enable (CUDA events)."""
+        import json
+        L = load_library()
+        L.sb_prof_timeline.restype = C.c_size_t
+        buf = C.create_string_buffer(1 << 20)
+        L.sb_prof_timeline(buf, C.c_size_t(len(buf)))
+        return json.loads(buf.value.decode() or "[]")
 
     def set_serial_msm(self, on=True):
         load_library().sb_set_serial_msm(self.h, C.c_int(1 if on else 0))

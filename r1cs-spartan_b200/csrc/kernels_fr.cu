@@ -27,6 +27,25 @@ void sb_prof_begin(const char* name, cudaStream_t stream) {
     g_prof_recs.push_back(r);
 }
 void sb_prof_end(cudaStream_t stream) { cudaEventRecord(g_prof_recs.back().e1, stream); }
+// JSON array [[name, start_ms, end_ms], ...] relative to the first recorded launch; clears the records
+std::string sb_prof_timeline_collect() {
+    std::string out = "[";
+    if (!g_prof_recs.empty()) {
+        for (auto& r : g_prof_recs) cudaEventSynchronize(r.e1);
+        cudaEvent_t base = g_prof_recs[0].e0;
+        bool first = true;
+        for (auto& r : g_prof_recs) {
+            float t0 = 0, t1 = 0;
+            cudaEventElapsedTime(&t0, base, r.e0); cudaEventElapsedTime(&t1, base, r.e1);
+            char buf[256];
+            snprintf(buf, sizeof buf, "%s[\"%s\", %.4f, %.4f]", first ? "" : ", ", r.name, t0, t1);
+            out += buf; first = false;
+        }
+        for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1); }
+        g_prof_recs.clear();
+    }
+    return out + "]";
+}
 // JSON object {"kernel": {"launches": n, "ms": total}, ...}; clears the records
 std::string sb_prof_collect() {
     std::map<std::string, std::pair<int, double>> acc;

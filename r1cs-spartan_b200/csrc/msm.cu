@@ -54,29 +54,78 @@ __global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict__ scala
     }
 }
 
-// exclusive scan of `total` counters by one CTA; offsets[total] = grand total; cursors = copy of offsets
-__global__ void __launch_bounds__(1024) k_scan_exclusive(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
-                                                         uint32_t* __restrict__ cursors, uint32_t total, uint32_t* __restrict__ info) {
-    __shared__ uint32_t sh[1024];
-    __shared__ uint32_t sh_max;
-    if (threadIdx.x == 0) sh_max = 0;
+// Chunk size and number of accumulation levels for a longest bucket run of `maxrun` entries: the smallest S
+// with S^levels >= maxrun; two levels while runs are short, more for adversarially skewed scalars.
+// `entries` small (a latency-bound MSM): one more level, i.e. shorter dependent chains and finer work items.
+__host__ __device__ inline void msm_chunking(uint32_t maxrun, uint32_t entries, uint32_t& S, uint32_t& levels) {
+    if (maxrun < 1) maxrun = 1;
+    levels = maxrun <= 1 ? 1 : maxrun <= (1u << 12) ? 2 : maxrun <= (1u << 18) ? 3 : 4;
+    if (levels == 2 && maxrun > 27 && entries < (1u << 22)) levels = 3;
+    S = 2;
+    while (true) {
+        uint64_t pw = 1;
+        for (uint32_t i = 0; i < levels; i++) pw *= S;
+        if (pw >= maxrun) break;
+        S++;
+    }
+}
+
+__device__ inline uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t* sh, uint32_t& total) {
     const uint32_t tid = threadIdx.x;
-    const uint32_t chunk = (total + 1023) / 1024;
-    const uint32_t beg = tid * chunk, end = min(beg + chunk, total);
-    uint32_t sum = 0, mx = 0;
-    for (uint32_t i = beg; i < end; i++) { uint32_t cnt = counts[i]; sum += cnt; mx = max(mx, cnt); }
-    sh[tid] = sum;
+    sh[tid] = v;
     __syncthreads();
-    atomicMax(&sh_max, mx);
     for (uint32_t off = 1; off < 1024; off <<= 1) {
-        uint32_t v = tid >= off ? sh[tid - off] : 0;
+        uint32_t t = tid >= off ? sh[tid - off] : 0;
         __syncthreads();
-        sh[tid] += v;
+        sh[tid] += t;
         __syncthreads();
     }
-    uint32_t run = sh[tid] - sum;
+    uint32_t incl = sh[tid];
+    total = sh[1023];
+    __syncthreads();
+    return incl - v;
+}
+
+// One CTA: exclusive scan of the B bucket counters (-> offsets, cursors), the run statistics, the chunking
+// (S, levels) chosen from them, and the chunk plan of EVERY accumulation level:
+//   plan[l][b] = exclusive scan over buckets of ceil(count_b / S^(l+1)),  plan[l][B] = items of level l.
+// info: entries, longest run, S, levels, items[0..3].
+__global__ void __launch_bounds__(1024) k_scan_plan(const uint32_t* __restrict__ counts, uint32_t B, uint32_t* __restrict__ offsets,
+                                                    uint32_t* __restrict__ cursors, uint32_t* __restrict__ plan0, uint32_t* __restrict__ plan1,
+                                                    uint32_t* __restrict__ plan2, uint32_t* __restrict__ plan3, uint32_t* __restrict__ info) {
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t sh_max, sh_S, sh_levels;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) sh_max = 0;
+    const uint32_t per = (B + 1023) / 1024;
+    const uint32_t beg = min(tid * per, B), end = min(beg + per, B);
+    uint32_t sum = 0, mx = 0;
+    for (uint32_t i = beg; i < end; i++) { uint32_t cnt = counts[i]; sum += cnt; mx = max(mx, cnt); }
+    __syncthreads();
+    atomicMax(&sh_max, mx);
+    uint32_t total;
+    uint32_t run = block_exclusive_scan_1024(sum, sh, total);
     for (uint32_t i = beg; i < end; i++) { offsets[i] = run; cursors[i] = run; run += counts[i]; }
-    if (tid == 1023) { offsets[total] = sh[1023]; info[0] = sh[1023]; info[1] = sh_max; }
+    if (tid == 0) {
+        offsets[B] = total;
+        uint32_t S, levels;
+        msm_chunking(sh_max, total, S, levels);
+        sh_S = S; sh_levels = levels;
+        info[0] = total; info[1] = sh_max; info[2] = S; info[3] = levels;
+    }
+    __syncthreads();
+    const uint32_t S = sh_S;
+    uint32_t* plans[MSM_MAX_LEVELS] = {plan0, plan1, plan2, plan3};
+    uint64_t div = 1;
+    for (int l = 0; l < MSM_MAX_LEVELS; l++) {
+        div *= S;
+        uint32_t s = 0;
+        for (uint32_t i = beg; i < end; i++) s += (uint32_t)((counts[i] + div - 1) / div);
+        uint32_t tot;
+        uint32_t r = block_exclusive_scan_1024(s, sh, tot);
+        for (uint32_t i = beg; i < end; i++) { plans[l][i] = r; r += (uint32_t)((counts[i] + div - 1) / div); }
+        if (tid == 0) { plans[l][B] = tot; info[4 + l] = tot; }
+    }
 }
 
 __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __restrict__ codes, size_t total, uint32_t* __restrict__ cursors,
@@ -96,28 +145,6 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __restrict_
 // most S consecutive entries of one run.  Level 1 turns chunks of base indices into partial sums (mixed
 // additions); every further level sums chunks of the previous level's partial sums, until each bucket
 // is down to one point.  Work per thread is bounded by S at every level whatever the scalars are.
-
-// chunk_start = exclusive scan of ceil(len_b / S) over the runs seg_off[b] .. seg_off[b+1]; one CTA
-__global__ void __launch_bounds__(1024) k_chunk_plan(const uint32_t* __restrict__ seg_off, uint32_t nseg, uint32_t S,
-                                                     uint32_t* __restrict__ chunk_start) {
-    __shared__ uint32_t sh[1024];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t per = (nseg + 1023) / 1024;
-    const uint32_t beg = tid * per, end = min(beg + per, nseg);
-    uint32_t sum = 0;
-    for (uint32_t i = beg; i < end; i++) sum += (seg_off[i + 1] - seg_off[i] + S - 1) / S;
-    sh[tid] = sum;
-    __syncthreads();
-    for (uint32_t off = 1; off < 1024; off <<= 1) {
-        uint32_t v = tid >= off ? sh[tid - off] : 0;
-        __syncthreads();
-        sh[tid] += v;
-        __syncthreads();
-    }
-    uint32_t run = sh[tid] - sum;
-    for (uint32_t i = beg; i < end; i++) { chunk_start[i] = run; run += (seg_off[i + 1] - seg_off[i] + S - 1) / S; }
-    if (tid == 1023) chunk_start[nseg] = sh[1023];
-}
 
 // one thread per chunk: out[p] = sum of the chunk's elements
 template <class F, bool MIXED>
@@ -277,79 +304,72 @@ void msm_prepare(const AffinePt<F>* bases_dev, size_t m, MsmBases<F>& out, cudaS
     }
 }
 
+template <class T>
+static inline void ensure(DevBuf<T>& b, size_t n, cudaStream_t s) { if (b.n < n) b.alloc(n, s); }
+
 template <class F>
 void msm_begin(MsmJob<F>& job) {
     const MsmBases<F>& bases = *job.bases;
+    MsmScratch<F>& sc = bases.scratch;
     cudaStream_t stream = job.stream;
     const size_t m = job.m;
     SB_REQUIRE(m == bases.m, "msm: scalar count does not match the prepared bases");
     const uint32_t B = 1u << (bases.lay.c - 1);
     const size_t total = (size_t)bases.lay.W * m;             // upper bound on the number of entries
     SB_REQUIRE(total < ((size_t)1 << 31), "msm: too many (window, point) pairs for 31-bit table indices");
-    job.codes.alloc(total, stream); job.sorted.alloc(total, stream);
-    job.counts.alloc(B, stream); job.offsets.alloc(B + 1, stream); job.cursors.alloc(B, stream); job.info.alloc(2, stream);
-    SB_CUDA(cudaMemsetAsync(job.counts.get(), 0, job.counts.bytes(), stream));
-    SB_LAUNCH(k_msm_digits, grid_for(m, 256, 8), 256, 0, stream, job.scalars, m, bases.lay, job.codes.get(), job.counts.get());
-    SB_LAUNCH(k_scan_exclusive, 1, 1024, 0, stream, job.counts.get(), job.offsets.get(), job.cursors.get(), B, job.info.get());
-    SB_CUDA(cudaMemcpyAsync(job.info_host, job.info.get(), 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    SB_LAUNCH(k_msm_scatter, grid_for(total, 256, 8), 256, 0, stream, job.codes.get(), total, job.cursors.get(), job.sorted.get());
+    ensure(sc.codes, total, stream); ensure(sc.sorted, total, stream);
+    ensure(sc.counts, B, stream); ensure(sc.offsets, B + 1, stream); ensure(sc.cursors, B, stream); ensure(sc.info, 8, stream);
+    for (int l = 0; l < MSM_MAX_LEVELS; l++) ensure(sc.plan[l], B + 1, stream);
+    SB_CUDA(cudaMemsetAsync(sc.counts.get(), 0, B * sizeof(uint32_t), stream));
+    SB_LAUNCH(k_msm_digits, grid_for(m, 256, 8), 256, 0, stream, job.scalars, m, bases.lay, sc.codes.get(), sc.counts.get());
+    SB_LAUNCH(k_scan_plan, 1, 1024, 0, stream, sc.counts.get(), B, sc.offsets.get(), sc.cursors.get(), sc.plan[0].get(), sc.plan[1].get(),
+              sc.plan[2].get(), sc.plan[3].get(), sc.info.get());
+    SB_CUDA(cudaMemcpyAsync(job.info_host, sc.info.get(), 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    SB_LAUNCH(k_msm_scatter, grid_for(total, 256, 8), 256, 0, stream, sc.codes.get(), total, sc.cursors.get(), sc.sorted.get());
 }
 
-// Chunk size S and level count from the measured longest run: two levels (chunks of S, then at most S
-// partial sums per bucket) while the longest run is <= 2^12, more levels beyond (adversarial scalars).
+// Accumulation levels (chunks of S: level 0 mixed additions of table entries, later levels full additions of the
+// previous level's partial sums), then sum_k k B_k.  Everything was planned on the device in msm_begin; the
+// host only needs the item counts to size the grids.
 template <class F>
 void msm_finish(MsmJob<F>& job) {
     const MsmBases<F>& bases = *job.bases;
+    MsmScratch<F>& sc = bases.scratch;
     cudaStream_t stream = job.stream;
     const uint32_t B = 1u << (bases.lay.c - 1);
-    const size_t entries = job.info_host[0];
-    const size_t maxrun = job.info_host[1] ? job.info_host[1] : 1;
-    int levels = maxrun <= 1 ? 1 : maxrun <= (1u << 12) ? 2 : maxrun <= (1u << 18) ? 3 : 4;
-    uint32_t S = 1;
-    while (true) {                                             // smallest S with S^levels >= maxrun
-        size_t pw = 1;
-        for (int i = 0; i < levels; i++) pw *= S;
-        if (pw >= maxrun) break;
-        S++;
-    }
-    if (S < 2) S = 2;
-    const size_t bound1 = entries / S + B + 1;
-    const size_t bound2 = bound1 / S + B + 1;
-    job.ptsA.alloc(bound1, stream); job.ptsB.alloc(bound2, stream);
-    job.planA.alloc(B + 1, stream); job.planB.alloc(B + 1, stream);
-    const uint32_t* seg = job.offsets.get();
+    const uint32_t S = job.info_host[2], levels = job.info_host[3];
+    const uint32_t* items = job.info_host + 4;
+    SB_REQUIRE(levels >= 1 && levels <= (uint32_t)MSM_MAX_LEVELS && S >= 2, "msm: bad plan");
+    ensure(sc.ptsA, std::max<size_t>(items[0], 1), stream);
+    if (levels > 1) ensure(sc.ptsB, std::max<size_t>(items[1], 1), stream);
+    const uint32_t* seg = sc.offsets.get();
     const XyzzPt<F>* in_pts = nullptr;
-    size_t elems = entries, run = maxrun;
-    int level = 0;
-    const XyzzPt<F>* last_pts = nullptr; const uint32_t* last_plan = nullptr;
-    while (true) {
-        uint32_t* plan = (level % 2 == 0) ? job.planA.get() : job.planB.get();
-        XyzzPt<F>* outp = (level % 2 == 0) ? job.ptsA.get() : job.ptsB.get();
-        size_t items = elems / S + B + 1;
-        SB_LAUNCH(k_chunk_plan, 1, 1024, 0, stream, seg, B, S, plan);
-        if (level == 0)
-            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_mixed"), (k_seg_accum<F, true>), (int)((items + 127) / 128), 128, 0, stream,
-                            bases.tab.get(), job.sorted.get(), in_pts, seg, plan, B, S, outp);
+    const XyzzPt<F>* last_pts = nullptr;
+    for (uint32_t l = 0; l < levels; l++) {
+        XyzzPt<F>* outp = (l % 2 == 0) ? sc.ptsA.get() : sc.ptsB.get();
+        const uint32_t* plan = sc.plan[l].get();
+        const int grid = (int)((std::max<uint32_t>(items[l], 1) + 127) / 128);
+        if (l == 0)
+            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_mixed"), (k_seg_accum<F, true>), grid, 128, 0, stream,
+                            bases.tab.get(), sc.sorted.get(), in_pts, seg, plan, B, S, outp);
         else
-            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, false>), (int)((items + 127) / 128), 128, 0, stream,
-                            bases.tab.get(), job.sorted.get(), in_pts, seg, plan, B, S, outp);
-        last_pts = outp; last_plan = plan;
-        run = (run + S - 1) / S;
-        if (run <= 1) break;
-        seg = plan; in_pts = outp; elems = items; level++;
+            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, false>), grid, 128, 0, stream,
+                            bases.tab.get(), sc.sorted.get(), in_pts, seg, plan, B, S, outp);
+        last_pts = outp; seg = plan; in_pts = outp;
     }
+    const uint32_t* last_plan = sc.plan[levels - 1].get();
     const uint32_t L = B >= 8 * RED_THREADS ? 8 : 1;
     const uint32_t nthreads = (B + L - 1) / L;
     const uint32_t nblocks = (nthreads + RED_THREADS - 1) / RED_THREADS;
-    job.block_out.alloc(nblocks, stream);
+    ensure(sc.block_out, nblocks, stream);
     const size_t smem = RED_THREADS * sizeof(XyzzPt<F>);
-    SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce1"), (k_bucket_reduce1<F>), (int)nblocks, RED_THREADS, smem, stream, last_pts, last_plan, B, L, job.block_out.get());
-    SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce2"), (k_bucket_reduce2<F>), 1, RED_THREADS, smem, stream, job.block_out.get(), nblocks, job.out);
+    SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce1"), (k_bucket_reduce1<F>), (int)nblocks, RED_THREADS, smem, stream, last_pts, last_plan, B, L, sc.block_out.get());
+    SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce2"), (k_bucket_reduce2<F>), 1, RED_THREADS, smem, stream, sc.block_out.get(), nblocks, job.out);
 }
 
 template <class F>
 void msm_run(const MsmBases<F>& bases, const Fr* scalars_dev, size_t m, XyzzPt<F>* out_dev, cudaStream_t stream) {
-    static thread_local PinnedBuf<uint32_t> info(2);
+    static thread_local PinnedBuf<uint32_t> info(8);
     MsmJob<F> job;
     job.bases = &bases; job.scalars = scalars_dev; job.m = m; job.out = out_dev; job.stream = stream; job.info_host = info.get();
     msm_begin(job);

@@ -25,11 +25,23 @@ struct WinLayout {
 };
 WinLayout msm_layout(size_t m);
 
+constexpr int MSM_MAX_LEVELS = 4;
+
+// Scratch of one MSM over one base table; kept with the table and reused by every proof (allocated on first
+// use, grown on demand), so that the steady state performs no device allocation at all.
+template <class F>
+struct MsmScratch {
+    DevBuf<uint32_t> codes, sorted, counts, offsets, cursors, info;
+    DevBuf<uint32_t> plan[MSM_MAX_LEVELS];
+    DevBuf<XyzzPt<F>> ptsA, ptsB, block_out;
+};
+
 template <class F>
 struct MsmBases {
     DevBuf<AffinePt<F>> tab;   // [W][m]: tab[w * m + i] = 2^(shift[w]) * P_i
     size_t m = 0;
     WinLayout lay{};
+    mutable MsmScratch<F> scratch;
 };
 
 // One MSM in flight: phase A (digits, counting sort, run statistics) and phase B (chunked accumulation,
@@ -42,9 +54,7 @@ struct MsmJob {
     size_t m = 0;
     XyzzPt<F>* out = nullptr;
     cudaStream_t stream = nullptr;
-    uint32_t* info_host = nullptr;     // pinned: [0] = number of entries, [1] = longest bucket run
-    DevBuf<uint32_t> codes, sorted, counts, offsets, cursors, info, planA, planB;
-    DevBuf<XyzzPt<F>> ptsA, ptsB, block_out;
+    uint32_t* info_host = nullptr;     // pinned, 8 words: entries, longest run, S, levels, items per level (4)
 };
 template <class F> void msm_begin(MsmJob<F>& job);
 template <class F> void msm_finish(MsmJob<F>& job);   // job.stream must have been synchronised after msm_begin

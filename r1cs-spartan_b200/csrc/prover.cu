@@ -33,7 +33,11 @@ struct sb_ctx {
     DevBuf<Fr> d_mail;                 // device scratch for scalars going in / results coming out
     PinnedBuf<Fr> h_mail;
     // auxiliary streams: the ladder of G2 MSMs of one opening runs concurrently on these
-    static constexpr int NAUX = 8;
+    // one stream per ladder level.  Levels 4.. (small, latency-bound: ~4 ms of dependent point additions whatever
+    // their size) run at the highest priority so that their short kernels always find a slot; the four large,
+    // throughput-bound levels follow in decreasing size.
+    static constexpr int NAUX = 32;
+    static constexpr int NBIG = 4;
     cudaStream_t aux[NAUX] = {};
     cudaEvent_t ev_main = nullptr, ev_aux[NAUX] = {};
     PinnedBuf<uint32_t> msm_info;      // 2 words per ladder level
@@ -467,91 +471,98 @@ static G1Aff commit_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full) {
     return xyzz_to_affine_host(acc);
 }
 
-// open.rs:19-58 with the halved MSMs on one parameter set: pi_i = MSM(g2[i+1], q_k), k = nv - i.
-// The fold/quotient chain runs first on the main stream (it is microseconds of work); the nv MSMs are
-// then independent and are spread over the auxiliary streams, largest first, so that the latency-bound
-// tails of the small ones hide behind the throughput-bound accumulation of the large ones.
-// Leaves the nv results (XYZZ) in res_dev and the fully folded value in the mailbox slot SLOT_OUT.
-static void open_partial(sb_ctx* c, const sb_pp* pp, const Fr* table_dev, const Fr* point_host, G2Xyzz* res_dev,
-                         DevBuf<Fr>& r0, DevBuf<Fr>& r1, DevBuf<Fr>& q) {
-    uint32_t nv = pp->nv;
+// open.rs:19-58 with the halved MSMs: pi_i = MSM(g2[i+1], q_k), k = nv - i.
+// Stage 1 -- the fold/quotient chain of one parameter set on the main stream (microseconds of work): fills the
+// quotient pyramid q (level with `half` entries at q + half) and leaves the fully folded value in d_mail[out_slot].
+static void open_folds(sb_ctx* c, uint32_t nv, const Fr* table_dev, int point_slot, DevBuf<Fr>& r0, DevBuf<Fr>& r1, DevBuf<Fr>& q, int out_slot) {
     size_t n = (size_t)1 << nv;
     cudaStream_t st = c->stream;
-    SB_REQUIRE(nv <= 64, "nv too large for the mailbox");
-    h2d_fr(c, sb_ctx::SLOT_VEC2, point_host, nv);
     if (r0.n < std::max<size_t>(n / 2, 1)) r0.alloc(std::max<size_t>(n / 2, 1), st);
     if (r1.n < std::max<size_t>(n / 4, 1)) r1.alloc(std::max<size_t>(n / 4, 1), st);
-    if (q.n < n) q.alloc(n, st);                       // quotient pyramid: level with `half` entries lives at q + half
+    if (q.n < n) q.alloc(n, st);
     const Fr* cur = table_dev;
     for (uint32_t i = 0; i < nv; i++) {
         size_t half = (size_t)1 << (nv - i - 1);
         Fr* dst = (i % 2 == 0) ? r0.get() : r1.get();
-        launch_open_fold(cur, dst, q.get() + half, c->d_mail.get() + sb_ctx::SLOT_VEC2 + i, half, st);
+        launch_open_fold(cur, dst, q.get() + half, c->d_mail.get() + point_slot + i, half, st);
         cur = dst;
     }
-    SB_CUDA(cudaMemcpyAsync(c->d_mail.get() + sb_ctx::SLOT_OUT, cur, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-    SB_CUDA(cudaEventRecord(c->ev_main, st));
-    std::vector<MsmJob<Fq2>> jobs(nv);
-    const int na = (int)std::min<uint32_t>(nv, sb_ctx::NAUX);
-    for (int s = 0; s < na; s++) SB_CUDA(cudaStreamWaitEvent(c->aux[s], c->ev_main, 0));
-    for (uint32_t i = 0; i < nv; i++) {
-        size_t half = (size_t)1 << (nv - i - 1);
-        MsmJob<Fq2>& j = jobs[i];
-        j.bases = &pp->g2[i + 1]; j.scalars = q.get() + half; j.m = half; j.out = res_dev + i;
-        j.stream = c->serial_msm ? c->aux[0] : c->aux[i % sb_ctx::NAUX]; j.info_host = c->msm_info.get() + 2 * i;
-        msm_begin(j);
+    SB_CUDA(cudaMemcpyAsync(c->d_mail.get() + out_slot, cur, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+}
+// Stage 2 -- the nv MSMs of one parameter set as jobs; they are independent of one another.
+static void open_add_jobs(sb_ctx* c, const sb_pp* pp, const Fr* q, G2Xyzz* res_dev, std::vector<MsmJob<Fq2>>& jobs) {
+    for (uint32_t i = 0; i < pp->nv; i++) {
+        size_t half = (size_t)1 << (pp->nv - i - 1);
+        jobs.emplace_back();
+        MsmJob<Fq2>& j = jobs.back();
+        size_t k = jobs.size() - 1;
+        j.bases = &pp->g2[i + 1]; j.scalars = q + half; j.m = half; j.out = res_dev + i;
+        j.stream = c->serial_msm ? c->aux[0] : c->aux[k % sb_ctx::NAUX]; j.info_host = c->msm_info.get() + 8 * k;
     }
+}
+// Stage 3 -- run every queued job: one stream per job (largest first = highest priority, so the latency-bound
+// tails of the small ones hide behind the throughput-bound accumulation of the large ones), one host
+// synchronisation between the sorting phase and the accumulation phase.
+static void open_run_jobs(sb_ctx* c, std::vector<MsmJob<Fq2>>& jobs) {
+    cudaStream_t st = c->stream;
+    SB_CUDA(cudaEventRecord(c->ev_main, st));
+    const int na = (int)std::min<size_t>(jobs.size(), sb_ctx::NAUX);
+    for (int s = 0; s < na; s++) SB_CUDA(cudaStreamWaitEvent(c->aux[s], c->ev_main, 0));
+    for (auto& j : jobs) msm_begin(j);
     for (int s = 0; s < na; s++) SB_CUDA(cudaStreamSynchronize(c->aux[s]));
-    g_sb_d2h_bytes += 8 * nv;
-    for (uint32_t i = 0; i < nv; i++) msm_finish(jobs[i]);
+    g_sb_d2h_bytes += 32 * jobs.size();
+    for (auto& j : jobs) msm_finish(j);
     for (int s = 0; s < na; s++) {
         SB_CUDA(cudaEventRecord(c->ev_aux[s], c->aux[s]));
         SB_CUDA(cudaStreamWaitEvent(st, c->ev_aux[s], 0));
     }
-}   // job buffers are released in stream order on their own streams
+}
 
-// Full opening of the nv_total-variable polynomial z at `point`.  Sharded: each rank opens its slice over the
-// local variables with its slice of the parameters (partial sums per level + its folded value), one allgather
-// exchanges them, the per-level partial sums are added on the host, and the gathered folded values are the
-// table of the tail opening over the top glog variables, which every rank runs redundantly.
+// Full opening of the nv_total-variable polynomial z at `point`.  Sharded: each rank folds its slice over the
+// local variables; the G folded values are exchanged at once (32 bytes each) and are the table of the tail
+// opening over the top glog variables, which every rank runs redundantly; the MSMs of the local levels (on the
+// rank's slice of the parameters) and of the tail levels are queued together; finally the per-level partial sums
+// of the local levels are exchanged and added on the host.
 static void open_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full, const Fr* point_host, Fr* eval_out, G2Aff* proofs_out,
                      DevBuf<Fr>& r0, DevBuf<Fr>& r1, DevBuf<Fr>& q) {
-    const uint32_t loc = pp->nv, total = pp->nv_total;
+    const uint32_t loc = pp->nv, total = pp->nv_total, g = total - loc;
     const size_t nl = (size_t)1 << loc;
+    const int G = c->world;
     cudaStream_t st = c->stream;
+    SB_REQUIRE(total <= 64, "nv too large for the mailbox");
+    h2d_fr(c, sb_ctx::SLOT_VEC2, point_host, total);
     DevBuf<G2Xyzz> res(total, st);
-    open_partial(c, pp, z_dev_full + (size_t)c->rank * nl, point_host, res.get(), r0, r1, q);
-    std::vector<G2Xyzz> pts(total);
-    if (!c->sharded()) {
-        fetch_xyzz(c, res.get(), total, pts.data());
-        d2h_fr(c, sb_ctx::SLOT_OUT, eval_out, 1);
-    } else {
-        const int G = c->world; const uint32_t g = (uint32_t)c->glog;
-        const size_t rec = loc * sizeof(G2Xyzz) + sizeof(Fr);
-        std::vector<uint8_t> mine(rec), all(rec * G);
-        fetch_xyzz(c, res.get(), loc, reinterpret_cast<G2Xyzz*>(mine.data()));
+    DevBuf<Fr> tt, t0, t1, tq;                      // tail scratch (must outlive the jobs)
+    std::vector<MsmJob<Fq2>> jobs;
+    jobs.reserve(total);
+    open_folds(c, loc, z_dev_full + (size_t)c->rank * nl, sb_ctx::SLOT_VEC2, r0, r1, q, sb_ctx::SLOT_OUT);
+    open_add_jobs(c, pp, q.get(), res.get(), jobs);
+    if (c->sharded()) {
         Fr folded; d2h_fr(c, sb_ctx::SLOT_OUT, &folded, 1);
-        memcpy(mine.data() + loc * sizeof(G2Xyzz), &folded, sizeof(Fr));
-        c->allgather(mine.data(), all.data(), rec);
         std::vector<Fr> tail_tab(G);
-        for (uint32_t i = 0; i < loc; i++) {
-            G2Xyzz acc = G2Xyzz::inf();
-            for (int r = 0; r < G; r++) {
-                G2Xyzz part; memcpy(&part, all.data() + r * rec + i * sizeof(G2Xyzz), sizeof part);
-                acc = G2Xyzz::add(acc, part);
-            }
-            pts[i] = acc;
-        }
-        for (int r = 0; r < G; r++) memcpy(&tail_tab[r], all.data() + r * rec + loc * sizeof(G2Xyzz), sizeof(Fr));
-        DevBuf<Fr> tt(G, st), t0, t1, tq;
+        c->allgather(&folded, tail_tab.data(), sizeof(Fr));
+        tt.alloc(G, st);
         SB_CUDA(cudaMemcpyAsync(tt.get(), tail_tab.data(), G * sizeof(Fr), cudaMemcpyHostToDevice, st));
         g_sb_h2d_bytes += G * sizeof(Fr);
-        open_partial(c, pp->tail.get(), tt.get(), point_host + loc, res.get() + loc, t0, t1, tq);
-        fetch_xyzz(c, res.get() + loc, g, pts.data() + loc);
-        d2h_fr(c, sb_ctx::SLOT_OUT, eval_out, 1);
+        open_folds(c, g, tt.get(), sb_ctx::SLOT_VEC2 + loc, t0, t1, tq, sb_ctx::SLOT_OUT);
+        ctx_sync(c);                                // tail_tab (host) is read by the async copy above
+        open_add_jobs(c, pp->tail.get(), tq.get(), res.get() + loc, jobs);
+    }
+    open_run_jobs(c, jobs);
+    std::vector<G2Xyzz> pts(total);
+    fetch_xyzz(c, res.get(), total, pts.data());
+    d2h_fr(c, sb_ctx::SLOT_OUT, eval_out, 1);
+    if (c->sharded()) {
+        std::vector<G2Xyzz> all((size_t)loc * G);
+        c->allgather(pts.data(), all.data(), loc * sizeof(G2Xyzz));
+        for (uint32_t i = 0; i < loc; i++) {
+            G2Xyzz acc = all[i];
+            for (int r = 1; r < G; r++) acc = G2Xyzz::add(acc, all[(size_t)r * loc + i]);
+            pts[i] = acc;
+        }
     }
     to_affine_many_host(pts.data(), total, proofs_out);
-}
+}   // job buffers are released in stream order on their own streams
 
 // ====================================================================== prover rounds
 static void prover_setup_common(sb_prover* p, sb_ctx* c, const sb_index* ix, size_t nv_len) {
@@ -810,9 +821,16 @@ sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
         SB_CUDA(cudaMemsetAsync(c->ticket.get(), 0, sizeof(unsigned int), c->stream));
         c->d_mail.alloc(sb_ctx::MAIL, c->stream);
         c->h_mail.alloc(sb_ctx::MAIL);
-        c->msm_info.alloc(2 * 64);
+        c->msm_info.alloc(8 * 64);
+        int prio_least = 0, prio_greatest = 0;
+        SB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
         for (int i = 0; i < sb_ctx::NAUX; i++) {
-            SB_CUDA(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+            // SB_STREAM_PRIORITIES=1: small (latency-bound) levels at the highest priority, the four large ones
+            // below them in decreasing size; default: one priority for all (measured faster)
+            static const bool use_prio = getenv("SB_STREAM_PRIORITIES") && atoi(getenv("SB_STREAM_PRIORITIES")) != 0;
+            int prio = !use_prio ? prio_least : (i >= sb_ctx::NBIG ? prio_greatest : prio_greatest + 1 + i);
+            if (prio > prio_least) prio = prio_least;
+            SB_CUDA(cudaStreamCreateWithPriority(&c->aux[i], cudaStreamNonBlocking, prio));
             SB_CUDA(cudaEventCreateWithFlags(&c->ev_aux[i], cudaEventDisableTiming));
         }
         SB_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
@@ -1106,6 +1124,7 @@ sb_status sb_prover_export_abc(sb_prover* p, void* az, void* bz, void* cz) {
 
 // ---------------------------------------------------------------- MLArgumentForR1CS::prove (lib.rs:58-146)
 std::string sb_prof_collect();    // kernels_fr.cu
+std::string sb_prof_timeline_collect();
 
 static void prove_body(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const void* v, size_t nv_len, const void* w, size_t nw_len,
                        const sb_witness* resident, uint8_t* proof, size_t* len, sb_trace* tr) {
@@ -1259,6 +1278,11 @@ void sb_copy_counters(uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
     if (d2h_bytes) *d2h_bytes = g_sb_d2h_bytes;
 }
 void sb_prof_enable(int on) { g_sb_prof_on = on != 0; }
+size_t sb_prof_timeline(char* buf, size_t cap) {
+    std::string s = sb_prof_timeline_collect();
+    if (buf && cap) { size_t k = s.size() < cap - 1 ? s.size() : cap - 1; memcpy(buf, s.data(), k); buf[k] = 0; }
+    return s.size() + 1;
+}
 void sb_set_serial_msm(sb_ctx* ctx, int on) { if (ctx) ctx->serial_msm = on != 0; }
 size_t sb_prof_report(char* buf, size_t cap) {
     std::string s = sb_prof_collect();
