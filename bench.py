@@ -248,9 +248,12 @@ def run_ours(args):
         # algorithmic bytes of one launch of the dominant kernel (DESIGN.md "Roofline accounting")
         alg = algorithmic_bytes(name, n, LOG_N, rec["launches"] // args.steps)
         ach = alg / (per_launch_ms * 1e-3) / 1e9 if alg else None
+        traffic = NCU_TRAFFIC.get((name, LOG_N))
         roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": (ach / hbm_peak) if ach else None,
-                    "traffic": None, "peak_source": peak_src, "avg_launch_ms": per_launch_ms,
-                    "note": "dominant kernel is integer-pipe (IMAD.WIDE) bound, not HBM bound: see roofline_imad"}
+                    "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None,
+                    "algorithmic_bytes_per_launch": alg, "peak_source": peak_src, "avg_launch_ms": per_launch_ms,
+                    "note": "the dominant kernel is bound by the integer pipe (IMAD.WIDE issue rate), not by HBM: see roofline_imad "
+                            "for its achieved Fq products per second against the ceiling measured in this run"}
     # integer-pipe ceiling measured in the same run: dependent-free Montgomery products (2 chains per thread)
     single = sb.Context(local_rank) if world > 1 else ctx
     fq_ms = single.mul_bench("fq", 148 * 1024, 1000)
@@ -299,43 +302,59 @@ def run_ours(args):
     print(json.dumps(line))
 
 
+def msm_layout(m):
+    """window bits c and window count W of an MSM over m points (mirror of msm_layout in csrc/msm.cu)"""
+    lg = max(m - 1, 0).bit_length()
+    c = min(16, max(4, lg - 3))
+    rest = 255 - (c - 1)
+    return c, (rest + c - 1) // c + 1
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the `ncu --set full` capture under profiles/
+NCU_TRAFFIC = {("k_seg_accum_mixed:top<Fq2>", 20): (2.167095e9 + 0.934841e9, "profiles/r01_ncu_g2_accum_top.txt")}
+
+
 def algorithmic_bytes(name, n, ell, launches_per_step):
-    """Algorithmic HBM bytes of ONE launch (average over the launches of a step) of the named kernel."""
-    if name.startswith("k_seg_accum_mixed<Fq2>"):
-        # two openings: sum over levels of m_k * W_k entries, each one 192-byte affine base + 4-byte index, plus one
-        # 384-byte bucket write per (window, bucket)
-        total = 0
-        for k in range(0, ell):
-            m = 1 << k
-            c = max(4, min(16, max(k, 0) - 3)) if m > 1 else 4
-            W = 255 // c + 1
-            total += m * W * (192 + 4) + W * (1 << (c - 1)) * 384
-        return 2.0 * total / launches_per_step
+    """Algorithmic HBM bytes of ONE launch of the named kernel."""
+    if name.startswith("k_seg_accum_mixed:top<Fq2>"):
+        # first level of an opening: m = n/2 bases; every (window, point) entry reads a 4-byte index and gathers one
+        # 192-byte affine base; every chunk of <= S entries writes one 384-byte partial sum
+        m = n // 2
+        c, W = msm_layout(m)
+        entries = W * m
+        S = 19
+        return entries * (192 + 4) + (entries // S + (1 << (c - 1))) * 384
     if name.startswith("k_seg_accum_mixed<Fq>"):
-        c, W = 16, 16
-        return n * W * (96 + 4) + W * (1 << (c - 1)) * 192
+        c, W = msm_layout(n)
+        entries = W * n
+        return entries * (96 + 4) + (entries // 32 + (1 << (c - 1))) * 192
     return None
 
 
 def imad_roofline(kernels, n, ell, fq_peak, fr_peak):
-    """Achieved Fq products per second of the two bucket-accumulation kernels against the measured ceiling.
+    """Achieved Fq products per second of the bucket-accumulation kernels against the measured ceiling.
     One mixed addition in XYZZ = 8M + 2S = 10 Fq products over G1, and 8*3 + 2*2 = 28 over G2 (Karatsuba Fq2)."""
     out = {}
     k1 = kernels.get("k_seg_accum_mixed<Fq>")
     if k1:
-        adds = n * 16 * (1 - 2.0 ** -16)
-        out["g1_accum"] = {"ms": k1["ms_per_step"], "fq_gmul_s": adds * 10 / k1["ms_per_step"] / 1e6}
+        c, W = msm_layout(n)
+        out["g1_accum"] = {"ms": k1["ms_per_step"], "fq_gmul_s": W * n * 10 / k1["ms_per_step"] / 1e6}
         out["g1_accum"]["frac"] = out["g1_accum"]["fq_gmul_s"] / fq_peak
+    kt = kernels.get("k_seg_accum_mixed:top<Fq2>")
+    if kt:
+        c, W = msm_layout(n // 2)
+        adds = 2 * W * (n // 2)                      # two openings per proof
+        out["g2_accum_top_level"] = {"ms": kt["ms_per_step"], "fq_gmul_s": adds * 28 / kt["ms_per_step"] / 1e6}
+        out["g2_accum_top_level"]["frac"] = out["g2_accum_top_level"]["fq_gmul_s"] / fq_peak
     k2 = kernels.get("k_seg_accum_mixed<Fq2>")
     if k2:
         adds = 0
-        for k in range(0, ell):
-            m = 1 << k
-            c = max(4, min(16, k - 3)) if m > 1 else 4
-            adds += m * (255 // c + 1)
+        for k in range(0, ell - 1 if kt else ell):
+            c, W = msm_layout(1 << k)
+            adds += W * (1 << k)
         adds *= 2
-        out["g2_accum"] = {"ms": k2["ms_per_step"], "fq_gmul_s": adds * 28 / k2["ms_per_step"] / 1e6}
-        out["g2_accum"]["frac"] = out["g2_accum"]["fq_gmul_s"] / fq_peak
+        out["g2_accum_lower_levels"] = {"ms": k2["ms_per_step"], "fq_gmul_s": adds * 28 / k2["ms_per_step"] / 1e6}
+        out["g2_accum_lower_levels"]["frac"] = out["g2_accum_lower_levels"]["fq_gmul_s"] / fq_peak
     return out
 
 

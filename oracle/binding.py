@@ -352,6 +352,34 @@ class PP:
         return (ev, proofs, q) if want_q else (ev, proofs)
 
 
+def verify(r1cs, vp, v, proof):
+    """MLArgumentForR1CS::verify (lib.rs:147-212): 1 accept, 0 malformed, < 0 the failed check (see oracle source)."""
+    v = _c(v, 4)
+    buf = (C.c_uint8 * len(proof)).from_buffer_copy(proof)
+    return int(lib().or_verify(r1cs.h, vp.h, _p(v), C.c_size_t(v.shape[0]), buf, C.c_size_t(len(proof))))
+
+
+def pc_verify(vp, commitment, point, ev, proofs):
+    """MLPolyCommit::verify (commitment/verify.rs:12-45)"""
+    commitment = _c(commitment); point = _c(point, 4); ev = _c(ev); proofs = _c(proofs, 24)
+    return bool(lib().or_pc_verify(vp.h, _p(commitment), _p(point), _p(ev), _p(proofs)))
+
+
+def pairing_check(a, b):
+    a = _c(a); b = _c(b)
+    return bool(lib().or_pairing_check(_p(a), _p(b)))
+
+
+def deser_g1(data):
+    out = np.empty(12, dtype=np.uint64); buf = (C.c_uint8 * 48).from_buffer_copy(data)
+    assert lib().or_deser_g1(buf, _p(out)); return out
+
+
+def deser_g2(data):
+    out = np.empty(24, dtype=np.uint64); buf = (C.c_uint8 * 96).from_buffer_copy(data)
+    assert lib().or_deser_g2(buf, _p(out)); return out
+
+
 class Trace:
     def __init__(self, handle): self.h = C.c_void_p(handle)
     def __del__(self):

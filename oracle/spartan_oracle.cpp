@@ -22,6 +22,7 @@
 #include "ff.hpp"
 #include "ec.hpp"
 #include "blake2s.hpp"
+#include "pairing.hpp"
 #include <vector>
 #include <map>
 #include <unordered_map>
@@ -513,6 +514,209 @@ static int prove(const R1CS& cs, const PublicParameter& pp, const std::vector<Fr
     return 0;
 }
 
+
+// ------------------------------------------------------------------ deserialization (UPSTREAM CanonicalDeserialize)
+struct Reader {
+    const uint8_t* p; size_t left; bool ok;
+    Reader(const uint8_t* d, size_t n) : p(d), left(n), ok(true) {}
+    bool take(void* out, size_t n) { if (left < n) { ok = false; return false; } memcpy(out, p, n); p += n; left -= n; return true; }
+    uint64_t u64() { uint8_t b[8] = {0}; take(b, 8); uint64_t v = 0; for (int i = 7; i >= 0; i--) v = (v << 8) | b[i]; return v; }
+    Fr fr() {
+        uint64_t c[4] = {0, 0, 0, 0}; uint8_t b[32] = {0}; take(b, 32);
+        for (int i = 0; i < 4; i++) for (int j = 7; j >= 0; j--) c[i] = (c[i] << 8) | b[8 * i + j];
+        if (Fr::geq_mod(c)) ok = false;
+        return Fr::from_canonical(c);
+    }
+};
+static bool fq_from_bytes(const uint8_t* b, Fq& out) {
+    uint64_t c[6];
+    for (int i = 0; i < 6; i++) { c[i] = 0; for (int j = 7; j >= 0; j--) c[i] = (c[i] << 8) | b[8 * i + j]; }
+    if (Fq::geq_mod(c)) return false;
+    out = Fq::from_canonical(c); return true;
+}
+static bool fq_sqrt(const Fq& a, Fq& out) {             // p = 3 mod 4: a^((p+1)/4)
+    static const uint64_t E[6] = {0xee7fbfffffffeaabULL, 0x07aaffffac54ffffULL, 0xd9cc34a83dac3d89ULL, 0xd91dd2e13ce144afULL, 0x92c6e9ed90d2eb35ULL, 0x0680447a8e5ff9a6ULL};
+    Fq s = Fq::pow(a, E, 6);
+    if (Fq::sqr(s) != a) return false;
+    out = s; return true;
+}
+static bool fq2_sqrt(const Fq2& a, Fq2& out) {          // complex method
+    if (a.is_zero()) { out = a; return true; }
+    Fq n = Fq::add(Fq::sqr(a.c0), Fq::sqr(a.c1)), s;
+    if (!fq_sqrt(n, s)) return false;
+    Fq inv2 = Fq::inv(Fq::from_u64(2));
+    for (int k = 0; k < 2; k++) {
+        Fq sg = k == 0 ? s : Fq::neg(s);
+        Fq d = Fq::mul(Fq::add(a.c0, sg), inv2), x0;
+        if (!fq_sqrt(d, x0) || x0.is_zero()) continue;
+        Fq x1 = Fq::mul(a.c1, Fq::inv(Fq::dbl(x0)));
+        Fq2 c; c.c0 = x0; c.c1 = x1;
+        if (Fq2::sqr(c) == a) { out = c; return true; }
+    }
+    return false;
+}
+static bool read_g1(Reader& r, G1Affine& out) {
+    uint8_t b[48]; if (!r.take(b, 48)) return false;
+    bool inf = b[47] & 0x40, pos = b[47] & 0x80; b[47] &= 0x3f;
+    if (inf) { out = G1Affine::inf(); return true; }
+    Fq x, y;
+    if (!fq_from_bytes(b, x)) return r.ok = false;
+    if (!fq_sqrt(Fq::add(Fq::mul(Fq::sqr(x), x), Fq::from_u64(4)), y)) return r.ok = false;
+    bool y_larger = Fq::cmp_canonical(y, Fq::neg(y)) > 0;
+    out.x = x; out.y = (y_larger == pos) ? y : Fq::neg(y);
+    return true;
+}
+static bool read_g2(Reader& r, G2Affine& out) {
+    uint8_t b[96]; if (!r.take(b, 96)) return false;
+    bool inf = b[95] & 0x40, pos = b[95] & 0x80; b[95] &= 0x3f;
+    if (inf) { out = G2Affine::inf(); return true; }
+    Fq2 x, y;
+    if (!fq_from_bytes(b, x.c0) || !fq_from_bytes(b + 48, x.c1)) return r.ok = false;
+    Fq2 bb; bb.c0 = Fq::from_u64(4); bb.c1 = Fq::from_u64(4);
+    if (!fq2_sqrt(Fq2::add(Fq2::mul(Fq2::sqr(x), x), bb), y)) return r.ok = false;
+    bool y_larger = Fq2::cmp_canonical(y, Fq2::neg(y)) > 0;
+    out.x = x; out.y = (y_larger == pos) ? y : Fq2::neg(y);
+    return true;
+}
+
+// ------------------------------------------------------------------ verifier
+// src/commitment/verify.rs:12-45:  e(C - g^eval, h) == prod_i e(g^{t_i} - g^{p_i}, pi_i)
+static bool pc_verify(const PublicParameter& vp, const G1Affine& commitment, const std::vector<Fr>& point, const Fr& eval,
+                      const std::vector<G2Affine>& proofs) {
+    if (proofs.size() != vp.nv || point.size() != vp.nv) return false;
+    uint64_t c[4];
+    eval.to_canonical(c);
+    G1Jac left = G1Jac::add(G1Jac::from_affine(commitment), G1Jac::neg(G1Jac::mul(G1Jac::from_affine(vp.g), c, 4)));
+    Fq12 lhs = miller_loop(left.to_affine(), vp.h);
+    Fq12 rhs = Fq12::one();
+    for (size_t i = 0; i < vp.nv; i++) {
+        point[i].to_canonical(c);
+        G1Jac l = G1Jac::add(G1Jac::from_affine(vp.g_mask_random[i]), G1Jac::neg(G1Jac::mul(G1Jac::from_affine(vp.g), c, 4)));
+        rhs = Fq12::mul(rhs, miller_loop(l.to_affine(), proofs[i]));
+    }
+    return final_exponentiation(lhs) == final_exponentiation(rhs);
+}
+// UPSTREAM interpolate_uni_poly: value at r of the polynomial with the given evaluations at 0..d
+static Fr interpolate(const std::vector<Fr>& ev, const Fr& r) {
+    size_t d = ev.size() - 1;
+    std::vector<Fr> diff(d + 1);
+    Fr prod = Fr::R1;
+    for (size_t k = 0; k <= d; k++) {
+        diff[k] = Fr::sub(r, Fr::from_u64(k));
+        if (diff[k].is_zero()) return ev[k];
+        prod = Fr::mul(prod, diff[k]);
+    }
+    Fr acc = Fr::ZERO;
+    for (size_t i = 0; i <= d; i++) {
+        Fr w = Fr::R1;                                  // prod_{k != i} (i - k)
+        for (size_t k = 0; k <= d; k++) if (k != i) w = Fr::mul(w, Fr::sub(Fr::from_u64(i), Fr::from_u64(k)));
+        acc = Fr::add(acc, Fr::mul(ev[i], Fr::mul(prod, Fr::inv(Fr::mul(w, diff[i])))));
+    }
+    return acc;
+}
+// UPSTREAM check_and_generate_subclaim: returns false when some round violates P_j(0) + P_j(1) == expected_j
+static bool sumcheck_subclaim(const std::vector<std::vector<Fr>>& msgs, const std::vector<Fr>& chal, const Fr& asserted, Fr& expected_out) {
+    Fr expected = asserted;
+    for (size_t j = 0; j < msgs.size(); j++) {
+        if (msgs[j].size() < 2) return false;
+        if (Fr::add(msgs[j][0], msgs[j][1]) != expected) return false;
+        expected = interpolate(msgs[j], chal[j]);
+    }
+    expected_out = expected; return true;
+}
+
+// MLArgumentForR1CS::verify (src/lib.rs:147-212) + verify_sixth_round (src/ahp/verifier.rs:443-512).
+// Returns 1 = accept; 0 = malformed proof; negative = the failed check.
+static int verify(const R1CS& cs, const PublicParameter& vp, const std::vector<Fr>& v, const uint8_t* proof, size_t len) {
+    const size_t log_n = cs.log_n, n = cs.n;
+    if (v.empty() || (v.size() & (v.size() - 1)) || v.size() > n) return 0;       // verifier.rs:144-146
+    size_t log_v = 0; while ((size_t(1) << log_v) < v.size()) log_v++;
+    Reader rd(proof, len);
+    FsRng fs; fs.setup();
+    { Bytes b; ser_matrix(b, cs.a, n); fs.feed(b.data(), b.size()); }
+    { Bytes b; ser_matrix(b, cs.b, n); fs.feed(b.data(), b.size()); }
+    { Bytes b; ser_matrix(b, cs.c, n); fs.feed(b.data(), b.size()); }
+    { Bytes b; ser_fr_vec(b, v); fs.feed(b.data(), b.size()); }
+    auto feed_span = [&](const uint8_t* from) { fs.feed(from, (size_t)(rd.p - from)); };
+    // pm1
+    const uint8_t* mark = rd.p;
+    uint64_t com_nv = rd.u64(); G1Affine com; if (!read_g1(rd, com)) return 0;
+    (void)com_nv;
+    feed_span(mark);
+    std::vector<Fr> r_v; for (size_t i = 0; i < log_v; i++) r_v.push_back(fr_rand(fs));
+    // pm2
+    mark = rd.p;
+    Fr z_rv_0 = rd.fr(); G2Affine h1; if (!read_g2(rd, h1)) return 0;
+    uint64_t np1 = rd.u64(); if (!rd.ok || np1 != log_n) return 0;
+    std::vector<G2Affine> proofs1(np1); for (auto& q : proofs1) if (!read_g2(rd, q)) return 0;
+    feed_span(mark);
+    std::vector<Fr> tor; for (size_t i = 0; i < log_n; i++) tor.push_back(fr_rand(fs));
+    // pm3
+    mark = rd.p;
+    uint64_t mm1 = rd.u64(), nv1 = rd.u64();
+    if (!rd.ok || nv1 != log_n) return 0;                                        // verifier.rs:249-252
+    feed_span(mark);
+    uint64_t cnt = rd.u64(); if (!rd.ok || cnt != log_n) return 0;
+    std::vector<std::vector<Fr>> sc1(log_n); std::vector<Fr> r_x;
+    for (size_t j = 0; j < log_n; j++) {
+        mark = rd.p;
+        uint64_t k = rd.u64(); if (!rd.ok || k != mm1 + 1) return 0;
+        for (uint64_t t = 0; t < k; t++) sc1[j].push_back(rd.fr());
+        if (!rd.ok) return 0;
+        feed_span(mark);
+        r_x.push_back(fr_rand(fs));
+    }
+    // pm4
+    mark = rd.p;
+    Fr va = rd.fr(), vb = rd.fr(), vc = rd.fr(); if (!rd.ok) return 0;
+    feed_span(mark);
+    Fr r_a = fr_rand(fs), r_b = fr_rand(fs), r_c = fr_rand(fs);
+    // pm5
+    mark = rd.p;
+    uint64_t mm2 = rd.u64(), nv2 = rd.u64();
+    if (!rd.ok || nv2 != log_n) return 0;                                        // verifier.rs:399-402
+    feed_span(mark);
+    cnt = rd.u64(); if (!rd.ok || cnt != log_n) return 0;
+    std::vector<std::vector<Fr>> sc2(log_n); std::vector<Fr> r_y;
+    for (size_t j = 0; j < log_n; j++) {
+        mark = rd.p;
+        uint64_t k = rd.u64(); if (!rd.ok || k != mm2 + 1) return 0;
+        for (uint64_t t = 0; t < k; t++) sc2[j].push_back(rd.fr());
+        if (!rd.ok) return 0;
+        feed_span(mark);
+        r_y.push_back(fr_rand(fs));
+    }
+    // pm6
+    Fr z_ry = rd.fr(); G2Affine h2; if (!read_g2(rd, h2)) return 0;
+    uint64_t np2 = rd.u64(); if (!rd.ok || np2 != log_n) return 0;
+    std::vector<G2Affine> proofs2(np2); for (auto& q : proofs2) if (!read_g2(rd, q)) return 0;
+    if (!rd.ok || rd.left != 0) return 0;
+
+    // verify_sixth_round (verifier.rs:443-512)
+    std::vector<Fr> r_v_0(r_v); r_v_0.resize(log_n, Fr::ZERO);
+    if (!pc_verify(vp, com, r_v_0, z_rv_0, proofs1)) return -1;                  // "public witness failed in commitment check"
+    if (mle_eval_at(v, r_v) != z_rv_0) return -2;                                // "public witness is inconsistent with proof"
+    Fr expected1;
+    if (!sumcheck_subclaim(sc1, r_x, Fr::ZERO, expected1)) return -3;
+    {
+        Fr eq_rx = Fr::R1;                                                       // prod_i eq_i(r_x) (verifier.rs:471-474)
+        for (size_t i = 0; i < log_n; i++) {
+            Fr t = tor[i], x = r_x[i];
+            Fr tx = Fr::mul(t, x);
+            eq_rx = Fr::mul(eq_rx, Fr::add(Fr::sub(Fr::sub(Fr::add(tx, tx), x), t), Fr::R1));
+        }
+        if (Fr::mul(Fr::sub(Fr::mul(va, vb), vc), eq_rx) != expected1) return -4; // "first sumcheck has wrong subclaim"
+    }
+    Fr claimed2 = Fr::add(Fr::add(Fr::mul(r_a, va), Fr::mul(r_b, vb)), Fr::mul(r_c, vc));
+    Fr expected2;
+    if (!sumcheck_subclaim(sc2, r_y, claimed2, expected2)) return -5;
+    Fr a_rxy = mle_eval_at(eval_on_x(cs.a, r_x), r_y), b_rxy = mle_eval_at(eval_on_x(cs.b, r_x), r_y), c_rxy = mle_eval_at(eval_on_x(cs.c, r_x), r_y);
+    Fr actual = Fr::mul(Fr::add(Fr::add(Fr::mul(r_a, a_rxy), Fr::mul(r_b, b_rxy)), Fr::mul(r_c, c_rxy)), z_ry);
+    if (expected2 != actual) return -6;                                          // "Cannot verify matrix A, B, C"
+    if (!pc_verify(vp, com, r_y, z_ry, proofs2)) return -7;                      // "Cannot verify z_ry"
+    return 1;
+}
+
 // ------------------------------------------------------------------ generators
 static bool hex_to_limbs(const char* hex, uint64_t* out, int n) {
     for (int i = 0; i < n; i++) out[i] = 0;
@@ -718,6 +922,35 @@ void or_open(void* pph, const Fr* z, const Fr* point, size_t nv, Fr* eval, G2Aff
     memcpy(proofs, pr.data(), pr.size() * sizeof(G2Affine));
     if (q_flat) { size_t o = 0; for (size_t k = nv; k >= 1; k--) { memcpy(q_flat + o, q[k].data(), q[k].size() * 32); o += q[k].size(); } }
 }
+
+
+// ---- verifier
+int or_verify(void* r1cs, void* vp, const Fr* v, size_t nv_len, const uint8_t* proof, size_t len) {
+    std::vector<Fr> vv(v, v + nv_len);
+    return verify(*(R1CS*)r1cs, *(PublicParameter*)vp, vv, proof, len);
+}
+int or_pc_verify(void* vp, const G1Affine* commitment, const Fr* point, const Fr* eval, const G2Affine* proofs) {
+    PublicParameter* pp = (PublicParameter*)vp;
+    std::vector<Fr> p(point, point + pp->nv); std::vector<G2Affine> pr(proofs, proofs + pp->nv);
+    return pc_verify(*pp, *commitment, p, *eval, pr) ? 1 : 0;
+}
+// e(a P, b Q) == e(P, Q)^(ab) and e(P, Q) != 1: returns 1 when both hold
+int or_pairing_check(const Fr* a, const Fr* b) {
+    ff_init_all();
+    G1Affine g = g1_generator(); G2Affine h = g2_generator();
+    uint64_t ca[4], cb[4]; a->to_canonical(ca); b->to_canonical(cb);
+    G1Affine ag = G1Jac::mul(G1Jac::from_affine(g), ca, 4).to_affine();
+    G2Affine bh = G2Jac::mul(G2Jac::from_affine(h), cb, 4).to_affine();
+    Fq12 e = pairing(g, h);
+    if (e == Fq12::one()) return 0;
+    uint64_t cab[4]; Fr::mul(*a, *b).to_canonical(cab);
+    Fq12 acc = Fq12::one();
+    for (int i = 255; i >= 0; i--) { acc = Fq12::sqr(acc); if ((cab[i / 64] >> (i % 64)) & 1) acc = Fq12::mul(acc, e); }
+    return pairing(ag, bh) == acc ? 1 : 0;
+}
+// decompress round trip helpers
+int or_deser_g1(const uint8_t* in48, G1Affine* out) { ff_init_all(); Reader r(in48, 48); return read_g1(r, *out) && r.ok; }
+int or_deser_g2(const uint8_t* in96, G2Affine* out) { ff_init_all(); Reader r(in96, 96); return read_g2(r, *out) && r.ok; }
 
 // ---- prove
 void* or_prove(void* r1cs, void* pph, const Fr* v, size_t nv_len, const Fr* w, size_t nw_len, int* status) {

@@ -350,7 +350,7 @@ void msm_finish(MsmJob<F>& job) {
         const uint32_t* plan = sc.plan[l].get();
         const int grid = (int)((std::max<uint32_t>(items[l], 1) + 127) / 128);
         if (l == 0)
-            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_mixed"), (k_seg_accum<F, true>), grid, 128, 0, stream,
+            SB_LAUNCH_NAMED(job.top ? SB_KNAME(F, "k_seg_accum_mixed:top") : SB_KNAME(F, "k_seg_accum_mixed"), (k_seg_accum<F, true>), grid, 128, 0, stream,
                             bases.tab.get(), sc.sorted.get(), in_pts, seg, plan, B, S, outp);
         else
             SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, false>), grid, 128, 0, stream,

@@ -55,6 +55,7 @@ struct MsmJob {
     XyzzPt<F>* out = nullptr;
     cudaStream_t stream = nullptr;
     uint32_t* info_host = nullptr;     // pinned, 8 words: entries, longest run, S, levels, items per level (4)
+    bool top = false;                  // first (largest) level of an opening: its accumulation is profiled under its own name
 };
 template <class F> void msm_begin(MsmJob<F>& job);
 template <class F> void msm_finish(MsmJob<F>& job);   // job.stream must have been synchronised after msm_begin

@@ -497,6 +497,7 @@ static void open_add_jobs(sb_ctx* c, const sb_pp* pp, const Fr* q, G2Xyzz* res_d
         MsmJob<Fq2>& j = jobs.back();
         size_t k = jobs.size() - 1;
         j.bases = &pp->g2[i + 1]; j.scalars = q + half; j.m = half; j.out = res_dev + i;
+        j.top = (i == 0 && pp->nv >= 8);
         j.stream = c->serial_msm ? c->aux[0] : c->aux[k % sb_ctx::NAUX]; j.info_host = c->msm_info.get() + 8 * k;
     }
 }

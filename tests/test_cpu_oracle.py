@@ -208,3 +208,51 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle/" not in src.replace("oracle/spartan_oracle.cpp synth_r1cs", "") or f == "workload.py", f
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+# ---------------------------------------------------------------- verifier (pairing) on the oracle
+def test_pairing_is_bilinear_and_nondegenerate(oracle):
+    assert oracle.pairing_check(oracle.fr_rand(1, 1)[0], oracle.fr_rand(2, 1)[0])
+    assert oracle.pairing_check(oracle.fr_from_ints([1])[0], oracle.fr_from_ints([FR_MOD - 1])[0])
+
+
+def test_point_decompression_round_trip(oracle):
+    g, h = oracle.generators()
+    for k in oracle.fr_rand(3, 6):
+        p1, p2 = oracle.g1_mul(g, k), oracle.g2_mul(h, k)
+        assert np.array_equal(oracle.deser_g1(oracle.ser_g1(p1)), p1)
+        assert np.array_equal(oracle.deser_g2(oracle.ser_g2(p2)), p2)
+    assert not oracle.deser_g1(oracle.ser_g1(np.zeros(12, dtype=np.uint64))).any()
+
+
+def test_commit_open_verify(oracle):
+    # reference: commitment::verify::sanity (verify.rs:61-95), nv = 6
+    nv = 6
+    pp = oracle.PP.keygen(nv, 21)
+    z = oracle.fr_rand(22, 1 << nv)
+    point = oracle.fr_rand(23, nv)
+    com = pp.commit(z)
+    ev, proofs = pp.open(z, point)
+    assert oracle.pc_verify(pp, com, point, ev, proofs)
+    assert not oracle.pc_verify(pp, com, point, oracle.fr_rand(24, 1)[0], proofs)        # wrong evaluation
+    bad = proofs.copy(); bad[[0, 1]] = bad[[1, 0]]
+    assert not oracle.pc_verify(pp, com, point, ev, bad)                                  # proofs out of order
+
+
+def test_prove_then_verify_accepts_and_rejects(oracle):
+    # reference: ahp::tests::test_small (ahp/tests.rs:73-75: log_n = 8, log_v = 2, density 1) through the
+    # non-interactive driver (benchmark.rs:35-47: prove -> serialize -> deserialize -> verify)
+    log_n, log_v = 8, 2
+    cs = oracle.R1CS.synth(1 << log_v, (1 << log_n) - (1 << log_v), 1, 12345)
+    v, w = cs.vw()
+    pp = oracle.PP.keygen(log_n, 54321)
+    proof, _ = oracle.prove(cs, pp, v, w)
+    assert oracle.verify(cs, pp, v, proof) == 1
+    w_bad = w.copy(); w_bad[5] = oracle.fr_rand(9, 1)[0]
+    bad_proof, _ = oracle.prove(cs, pp, v, w_bad)
+    assert oracle.verify(cs, pp, v, bad_proof) < 0                # WrongWitness
+    v_bad = v.copy(); v_bad[1] = oracle.fr_rand(10, 1)[0]
+    assert oracle.verify(cs, pp, v_bad, proof) < 0                # public input does not match the commitment
+    assert oracle.verify(cs, pp, v, proof[:-1]) == 0              # truncated proof
+    flipped = bytearray(proof); flipped[8 + 48 + 5] ^= 1          # z_rv_0
+    assert oracle.verify(cs, pp, v, bytes(flipped)) <= 0

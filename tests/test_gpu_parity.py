@@ -354,3 +354,25 @@ def test_invalid_arguments(sb, oracle, gpu_ctx):
     st = sb.MLProofForR1CS.prover_init(pk, cs.v, cs.w)
     with pytest.raises(sb.InvalidArgument):      # rounds out of order
         sb.MLProofForR1CS.prover_third_round(st, oracle.fr_rand(1, log_n))
+
+
+# ---------------------------------------------------------------- acceptance: the CPU verifier accepts GPU proofs
+def test_gpu_proof_is_accepted_by_the_verifier(sb, oracle, gpu_ctx):
+    # benchmark.rs:35-47: prove -> serialize -> deserialize -> verify, with the prover on the GPU
+    log_n, log_v = 8, 2
+    cs = sb.SyntheticR1CS(1 << log_v, (1 << log_n) - (1 << log_v), 1, 12345)
+    g, h = oracle.generators()
+    t = oracle.fr_rand(777, log_n)
+    pp = sb.MLPolyCommit.keygen(log_n, g, h, t, ctx=gpu_ctx)
+    pk = sb.MLArgumentForR1CS.index(*cs.mats, ctx=gpu_ctx)
+    proof = sb.MLArgumentForR1CS.prove(pk, cs.v, cs.w, pp)
+    ocs = oracle.R1CS.from_csr(log_n, cs.mats)
+    vp = oracle.PP.keygen_with(log_n, g, h, t)
+    assert oracle.verify(ocs, vp, cs.v, proof) == 1
+    w_bad = cs.w.copy(); w_bad[7] = oracle.fr_rand(3, 1)[0]
+    assert oracle.verify(ocs, vp, cs.v, sb.MLArgumentForR1CS.prove(pk, cs.v, w_bad, pp)) < 0
+    # the commitment scheme alone (commitment::mod.rs commit_open_verify_bench)
+    z = np.concatenate([cs.v, cs.w]); point = oracle.fr_rand(4, log_n)
+    _, com = sb.MLPolyCommit.commit(pp, z)
+    ev, (_, proofs) = sb.MLPolyCommit.open(pp, z, point)
+    assert oracle.pc_verify(vp, com, point, ev, proofs)
