@@ -197,9 +197,28 @@ struct alignas(16) Fq2 {
     SB_HD static Fq2 dbl(const Fq2& a) { return add(a, a); }
     SB_HD static Fq2 neg(const Fq2& a) { Fq2 o; o.c0 = Fq::neg(a.c0); o.c1 = Fq::neg(a.c1); return o; }
     SB_FQ2_FN static Fq2 mul(const Fq2& a, const Fq2& b) {
+#if defined(__CUDA_ARCH__)
+        // Karatsuba with lazy reduction: three 768-bit products, combined before reducing, two Montgomery
+        // reductions instead of three (720 instead of 864 IMAD.WIDE).  Bounds: every product of operands < 2p is
+        // < 4p^2 < 2^764; c1 = a0 b1 + a1 b0 < 2p^2 and c0 = a0 b0 - a1 b1 + p^2 in (0, 2p^2), both < p 2^384.
+        uint32_t t0[24], t1[24], t2[24], u[24], sa[12], sb[12];
+        fq_mul_wide_ptx(t0, a.c0.l, b.c0.l);
+        fq_mul_wide_ptx(t1, a.c1.l, b.c1.l);
+        fq_wide_addn_ptx(sa, a.c0.l, a.c1.l);
+        fq_wide_addn_ptx(sb, b.c0.l, b.c1.l);
+        fq_mul_wide_ptx(t2, sa, sb);
+        fq_wide_sub_ptx(u, t2, t0);
+        fq_wide_sub_ptx(t2, u, t1);
+        fq_wide_subp2_ptx(u, t0, t1);
+        Fq2 o;
+        fq_redc_ptx(o.c0.l, u);
+        fq_redc_ptx(o.c1.l, t2);
+        return o;
+#else
         Fq v0 = Fq::mul(a.c0, b.c0), v1 = Fq::mul(a.c1, b.c1);
         Fq s = Fq::mul(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
         Fq2 o; o.c0 = Fq::sub(v0, v1); o.c1 = Fq::sub(Fq::sub(s, v0), v1); return o;
+#endif
     }
     SB_FQ2_FN static Fq2 sqr(const Fq2& a) {
         Fq s = Fq::add(a.c0, a.c1), d = Fq::sub(a.c0, a.c1), m = Fq::mul(a.c0, a.c1);

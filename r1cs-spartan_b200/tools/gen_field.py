@@ -125,6 +125,118 @@ def gen_sub(N, p):
     return ins
 
 
+
+# ------------------------------------------------------------------ lazy-reduction building blocks (Fq2 products)
+def gen_mul_wide(N):
+    """t[0..2N) = a * b, no reduction.  Even/odd accumulators X (pairs at even limbs) and Y (value Y << 32):
+    row i adds a_even*b_i and a_odd*b_i as two carry chains of N/2 fused pairs each; N^2 IMAD.WIDE in all."""
+    ins = []
+    X = ["x%d" % i for i in range(2 * N + 2)]
+    Y = ["y%d" % i for i in range(2 * N + 2)]
+    wx, wy = set(), set()
+
+    def chain(acc, written, base, mults, bi):
+        """(acc[base+2t], acc[base+2t+1]) += mults[t] * bi, carry into acc[base+N]"""
+        for t, m in enumerate(mults):
+            lo, hi = acc[base + 2 * t], acc[base + 2 * t + 1]
+            al = lo if lo in written else "0"
+            ah = hi if hi in written else "0"
+            ins.append(("mad.lo.cc" if t == 0 else "madc.lo.cc", lo, m, bi, al))
+            ins.append(("madc.hi.cc", hi, m, bi, ah))
+            written.add(lo); written.add(hi)
+        top = acc[base + N]
+        ins.append(("addc", top, top if top in written else "0", "0"))
+        written.add(top)
+
+    a_even = ["a%d" % j for j in range(0, N, 2)]
+    a_odd = ["a%d" % j for j in range(1, N, 2)]
+    for i in range(N):
+        bi = "b%d" % i
+        if i % 2 == 0:
+            chain(X, wx, i, a_even, bi)          # limbs i + 2t (even)
+            chain(Y, wy, i, a_odd, bi)           # limbs i + 2t + 1 -> Y index i + 2t
+        else:
+            chain(Y, wy, i - 1, a_even, bi)      # limbs i + 2t (odd) -> Y index i - 1 + 2t
+            chain(X, wx, i + 1, a_odd, bi)       # limbs i + 1 + 2t (even)
+    # merge: t[k] = X[k] + Y[k-1]
+    for k in range(2 * N):
+        xs = X[k] if X[k] in wx else "0"
+        ys = (Y[k - 1] if (k >= 1 and Y[k - 1] in wy) else "0")
+        op = "add.cc" if k == 0 else ("addc.cc" if k < 2 * N - 1 else "addc")
+        ins.append((op, "t%d" % k, xs, ys))
+    return ins
+
+
+def gen_redc(N, p):
+    """r = (t_lo + m p) / 2^(32N) + t_hi, conditionally reduced: Montgomery reduction of a 2N-limb t < p * 2^(32N).
+    Same even/odd row structure as gen_mul with the a*b_i products removed (N^2 IMAD.WIDE)."""
+    P = limbs(p, N)
+    ins = []
+    X = ["x%d" % i for i in range(N)]
+    Y = ["y%d" % i for i in range(N)]
+    p_even = ["p%d" % j for j in range(0, N, 2)]
+    p_odd = ["p%d" % j for j in range(1, N, 2)]
+    for i in range(N):
+        if i == 0:
+            for k in range(N):
+                ins.append(("mov", X[k], "t%d" % k))
+            E, O = X, Y
+            ins.append(("mul.lo", "m", E[0], "pinv"))
+            for t in range(N // 2):
+                ins.append(("mul.lo", O[2 * t], p_odd[t], "m"))
+                ins.append(("mul.hi", O[2 * t + 1], p_odd[t], "m"))
+        else:
+            # X: offset-0 array with X[0] == 0, Y: offset-1 array.  New offset-0 array = Y (+ X[1] into limb 0),
+            # new offset-1 array = X >> 64
+            ins.append(("add.cc", Y[0], Y[0], X[1]))
+            for k in range(N - 2):
+                ins.append(("addc.cc", X[k], X[k + 2], "0"))
+            ins.append(("addc", X[N - 2], "0", "0"))
+            ins.append(("mov", X[N - 1], "0"))
+            E, O = Y, X
+            ins.append(("mul.lo", "m", E[0], "pinv"))
+            for t in range(N // 2):
+                lo = "mad.lo.cc" if t == 0 else "madc.lo.cc"
+                ins.append((lo, O[2 * t], p_odd[t], "m", O[2 * t]))
+                hi = "madc.hi.cc" if t < N // 2 - 1 else "madc.hi"
+                ins.append((hi, O[2 * t + 1], p_odd[t], "m", O[2 * t + 1]))
+        for t in range(N // 2):
+            lo = "mad.lo.cc" if t == 0 else "madc.lo.cc"
+            ins.append((lo, E[2 * t], p_even[t], "m", E[2 * t]))
+            ins.append(("madc.hi.cc", E[2 * t + 1], p_even[t], "m", E[2 * t + 1]))
+        ins.append(("addc", O[N - 1], O[N - 1], "0"))
+        X, Y = E, O
+    r = ["r%d" % i for i in range(N)]
+    for k in range(N):
+        src = X[k + 1] if k + 1 < N else "0"
+        op = "add.cc" if k == 0 else ("addc.cc" if k < N - 1 else "addc")
+        ins.append((op, r[k], Y[k], src))
+    for k in range(N):                                   # + t_hi
+        op = "add.cc" if k == 0 else ("addc.cc" if k < N - 1 else "addc")
+        ins.append((op, r[k], r[k], "t%d" % (N + k)))
+    gen_final_sub(ins, N, P, r)
+    return ins
+
+
+def gen_wide_op(N, kind, p):
+    """2N-limb r = a - b + p^2 ("subp2"), a - b ("sub"), or N-limb unreduced r = a + b ("addn")."""
+    ins = []
+    if kind == "addn":
+        for k in range(N):
+            op = "add.cc" if k == 0 else ("addc.cc" if k < N - 1 else "addc")
+            ins.append((op, "r%d" % k, "a%d" % k, "b%d" % k))
+        return ins
+    M = 2 * N
+    for k in range(M):
+        op = "sub.cc" if k == 0 else "subc.cc"
+        ins.append((op, "r%d" % k, "a%d" % k, "b%d" % k))
+    if kind == "subp2":
+        P2 = limbs(p * p, M)
+        for k in range(M):
+            op = "add.cc" if k == 0 else "addc.cc"
+            ins.append((op, "r%d" % k, "r%d" % k, hex(P2[k])))
+    return ins
+
 # ------------------------------------------------------------------ emulator
 def emulate(ins, env, strict=True):
     """Execute the abstract stream on 32-bit registers with one carry flag (PTX CC.CF semantics)."""
@@ -162,6 +274,8 @@ def emulate(ins, env, strict=True):
             env[t[1]] = s & M32
             if op.endswith(".cc"):
                 cf = 1 if s < 0 else 0
+        elif op == "mov":
+            env[t[1]] = val(t[2])
         elif op == "selnz":
             env[t[1]] = val(t[2]) if val(t[4]) != 0 else val(t[3])
         elif op == "and":
@@ -182,6 +296,38 @@ def run_emulated(kind, field, a, b):
     env["pinv"] = (-pow(f["p"], -1, 1 << 32)) & M32
     emulate(ins, env)
     return sum(env["r%d" % i] << (32 * i) for i in range(N))
+
+
+def run_emulated_wide(field, a, b):
+    """(a * b) as an integer through gen_mul_wide"""
+    f = FIELDS[field]; N = f["N"]
+    env = {}
+    for i, (x, y) in enumerate(zip(limbs(a, N), limbs(b, N))):
+        env["a%d" % i] = x; env["b%d" % i] = y
+    emulate(gen_mul_wide(N), env)
+    return sum(env["t%d" % i] << (32 * i) for i in range(2 * N))
+
+
+def run_emulated_redc(field, t):
+    f = FIELDS[field]; N = f["N"]
+    env = {}
+    for i, x in enumerate(limbs(t, 2 * N)):
+        env["t%d" % i] = x
+    for i, x in enumerate(limbs(f["p"], N)):
+        env["p%d" % i] = x
+    env["pinv"] = (-pow(f["p"], -1, 1 << 32)) & M32
+    emulate(gen_redc(N, f["p"]), env)
+    return sum(env["r%d" % i] << (32 * i) for i in range(N))
+
+
+def run_emulated_wide_op(field, kind, a, b):
+    f = FIELDS[field]; N = f["N"]
+    M = N if kind == "addn" else 2 * N
+    env = {}
+    for i, (x, y) in enumerate(zip(limbs(a, M), limbs(b, M))):
+        env["a%d" % i] = x; env["b%d" % i] = y
+    emulate(gen_wide_op(N, kind, f["p"]), env, strict=False)
+    return sum(env["r%d" % i] << (32 * i) for i in range(M))
 
 
 # ------------------------------------------------------------------ PTX rendering
@@ -220,6 +366,8 @@ def render(name, ins, N, modc=None):
             s = "%s.u32 %s, %s, %s;" % (op, o(t[1]), o(t[2]), o(t[3]))
         elif op == "and":
             s = "and.b32 %s, %s, %s;" % (o(t[1]), o(t[2]), o(t[3]))
+        elif op == "mov":
+            env[t[1]] = val(t[2])
         elif op == "selnz":
             s = "setp.ne.u32 pz, %s, 0; selp.u32 %s, %s, %s, pz;" % (o(t[4]), o(t[1]), o(t[2]), o(t[3]))
         else:
@@ -232,6 +380,74 @@ def render(name, ins, N, modc=None):
     body = "\n".join(lines)
     return ("__device__ __forceinline__ void %s(uint32_t* __restrict__ r, const uint32_t* a, const uint32_t* b) {\n"
             "  asm(\n%s\n    : %s\n    : %s);\n}\n" % (name, body, outs, ins_))
+
+
+def render_general(name, ins, outputs, inputs, params):
+    """outputs / inputs: lists of (register name, C expression); params: C parameter list"""
+    regs = set()
+    for t in ins:
+        for x in t[1:]:
+            if not (x.startswith("0x") or x == "0"):
+                regs.add(x)
+    onames = [o for o, _ in outputs]; inames = [i for i, _ in inputs]
+    temps = sorted(regs - set(onames) - set(inames))
+    opmap = {}
+    for k, r in enumerate(onames):
+        opmap[r] = "%%%d" % k
+    for k, r in enumerate(inames):
+        opmap[r] = "%%%d" % (len(onames) + k)
+
+    def o(x):
+        if x.startswith("0x") or x == "0":
+            return x
+        return opmap.get(x, x)
+    lines = ["    \"{\\n\\t\""]
+    if temps:
+        lines.append("    \".reg .u32 %s;\\n\\t\"" % ", ".join(temps))
+    lines.append("    \".reg .pred pz;\\n\\t\"")
+    for t in ins:
+        op = t[0]
+        if op in ("mul.lo", "mul.hi"):
+            q = "%s.u32 %s, %s, %s;" % (op, o(t[1]), o(t[2]), o(t[3]))
+        elif op.startswith("mad"):
+            q = "%s.u32 %s, %s, %s, %s;" % (op, o(t[1]), o(t[2]), o(t[3]), o(t[4]))
+        elif op.startswith("add") or op.startswith("sub"):
+            q = "%s.u32 %s, %s, %s;" % (op, o(t[1]), o(t[2]), o(t[3]))
+        elif op == "and":
+            q = "and.b32 %s, %s, %s;" % (o(t[1]), o(t[2]), o(t[3]))
+        elif op == "mov":
+            q = "mov.u32 %s, %s;" % (o(t[1]), o(t[2]))
+        elif op == "selnz":
+            q = "setp.ne.u32 pz, %s, 0; selp.u32 %s, %s, %s, pz;" % (o(t[4]), o(t[1]), o(t[2]), o(t[3]))
+        else:
+            raise ValueError(op)
+        lines.append("    \"%s\\n\\t\"" % q)
+    lines.append("    \"}\"")
+    outs = ", ".join("\"=&r\"(%s)" % e for _, e in outputs)
+    inps = ", ".join("\"r\"(%s)" % e for _, e in inputs)
+    return ("__device__ __forceinline__ void %s(%s) {\n  asm(\n%s\n    : %s\n    : %s);\n}\n"
+            % (name, params, "\n".join(lines), outs, inps))
+
+
+def render_lazy(fname, f):
+    """mul_wide / redc / wide add-sub helpers used by the lazy-reduction Fq2 product"""
+    N, p, U = f["N"], f["p"], fname.upper()
+    parts = []
+    parts.append(render_general("%s_mul_wide_ptx" % fname, gen_mul_wide(N),
+                                [("t%d" % k, "t[%d]" % k) for k in range(2 * N)],
+                                [("a%d" % k, "a[%d]" % k) for k in range(N)] + [("b%d" % k, "b[%d]" % k) for k in range(N)],
+                                "uint32_t* __restrict__ t, const uint32_t* a, const uint32_t* b"))
+    parts.append(render_general("%s_redc_ptx" % fname, gen_redc(N, p),
+                                [("r%d" % k, "r[%d]" % k) for k in range(N)],
+                                [("t%d" % k, "t[%d]" % k) for k in range(2 * N)] + [("p%d" % k, "%s_MOD_C[%d]" % (U, k)) for k in range(N)] +
+                                [("pinv", "%s_MOD_C[%d]" % (U, N))],
+                                "uint32_t* __restrict__ r, const uint32_t* t"))
+    for kind, M in (("subp2", 2 * N), ("sub", 2 * N), ("addn", N)):
+        parts.append(render_general("%s_wide_%s_ptx" % (fname, kind), gen_wide_op(N, kind, p),
+                                    [("r%d" % k, "r[%d]" % k) for k in range(M)],
+                                    [("a%d" % k, "a[%d]" % k) for k in range(M)] + [("b%d" % k, "b[%d]" % k) for k in range(M)],
+                                    "uint32_t* __restrict__ r, const uint32_t* a, const uint32_t* b"))
+    return "\n".join(parts)
 
 
 def main(out_path):
@@ -259,6 +475,8 @@ def main(out_path):
         parts.append(render("%s_mul_ptx" % fname, gen_mul(N, f["p"]), N, modc="%s_MOD_C" % fname.upper()))
         parts.append(render("%s_add_ptx" % fname, gen_add(N, f["p"]), N))
         parts.append(render("%s_sub_ptx" % fname, gen_sub(N, f["p"]), N))
+        if fname == "fq":
+            parts.append(render_lazy(fname, f))
     parts.append("#endif  // __CUDACC__\n")
     open(out_path, "w").write("\n".join(parts))
 
