@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspartan_b200.so")
+LIB_PATH = os.environ.get("SB_LIB_PATH") or os.path.join(_HERE, "libspartan_b200.so")   # SB_LIB_PATH: A/B builds
 _lib = None
 
 SB_OK, SB_EINVAL, SB_ECUDA, SB_ENOMEM, SB_ECOMM, SB_EINTERNAL = range(6)

@@ -186,20 +186,18 @@ def gen_redc(N, p):
                 ins.append(("mul.lo", O[2 * t], p_odd[t], "m"))
                 ins.append(("mul.hi", O[2 * t + 1], p_odd[t], "m"))
         else:
-            # X: offset-0 array with X[0] == 0, Y: offset-1 array.  New offset-0 array = Y (+ X[1] into limb 0),
-            # new offset-1 array = X >> 64
+            # X: offset-0 array with X[0] == 0, Y: offset-1 array.  New offset-0 array E = Y (+ X[1] into limb 0),
+            # new offset-1 array O = X >> 64.  m only needs E[0], so the shift of X (and the carry out of E[0]) is
+            # folded into the p_odd * m chain instead of being propagated by a separate chain of additions.
             ins.append(("add.cc", Y[0], Y[0], X[1]))
-            for k in range(N - 2):
-                ins.append(("addc.cc", X[k], X[k + 2], "0"))
-            ins.append(("addc", X[N - 2], "0", "0"))
-            ins.append(("mov", X[N - 1], "0"))
             E, O = Y, X
-            ins.append(("mul.lo", "m", E[0], "pinv"))
+            ins.append(("mul.lo", "m", E[0], "pinv"))            # does not touch the carry flag
             for t in range(N // 2):
-                lo = "mad.lo.cc" if t == 0 else "madc.lo.cc"
-                ins.append((lo, O[2 * t], p_odd[t], "m", O[2 * t]))
+                a_lo = X[2 * t + 2] if 2 * t + 2 < N else "0"
+                a_hi = X[2 * t + 3] if 2 * t + 3 < N else "0"
+                ins.append(("madc.lo.cc", O[2 * t], p_odd[t], "m", a_lo))
                 hi = "madc.hi.cc" if t < N // 2 - 1 else "madc.hi"
-                ins.append((hi, O[2 * t + 1], p_odd[t], "m", O[2 * t + 1]))
+                ins.append((hi, O[2 * t + 1], p_odd[t], "m", a_hi))
         for t in range(N // 2):
             lo = "mad.lo.cc" if t == 0 else "madc.lo.cc"
             ins.append((lo, E[2 * t], p_even[t], "m", E[2 * t]))
