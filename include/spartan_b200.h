@@ -60,6 +60,12 @@ typedef struct {
     void* user;
 } sb_comm;
 
+/* A ready-made sb_comm for ranks on one node: allgather through a POSIX shared-memory mailbox (about a
+ * microsecond; the payloads are at most a few hundred bytes and already on the host).  `name` is a shm name
+ * ("/something") shared by all ranks; exactly one rank passes create != 0 and must do so before the others attach. */
+sb_status sb_comm_shm_open(const char* name, int rank, int world, int create, sb_comm* out);
+void sb_comm_shm_close(sb_comm* comm);
+
 /* ---- context ---------------------------------------------------------------------------------- */
 sb_status sb_ctx_create(int device, sb_ctx** out);
 sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out);

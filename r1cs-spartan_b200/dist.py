@@ -56,12 +56,54 @@ class TorchComm:
             return 1
 
 
-def sharded_context(device=0):
-    """Context for this rank of the default process group (a plain Context when world size is 1)."""
+class ShmComm:
+    """sb_comm over a POSIX shared-memory mailbox (csrc/comm_shm.cu): all ranks are on one node, the payloads
+    are tiny and already on the host, so this is ~50x lower latency than a device collective.  The process
+    group is only used to agree on the mailbox name and to order creation before attachment."""
+
+    def __init__(self):
+        import os
+        import torch.distributed as dist
+        from .api import load_library
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        if self.world & (self.world - 1):
+            raise ValueError("the hypercube is split on its top variables: world size must be a power of two")
+        names = [None]
+        if self.rank == 0:
+            names[0] = "/sb_b200_%d_%s" % (os.getpid(), os.environ.get("MASTER_PORT", "0"))
+        dist.broadcast_object_list(names, src=0)
+        self.name = names[0]
+        self.struct = CommStruct()
+        L = load_library()
+        if self.rank == 0:
+            st = L.sb_comm_shm_open(self.name.encode(), self.rank, self.world, 1, C.byref(self.struct))
+            if st != 0:
+                raise RuntimeError("cannot create the shared-memory mailbox %s" % self.name)
+        dist.barrier()
+        if self.rank != 0:
+            st = L.sb_comm_shm_open(self.name.encode(), self.rank, self.world, 0, C.byref(self.struct))
+            if st != 0:
+                raise RuntimeError("cannot attach to the shared-memory mailbox %s" % self.name)
+        dist.barrier()
+
+    @property
+    def cb(self):
+        return self.struct.allgather
+
+    def close(self):
+        from .api import load_library
+        load_library().sb_comm_shm_close(C.byref(self.struct))
+
+
+def sharded_context(device=0, comm=None):
+    """Context for this rank of the default process group (a plain Context when world size is 1).
+    comm: "shm" (default; single node) or "nccl"/"torch" (torch.distributed allgather); env SB_COMM overrides."""
+    import os
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return Context(device)
-    return Context(device, comm=TorchComm(device))
+    kind = os.environ.get("SB_COMM") or comm or "shm"
+    return Context(device, comm=ShmComm() if kind == "shm" else TorchComm(device))
 
 
 def slice_weight_mont(t_hi_mont, rho):

@@ -26,7 +26,17 @@ def _worker(rank, world, port, q):
         from r1cs_spartan_b200.workload import limbs_to_mont, mont_to_limbs
         from oracle import binding as ob
 
-        # 1. the hook, exactly as the C library calls it
+        # 1. the hooks, exactly as the C library calls them: torch.distributed (gloo here) and shared memory
+        shm = sbdist.ShmComm()
+        for rep in range(50):
+            nb = 96 + 8 * (rep % 5)
+            send = (C.c_uint8 * nb)(*[(rank * 17 + rep + i) % 251 for i in range(nb)])
+            recv = (C.c_uint8 * (nb * world))()
+            assert shm.cb(shm.struct.user, C.addressof(send), C.addressof(recv), nb) == 0
+            got = bytes(recv)
+            for r in range(world):
+                assert got[r * nb:(r + 1) * nb] == bytes((r * 17 + rep + i) % 251 for i in range(nb)), (rep, r)
+        shm.close()
         comm = sbdist.TorchComm()
         assert (comm.rank, comm.world) == (rank, world)
         for nbytes in (96, 8 * 384 + 32):
