@@ -290,11 +290,11 @@ def run_ours(args):
             t = prof["k_seg_accum_mixed:top<Fq2>"]
             t_ms = t["ms"] / t["launches"]
             t_alg = algorithmic_bytes("k_seg_accum_mixed:top<Fq2>", n, LOG_N, 2)
-            tr = NCU_TRAFFIC.get(("k_seg_accum_mixed:top<Fq2>", LOG_N))
+            ntr = NCU_TRAFFIC.get(("k_seg_accum_mixed:top<Fq2>", LOG_N))
             roofline["largest_launch"] = {"avg_launch_ms": t_ms, "algorithmic_bytes": t_alg, "achieved": t_alg / (t_ms * 1e-3) / 1e9,
                                           "frac": t_alg / (t_ms * 1e-3) / 1e9 / hbm_peak,
-                                          "traffic": tr[0] if tr else None, "traffic_source": tr[1] if tr else None}
-            roofline["traffic"] = tr[0] if tr else None
+                                          "traffic": ntr[0] if ntr else None, "traffic_source": ntr[1] if ntr else None}
+            roofline["traffic"] = ntr[0] if ntr else None
             roofline["traffic_note"] = "dram bytes of the largest launch (ncu --set full); see largest_launch for its own algorithmic bytes"
     # integer-pipe ceiling measured in the same run: dependent-free Montgomery products (2 chains per thread)
     single = sb.Context(local_rank) if world > 1 else ctx
@@ -307,7 +307,7 @@ def run_ours(args):
     extra["roofline_imad"]["peak_fr_gmul_s"] = fr_peak
     # sumcheck kernels alone, L2 flushed between launches
     sc = {}
-    for which, nm, mults, bts in ((0, "sc1_fused_round", 12 / 4.0, 152 / 4.0), (1, "sc1_first_round", 6 / 2.0, (6 * 32 + 32) / 2.0), (2, "sc2_fused_round", 7 / 4.0, (8 * 32 + 4 * 32) / 4.0)):
+    for which, nm, mults, bts in ((0, "sc1_fused_round", 12 / 4.0, 152.0), (1, "sc1_first_round", 6 / 2.0, (6 * 32 + 32) / 2.0), (2, "sc2_fused_round", 7 / 4.0, (8 * 32 + 4 * 32) / 4.0)):
         kms = single.kernel_bench(which, LOG_N, reps=10, flush_l2=True)
         sc[nm] = {"ms": kms, "fr_gmul_s": mults * n / kms / 1e6, "imad_frac": mults * n / kms / 1e6 / fr_peak,
                   "hbm_gb_s": bts * n / kms / 1e6, "hbm_frac": bts * n / kms / 1e6 / hbm_peak}
