@@ -46,7 +46,6 @@ void launch_sc1_round(const Fr* A, const Fr* B, const Fr* C, Fr* Ao, Fr* Bo, Fr*
 void launch_sc2_round(const Fr* M, const Fr* Z, Fr* Mo, Fr* Zo, const Fr* r_dev, size_t m_in, Fr* out3,
                       const RoundWs& ws, cudaStream_t stream);
 // out[k] = T_k[0] + r (T_k[1] - T_k[0]) for up to 3 two-entry tables (final fold; prover.rs:217-219)
-void launch_final_fold(const Fr* const* tabs_dev_ptrs3, int ntab, const Fr* r_dev, Fr* out, cudaStream_t stream);
 void launch_final_fold3(const Fr* A, const Fr* B, const Fr* C, int ntab, const Fr* r_dev, Fr* out, cudaStream_t stream);
 // open.rs:42-45: q[b] = in[2b+1] - in[2b]; r_out[b] = in[2b] + p (in[2b+1] - in[2b])
 void launch_open_fold(const Fr* in, Fr* r_out, Fr* q_out, const Fr* p_dev, size_t half, cudaStream_t stream);

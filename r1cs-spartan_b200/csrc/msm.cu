@@ -57,10 +57,10 @@ __global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict__ scala
 // Chunk size and number of accumulation levels for a longest bucket run of `maxrun` entries: the smallest S
 // with S^levels >= maxrun; two levels while runs are short, more for adversarially skewed scalars.
 // `entries` small (a latency-bound MSM): one more level, i.e. shorter dependent chains and finer work items.
-__host__ __device__ inline void msm_chunking(uint32_t maxrun, uint32_t entries, uint32_t& S, uint32_t& levels) {
+__host__ __device__ inline void msm_chunking(uint32_t maxrun, uint32_t entries, uint32_t l3_below, uint32_t& S, uint32_t& levels) {
     if (maxrun < 1) maxrun = 1;
     levels = maxrun <= 1 ? 1 : maxrun <= (1u << 12) ? 2 : maxrun <= (1u << 18) ? 3 : 4;
-    if (levels == 2 && maxrun > 27 && entries < (1u << 22)) levels = 3;
+    if (levels == 2 && maxrun > 27 && entries < l3_below) levels = 3;
     S = 2;
     while (true) {
         uint64_t pw = 1;
@@ -92,9 +92,10 @@ __device__ inline uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t* sh, u
 // info: entries, longest run, S, levels, items[0..3].
 __global__ void __launch_bounds__(1024) k_scan_plan(const uint32_t* __restrict__ counts, uint32_t B, uint32_t* __restrict__ offsets,
                                                     uint32_t* __restrict__ cursors, uint32_t* __restrict__ plan0, uint32_t* __restrict__ plan1,
-                                                    uint32_t* __restrict__ plan2, uint32_t* __restrict__ plan3, uint32_t* __restrict__ info) {
+                                                    uint32_t* __restrict__ plan2, uint32_t* __restrict__ plan3, uint32_t* __restrict__ info,
+                                                    uint32_t l3_below) {
     __shared__ uint32_t sh[1024];
-    __shared__ uint32_t sh_max, sh_S, sh_levels;
+    __shared__ uint32_t sh_max, sh_S;
     const uint32_t tid = threadIdx.x;
     if (tid == 0) sh_max = 0;
     const uint32_t per = (B + 1023) / 1024;
@@ -109,8 +110,8 @@ __global__ void __launch_bounds__(1024) k_scan_plan(const uint32_t* __restrict__
     if (tid == 0) {
         offsets[B] = total;
         uint32_t S, levels;
-        msm_chunking(sh_max, total, S, levels);
-        sh_S = S; sh_levels = levels;
+        msm_chunking(sh_max, total, l3_below, S, levels);
+        sh_S = S;
         info[0] = total; info[1] = sh_max; info[2] = S; info[3] = levels;
     }
     __syncthreads();
@@ -147,8 +148,9 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __restrict_
 // is down to one point.  Work per thread is bounded by S at every level whatever the scalars are.
 
 // one thread per chunk: out[p] = sum of the chunk's elements
+constexpr int ACC_THREADS = 64;
 template <class F, bool MIXED>
-__global__ void __launch_bounds__(128) k_seg_accum(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
+__global__ void __launch_bounds__(ACC_THREADS) k_seg_accum(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
                                                    const XyzzPt<F>* __restrict__ in_pts, const uint32_t* __restrict__ seg_off,
                                                    const uint32_t* __restrict__ chunk_start, uint32_t nseg, uint32_t S,
                                                    XyzzPt<F>* __restrict__ out) {
@@ -304,6 +306,16 @@ void msm_prepare(const AffinePt<F>* bases_dev, size_t m, MsmBases<F>& out, cudaS
     }
 }
 
+// MSMs with fewer entries than this use three accumulation levels instead of two (SB_MSM_L3_LOG2 overrides)
+static uint32_t msm_l3_below() {
+    static const uint32_t v = [] {
+        const char* e = getenv("SB_MSM_L3_LOG2");
+        int lg = e ? atoi(e) : 19;
+        return lg <= 0 ? 0u : lg >= 32 ? 0xffffffffu : (1u << lg);
+    }();
+    return v;
+}
+
 template <class T>
 static inline void ensure(DevBuf<T>& b, size_t n, cudaStream_t s) { if (b.n < n) b.alloc(n, s); }
 
@@ -323,7 +335,7 @@ void msm_begin(MsmJob<F>& job) {
     SB_CUDA(cudaMemsetAsync(sc.counts.get(), 0, B * sizeof(uint32_t), stream));
     SB_LAUNCH(k_msm_digits, grid_for(m, 256, 8), 256, 0, stream, job.scalars, m, bases.lay, sc.codes.get(), sc.counts.get());
     SB_LAUNCH(k_scan_plan, 1, 1024, 0, stream, sc.counts.get(), B, sc.offsets.get(), sc.cursors.get(), sc.plan[0].get(), sc.plan[1].get(),
-              sc.plan[2].get(), sc.plan[3].get(), sc.info.get());
+              sc.plan[2].get(), sc.plan[3].get(), sc.info.get(), msm_l3_below());
     SB_CUDA(cudaMemcpyAsync(job.info_host, sc.info.get(), 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     SB_LAUNCH(k_msm_scatter, grid_for(total, 256, 8), 256, 0, stream, sc.codes.get(), total, sc.cursors.get(), sc.sorted.get());
 }
@@ -348,12 +360,12 @@ void msm_finish(MsmJob<F>& job) {
     for (uint32_t l = 0; l < levels; l++) {
         XyzzPt<F>* outp = (l % 2 == 0) ? sc.ptsA.get() : sc.ptsB.get();
         const uint32_t* plan = sc.plan[l].get();
-        const int grid = (int)((std::max<uint32_t>(items[l], 1) + 127) / 128);
+        const int grid = (int)((std::max<uint32_t>(items[l], 1) + ACC_THREADS - 1) / ACC_THREADS);
         if (l == 0)
-            SB_LAUNCH_NAMED(job.top ? SB_KNAME(F, "k_seg_accum_mixed:top") : SB_KNAME(F, "k_seg_accum_mixed"), (k_seg_accum<F, true>), grid, 128, 0, stream,
+            SB_LAUNCH_NAMED(job.top ? SB_KNAME(F, "k_seg_accum_mixed:top") : SB_KNAME(F, "k_seg_accum_mixed"), (k_seg_accum<F, true>), grid, ACC_THREADS, 0, stream,
                             bases.tab.get(), sc.sorted.get(), in_pts, seg, plan, B, S, outp);
         else
-            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, false>), grid, 128, 0, stream,
+            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, false>), grid, ACC_THREADS, 0, stream,
                             bases.tab.get(), sc.sorted.get(), in_pts, seg, plan, B, S, outp);
         last_pts = outp; seg = plan; in_pts = outp;
     }

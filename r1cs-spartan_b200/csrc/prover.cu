@@ -794,7 +794,6 @@ size_t sb_proof_size(uint32_t l) {
 }
 
 sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
-    sb_ctx* _c = nullptr;
     try {
         if (!out) throw SbError(SB_EINVAL, "null out pointer");
         int ndev = 0;
@@ -847,7 +846,6 @@ sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
         g_create_error = e.what();
         return SB_EINTERNAL;
     }
-    (void)_c;
 }
 sb_status sb_ctx_create(int device, sb_ctx** out) { return sb_ctx_create_sharded(device, nullptr, out); }
 
