@@ -39,6 +39,7 @@ def lib():
         L.or_keygen.argtypes = [C.c_size_t, C.c_uint64]
         L.or_keygen_with.restype = C.c_void_p
         L.or_pp_from_arrays.restype = C.c_void_p
+        L.or_vp_from_arrays.restype = C.c_void_p
         L.or_prove.restype = C.c_void_p
         L.or_fs_new.restype = C.c_void_p
         for f in ("or_r1cs_n", "or_r1cs_num_public", "or_r1cs_nnz", "or_trace_get"):
@@ -307,6 +308,12 @@ class PP:
     def keygen_with(cls, nv, g, h, t):
         g = _c(g); h = _c(h); t = _c(t, 4)
         return cls(lib().or_keygen_with(C.c_size_t(nv), _p(g), _p(h), _p(t)), nv)
+
+    @classmethod
+    def verifier_only(cls, nv, g, h, g_mask):
+        """VerifierParameter {nv, g, h, g_mask_random} (data_structures.rs:20-25)"""
+        g = _c(g); h = _c(h); g_mask = _c(g_mask, 12)
+        return cls(lib().or_vp_from_arrays(C.c_size_t(nv), _p(g), _p(h), _p(g_mask)), nv)
 
     @classmethod
     def from_arrays(cls, nv, g1_level0, g2_all, h):

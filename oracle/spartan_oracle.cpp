@@ -906,6 +906,12 @@ void* or_pp_from_arrays(size_t nv, const G1Affine* g1_level0, const G2Affine* g2
     for (size_t i = 0; i < nv; i++) { size_t sz = size_t(1) << (nv - i); pp->powers_of_h.emplace_back(g2_all + start, g2_all + start + sz); start += sz; }
     return pp;
 }
+// verifier parameters only (VerifierParameter, data_structures.rs:20-25): enough for or_verify / or_pc_verify
+void* or_vp_from_arrays(size_t nv, const G1Affine* g, const G2Affine* h, const G1Affine* g_mask) {
+    ff_init_all(); PublicParameter* pp = new PublicParameter; pp->nv = nv; pp->g = *g; pp->h = *h;
+    pp->g_mask_random.assign(g_mask, g_mask + nv);
+    return pp;
+}
 void or_pp_free(void* h) { delete (PublicParameter*)h; }
 void or_pp_export_g1(void* h, size_t level, G1Affine* out) { auto& v = ((PublicParameter*)h)->powers_of_g[level]; memcpy(out, v.data(), v.size() * sizeof(G1Affine)); }
 void or_pp_export_g2(void* h, size_t level, G2Affine* out) { auto& v = ((PublicParameter*)h)->powers_of_h[level]; memcpy(out, v.data(), v.size() * sizeof(G2Affine)); }

@@ -404,3 +404,23 @@ def test_adversarial_scalars_do_not_serialise(sb, oracle, gpu_ctx):
     bases = np.stack([oracle.g1_mul(g, ks[i]) for i in range(n)])
     s = np.repeat(oracle.fr_rand(92, 1), n, axis=0)
     assert np.array_equal(sb.multi_scalar_mul(1, bases, s, ctx=gpu_ctx), oracle.msm_g1(bases, s))
+
+
+@pytest.mark.parametrize("log_n", [16, 20])
+def test_full_size_prove_is_accepted(sb, oracle, gpu_ctx, log_n):
+    # BASELINE.json's sizes (2^16, 2^20), where the literal CPU prover is too slow to be the checker: the
+    # size-independent property is prove -> verify (benchmark.rs:35-47) with the CPU pairing verifier, whose
+    # parameters are the g^{t_i} of the GPU keygen, and a proof for a corrupted witness must be rejected.
+    cs = sb.SyntheticR1CS(32, (1 << log_n) - 32, 0, 0x5EED0000 + log_n)
+    g, h = oracle.generators()
+    t = oracle.fr_rand(2024 + log_n, log_n)
+    pp = sb.MLPolyCommit.keygen(log_n, g, h, t, ctx=gpu_ctx)
+    pk = sb.MLArgumentForR1CS.index(*cs.mats, ctx=gpu_ctx)
+    proof = sb.MLArgumentForR1CS.prove(pk, cs.v, cs.w, pp)
+    assert len(proof) == sb.load_library().sb_proof_size(log_n)
+    ocs = oracle.R1CS.from_csr(log_n, cs.mats)
+    vp = oracle.PP.verifier_only(log_n, g, h, pp.g_mask_random())
+    assert oracle.verify(ocs, vp, cs.v, proof) == 1
+    if log_n <= 16:
+        w_bad = cs.w.copy(); w_bad[12345 % len(w_bad)] = oracle.fr_rand(1, 1)[0]
+        assert oracle.verify(ocs, vp, cs.v, sb.MLArgumentForR1CS.prove(pk, cs.v, w_bad, pp)) < 0
