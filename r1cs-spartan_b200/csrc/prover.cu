@@ -40,7 +40,9 @@ struct sb_ctx {
     static constexpr int NBIG = 4;
     cudaStream_t aux[NAUX] = {};
     cudaEvent_t ev_main = nullptr, ev_aux[NAUX] = {};
-    PinnedBuf<uint32_t> msm_info;      // 2 words per ladder level
+    PinnedBuf<uint32_t> msm_info;      // 8 words per ladder level
+    cudaStream_t copy_stream = nullptr; // witness upload that overlaps the commitment (sharded sb_prove)
+    cudaEvent_t ev_copy = nullptr;
     bool serial_msm = false;           // profiling aid: keep every MSM on the main stream
     RoundWs ws{};
     static constexpr int MAIL = 256;
@@ -120,6 +122,8 @@ struct sb_prover {
     ProverStage stage = ST_INIT;
     DevBuf<Fr> z_own;
     const Fr* z = nullptr;    // full z (replicated); z_own or a borrowed sb_witness table (never written)
+    bool z_rest_pending = false;   // sharded sb_prove: the other ranks' slices are still being uploaded on copy_stream
+    ~sb_prover() { if (z_rest_pending && ctx) cudaStreamSynchronize(ctx->copy_stream); }   // never outlive a borrowed buffer
     DevBuf<Fr> abc;           // local slices of Az | Bz | Cz (3 nl)
     DevBuf<Fr> pyr;           // eq suffix pyramid over the local variables (nl), reused full-size (n) for eq(r_x, .)
     DevBuf<Fr> ping, pong;    // folded tables: 3 * nl/2 and 3 * nl/4
@@ -570,7 +574,20 @@ static void prover_setup_common(sb_prover* p, sb_ctx* c, const sb_index* ix, siz
     p->ctx = c; p->idx = ix; p->log_n = ix->log_n; p->n = ix->n; p->loc = ix->loc; p->nl = ix->nl;
     p->log_v = 0; while (((size_t)1 << p->log_v) < nv_len) p->log_v++;
 }
-static sb_prover* prover_init(sb_ctx* c, const sb_index* ix, const void* v, size_t nv_len, const void* w, size_t nw_len) {
+// copy the range [a, b) of the virtual concatenation v || w to z + a
+static void upload_range(Fr* z, const Fr* v, size_t nv_len, const Fr* w, size_t a, size_t b, cudaStream_t st) {
+    if (a < nv_len) {
+        size_t e = std::min(b, nv_len);
+        SB_CUDA(cudaMemcpyAsync(z + a, v + a, (e - a) * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        a = e;
+    }
+    if (a < b) SB_CUDA(cudaMemcpyAsync(z + a, w + (a - nv_len), (b - a) * sizeof(Fr), cudaMemcpyHostToDevice, st));
+}
+
+// defer_rest: (sharded, one-shot sb_prove only) upload this rank's slice now and the rest of z -- which is first
+// needed by the sparse products of the third round -- on the copy stream, overlapping the commitment and the
+// first opening.  The caller's buffers stay borrowed until the call returns, which sb_prove guarantees.
+static sb_prover* prover_init(sb_ctx* c, const sb_index* ix, const void* v, size_t nv_len, const void* w, size_t nw_len, bool defer_rest = false) {
     // prover.rs:114-119
     SB_REQUIRE(nv_len >= 1 && (nv_len & (nv_len - 1)) == 0, "public input should be power of two");
     SB_REQUIRE(nv_len + nw_len == ix->n, "|v| + |w| != number of variables");
@@ -578,10 +595,20 @@ static sb_prover* prover_init(sb_ctx* c, const sb_index* ix, const void* v, size
     std::unique_ptr<sb_prover> p(new sb_prover);
     prover_setup_common(p.get(), c, ix, nv_len);
     p->z_own.alloc(p->n, c->stream);
-    SB_CUDA(cudaMemcpyAsync(p->z_own.get(), v, nv_len * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
-    if (nw_len) SB_CUDA(cudaMemcpyAsync(p->z_own.get() + nv_len, w, nw_len * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+    const Fr* vh = static_cast<const Fr*>(v); const Fr* wh = static_cast<const Fr*>(w);
     g_sb_h2d_bytes += (nv_len + nw_len) * sizeof(Fr);
-    ctx_sync(c);     // caller buffers are only borrowed for the duration of the call
+    if (defer_rest && c->sharded()) {
+        const size_t lo = (size_t)c->rank * p->nl, hi = lo + p->nl;
+        ctx_sync(c);                                   // the allocation is ordered on the main stream
+        upload_range(p->z_own.get(), vh, nv_len, wh, lo, hi, c->stream);
+        upload_range(p->z_own.get(), vh, nv_len, wh, 0, lo, c->copy_stream);
+        upload_range(p->z_own.get(), vh, nv_len, wh, hi, p->n, c->copy_stream);
+        SB_CUDA(cudaEventRecord(c->ev_copy, c->copy_stream));
+        p->z_rest_pending = true;
+    } else {
+        upload_range(p->z_own.get(), vh, nv_len, wh, 0, p->n, c->stream);
+        ctx_sync(c);     // caller buffers are only borrowed for the duration of the call
+    }
     p->z = p->z_own.get();
     return p.release();
 }
@@ -614,6 +641,7 @@ static void prover_third_round(sb_prover* p, const Fr* tor) {
         p->tail_ping.alloc(3 * std::max<size_t>(G / 2, 1), st); p->tail_pong.alloc(3 * std::max<size_t>(G / 4, 1), st);
         launch_eq_pyramid(p->tail_pyr.get(), c->d_mail.get() + sb_ctx::SLOT_VEC + p->loc, (uint32_t)c->glog, st);
     }
+    if (p->z_rest_pending) { SB_CUDA(cudaStreamWaitEvent(st, c->ev_copy, 0)); p->z_rest_pending = false; }
     p->abc.alloc(3 * nl, st);
     SB_CUDA(cudaMemsetAsync(p->abc.get(), 0, 3 * nl * sizeof(Fr), st));
     const SegPlan& pl = p->idx->rows;
@@ -834,6 +862,8 @@ sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
             SB_CUDA(cudaEventCreateWithFlags(&c->ev_aux[i], cudaEventDisableTiming));
         }
         SB_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+        SB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        SB_CUDA(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
         c->ws.block_partials = c->block_partials.get();
         c->ws.ticket = c->ticket.get();
         SB_CUDA(cudaStreamSynchronize(c->stream));
@@ -860,6 +890,8 @@ void sb_ctx_destroy(sb_ctx* c) {
         if (c->ev_aux[i]) cudaEventDestroy(c->ev_aux[i]);
     }
     if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1134,7 +1166,7 @@ static void prove_body(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const v
     if (!proof || *len < need) { *len = need; throw SbError(SB_EINVAL, "proof buffer too small"); }
     double t_all = now_ms(), t0 = t_all;
     double ph[16] = {0};
-    std::unique_ptr<sb_prover> p(resident ? prover_init_resident(ctx, ix, resident) : prover_init(ctx, ix, v, nv_len, w, nw_len));
+    std::unique_ptr<sb_prover> p(resident ? prover_init_resident(ctx, ix, resident) : prover_init(ctx, ix, v, nv_len, w, nw_len, true));
     if (resident) { v = resident->v_host.data(); nv_len = resident->v_host.size(); }
     const Fr* vh = static_cast<const Fr*>(v);
     sbhost::Transcript fs = ix->fs_after_matrices;              // lib.rs:61-64, absorbed once at index time
