@@ -86,16 +86,25 @@ __device__ inline uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t* sh, u
     return incl - v;
 }
 
-// One CTA: exclusive scan of the B bucket counters (-> offsets, cursors), the run statistics, the chunking
-// (S, levels) chosen from them, and the chunk plan of EVERY accumulation level:
-//   plan[l][b] = exclusive scan over buckets of ceil(count_b / S^(l+1)),  plan[l][B] = items of level l.
-// info: entries, longest run, S, levels, items[0..3].
-__global__ void __launch_bounds__(1024) k_scan_plan(const uint32_t* __restrict__ counts, uint32_t B, uint32_t* __restrict__ offsets,
-                                                    uint32_t* __restrict__ cursors, uint32_t* __restrict__ plan0, uint32_t* __restrict__ plan1,
-                                                    uint32_t* __restrict__ plan2, uint32_t* __restrict__ plan3, uint32_t* __restrict__ info,
-                                                    uint32_t l3_below) {
+struct PlanPtrs {
+    uint32_t* offsets; uint32_t* cursors; uint32_t* info;
+    uint32_t* plan[MSM_MAX_LEVELS];
+    uint32_t* hplan[MSM_MAX_HALVINGS];
+};
+constexpr uint32_t AFF_TARGET_RUN = 16;      // pairwise rounds run until the longest bucket run is at most this
+
+// One CTA: exclusive scan of the B bucket counters (-> offsets, cursors), the run statistics, and every plan
+// the accumulation needs, all chosen on the device:
+//   R        pairwise (batched-affine) rounds: 0 when the MSM has fewer than aff_min entries, else the
+//            smallest R with ceil(maxrun / 2^R) <= AFF_TARGET_RUN
+//   hplan[r-1][b] = exclusive scan of ceil(count_b / 2^r), r = 1..R      (layout of the list after round r)
+//   S, levels     chunking of the runs that remain after the R rounds (counts c'_b = ceil(count_b / 2^R))
+//   plan[l][b]    = exclusive scan of ceil(c'_b / S^(l+1))                (chunk plan of accumulation level l)
+// info: entries, longest run, S, levels, items[0..3], R, totals of the R rounds.
+__global__ void __launch_bounds__(1024) k_scan_plan(const uint32_t* __restrict__ counts, uint32_t B, PlanPtrs pp, uint32_t l3_below,
+                                                    uint32_t aff_min) {
     __shared__ uint32_t sh[1024];
-    __shared__ uint32_t sh_max, sh_S;
+    __shared__ uint32_t sh_max, sh_S, sh_R;
     const uint32_t tid = threadIdx.x;
     if (tid == 0) sh_max = 0;
     const uint32_t per = (B + 1023) / 1024;
@@ -106,26 +115,44 @@ __global__ void __launch_bounds__(1024) k_scan_plan(const uint32_t* __restrict__
     atomicMax(&sh_max, mx);
     uint32_t total;
     uint32_t run = block_exclusive_scan_1024(sum, sh, total);
-    for (uint32_t i = beg; i < end; i++) { offsets[i] = run; cursors[i] = run; run += counts[i]; }
+    for (uint32_t i = beg; i < end; i++) { pp.offsets[i] = run; pp.cursors[i] = run; run += counts[i]; }
     if (tid == 0) {
-        offsets[B] = total;
-        uint32_t S, levels;
-        msm_chunking(sh_max, total, l3_below, S, levels);
-        sh_S = S;
-        info[0] = total; info[1] = sh_max; info[2] = S; info[3] = levels;
+        pp.offsets[B] = total;
+        uint32_t R = 0;
+        if (total >= aff_min) while (R < (uint32_t)MSM_MAX_HALVINGS && ((sh_max + (1u << R) - 1) >> R) > AFF_TARGET_RUN) R++;
+        sh_R = R;
+        pp.info[0] = total; pp.info[1] = sh_max; pp.info[8] = R;
     }
     __syncthreads();
-    const uint32_t S = sh_S;
-    uint32_t* plans[MSM_MAX_LEVELS] = {plan0, plan1, plan2, plan3};
+    const uint32_t R = sh_R;
+    uint32_t reduced_total = total;
+    for (uint32_t r = 1; r <= R; r++) {
+        const uint32_t add = (1u << r) - 1;
+        uint32_t s = 0;
+        for (uint32_t i = beg; i < end; i++) s += (counts[i] + add) >> r;
+        uint32_t tot;
+        uint32_t x = block_exclusive_scan_1024(s, sh, tot);
+        for (uint32_t i = beg; i < end; i++) { pp.hplan[r - 1][i] = x; x += (counts[i] + add) >> r; }
+        if (tid == 0) { pp.hplan[r - 1][B] = tot; pp.info[9 + r - 1] = tot; }
+        reduced_total = tot;
+    }
+    if (tid == 0) {
+        uint32_t S, levels;
+        msm_chunking((sh_max + (1u << R) - 1) >> R, reduced_total, l3_below, S, levels);
+        sh_S = S;
+        pp.info[2] = S; pp.info[3] = levels;
+    }
+    __syncthreads();
+    const uint32_t S = sh_S, radd = (1u << R) - 1;
     uint64_t div = 1;
     for (int l = 0; l < MSM_MAX_LEVELS; l++) {
         div *= S;
         uint32_t s = 0;
-        for (uint32_t i = beg; i < end; i++) s += (uint32_t)((counts[i] + div - 1) / div);
+        for (uint32_t i = beg; i < end; i++) s += (uint32_t)((((counts[i] + radd) >> R) + div - 1) / div);
         uint32_t tot;
-        uint32_t r = block_exclusive_scan_1024(s, sh, tot);
-        for (uint32_t i = beg; i < end; i++) { plans[l][i] = r; r += (uint32_t)((counts[i] + div - 1) / div); }
-        if (tid == 0) { plans[l][B] = tot; info[4 + l] = tot; }
+        uint32_t x = block_exclusive_scan_1024(s, sh, tot);
+        for (uint32_t i = beg; i < end; i++) { pp.plan[l][i] = x; x += (uint32_t)((((counts[i] + radd) >> R) + div - 1) / div); }
+        if (tid == 0) { pp.plan[l][B] = tot; pp.info[4 + l] = tot; }
     }
 }
 
@@ -149,11 +176,13 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __restrict_
 
 // one thread per chunk: out[p] = sum of the chunk's elements
 constexpr int ACC_THREADS = 64;
-template <class F, bool MIXED>
+// MODE 0: sum XYZZ partial sums (in_pts);  1: mixed additions of table entries (sorted -> tab, sign in bit 31);
+// MODE 2: mixed additions of an affine list (aff_in), the output of the pairwise rounds
+template <class F, int MODE>
 __global__ void __launch_bounds__(ACC_THREADS) k_seg_accum(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
-                                                   const XyzzPt<F>* __restrict__ in_pts, const uint32_t* __restrict__ seg_off,
-                                                   const uint32_t* __restrict__ chunk_start, uint32_t nseg, uint32_t S,
-                                                   XyzzPt<F>* __restrict__ out) {
+                                                           const AffinePt<F>* __restrict__ aff_in, const XyzzPt<F>* __restrict__ in_pts,
+                                                           const uint32_t* __restrict__ seg_off, const uint32_t* __restrict__ chunk_start,
+                                                           uint32_t nseg, uint32_t S, XyzzPt<F>* __restrict__ out) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= chunk_start[nseg]) return;
     uint32_t lo = 0, hi = nseg;                 // last b with chunk_start[b] <= p (skips empty runs)
@@ -165,16 +194,107 @@ __global__ void __launch_bounds__(ACC_THREADS) k_seg_accum(const AffinePt<F>* __
     uint32_t end = min(beg + S, seg_off[lo + 1]);
     XyzzPt<F> acc = XyzzPt<F>::inf();
     for (uint32_t e = beg; e < end; e++) {
-        if (MIXED) {
+        if (MODE == 1) {
             uint32_t ent = __ldg(&sorted[e]);
             AffinePt<F> q = ldg_elem(&tab[ent & 0x7fffffffu]);
             if (ent & 0x80000000u) q.y = F::neg(q.y);
             acc = XyzzPt<F>::add_mixed(acc, q);
+        } else if (MODE == 2) {
+            acc = XyzzPt<F>::add_mixed(acc, ldg_elem(&aff_in[e]));
         } else {
             acc = XyzzPt<F>::add(acc, ldg_elem(&in_pts[e]));
         }
     }
     st_elem(&out[p], acc);
+}
+
+// ------------------------------------------------------------------ pairwise rounds in affine coordinates
+// One round halves every bucket run: output element j of bucket b is the sum of input elements 2j and 2j+1 of
+// that bucket (or a copy of element 2j when the run is odd).  An affine addition is one inversion plus 2M + 1S;
+// each thread owns AFF_K consecutive output elements and shares ONE inversion among them (Montgomery's trick:
+// +3M per element), so an addition costs about 5M + 1S + (one Fermat inversion) / AFF_K instead of the 8M + 2S of
+// a mixed XYZZ addition.  The exceptional cases of the group law (an input at infinity, P = Q, P = -Q) are
+// handled exactly; their denominator is replaced by 1 so that the shared inversion stays well defined.
+constexpr int AFF_K = 128;
+constexpr int AFF_THREADS = 64;
+enum { PAIR_COPY_P = 0, PAIR_COPY_Q = 1, PAIR_ADD = 2, PAIR_DBL = 3, PAIR_INF = 4 };
+
+template <class F>
+__device__ __forceinline__ int pair_classify(const AffinePt<F>& P, const AffinePt<F>& Q, bool has2, F& d) {
+    d = F::one();
+    if (!has2 || Q.is_inf()) return PAIR_COPY_P;
+    if (P.is_inf()) return PAIR_COPY_Q;
+    if (P.x == Q.x) {
+        if (P.y == Q.y && !P.y.is_zero()) { d = F::dbl(P.y); return PAIR_DBL; }
+        return PAIR_INF;
+    }
+    d = F::sub(Q.x, P.x);
+    return PAIR_ADD;
+}
+
+template <class F, bool FIRST>
+__global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
+                                                              const AffinePt<F>* __restrict__ in_aff, const uint32_t* __restrict__ in_off,
+                                                              const uint32_t* __restrict__ out_off, uint32_t B, uint32_t nthreads,
+                                                              F* __restrict__ prefix, AffinePt<F>* __restrict__ out_aff) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = out_off[B];
+    const uint32_t p0 = t * (uint32_t)AFF_K;
+    if (t >= nthreads || p0 >= total) return;
+    const uint32_t p1 = min(p0 + (uint32_t)AFF_K, total);
+    auto load_in = [&](uint32_t idx) -> AffinePt<F> {
+        if (FIRST) {
+            uint32_t ent = __ldg(&sorted[idx]);
+            AffinePt<F> q = ldg_elem(&tab[ent & 0x7fffffffu]);
+            if (ent & 0x80000000u) q.y = F::neg(q.y);
+            return q;
+        }
+        return ldg_elem(&in_aff[idx]);
+    };
+    uint32_t lo = 0, hi = B;                    // bucket of p0: last b with out_off[b] <= p0
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&out_off[mid]) <= p0) lo = mid; else hi = mid;
+    }
+    // pass 1: prefix products of the denominators
+    uint32_t b = lo;
+    F acc = F::one();
+    for (uint32_t p = p0; p < p1; p++) {
+        while (__ldg(&out_off[b + 1]) <= p) b++;
+        const uint32_t j = p - __ldg(&out_off[b]);
+        const uint32_t ib = __ldg(&in_off[b]), n_in = __ldg(&in_off[b + 1]) - ib;
+        const bool has2 = 2 * j + 1 < n_in;
+        AffinePt<F> P = load_in(ib + 2 * j), Q = has2 ? load_in(ib + 2 * j + 1) : P;
+        F d;
+        pair_classify(P, Q, has2, d);
+        st_elem(&prefix[(size_t)(p - p0) * nthreads + t], acc);
+        acc = F::mul(acc, d);
+    }
+    F inv = F::inv(acc);
+    // pass 2, backwards: 1/d_k = inv * prefix_k, then inv *= d_k
+    for (uint32_t p = p1; p-- > p0;) {
+        while (__ldg(&out_off[b]) > p) b--;
+        const uint32_t j = p - __ldg(&out_off[b]);
+        const uint32_t ib = __ldg(&in_off[b]), n_in = __ldg(&in_off[b + 1]) - ib;
+        const bool has2 = 2 * j + 1 < n_in;
+        AffinePt<F> P = load_in(ib + 2 * j), Q = has2 ? load_in(ib + 2 * j + 1) : P;
+        F d;
+        const int kind = pair_classify(P, Q, has2, d);
+        F dinv = F::mul(inv, ldg_elem(&prefix[(size_t)(p - p0) * nthreads + t]));
+        inv = F::mul(inv, d);
+        AffinePt<F> r;
+        if (kind == PAIR_COPY_P) r = P;
+        else if (kind == PAIR_COPY_Q) r = Q;
+        else if (kind == PAIR_INF) r = AffinePt<F>::inf();
+        else {
+            F lam;
+            if (kind == PAIR_ADD) lam = F::mul(F::sub(Q.y, P.y), dinv);
+            else { F xx = F::sqr(P.x); lam = F::mul(F::add(F::dbl(xx), xx), dinv); }
+            r.x = F::sub(F::sub(F::sqr(lam), P.x), Q.x);
+            r.y = F::sub(F::mul(lam, F::sub(P.x, r.x)), P.y);
+        }
+        st_elem(&out_aff[p], r);
+    }
 }
 
 template <class F>
@@ -319,6 +439,22 @@ static uint32_t msm_l3_below() {
 template <class T>
 static inline void ensure(DevBuf<T>& b, size_t n, cudaStream_t s) { if (b.n < n) b.alloc(n, s); }
 
+// MSMs with at least 2^SB_MSM_AFFINE_LOG2 entries run the pairwise affine rounds first (G2 only: over Fq the shared
+// inversion costs more than it saves).  OFF by default: measured at 2^20 constraints on B200 the rounds LOSE
+// (opening 34.3 ms against 26.2 ms) -- a thread's chain of AFF_K additions plus one Fermat inversion (~2e5
+// instructions) is milliseconds long, and the later rounds have too few threads to fill 148 SMs; a smaller AFF_K
+// makes the inversion share larger than the saving.  Kept (and parity-tested with the threshold forced down)
+// for instances large enough to amortise it and as the base for a cheaper inversion.
+template <class F>
+static uint32_t msm_affine_min() {
+    static const uint32_t v = [] {
+        const char* e = getenv("SB_MSM_AFFINE_LOG2");
+        int lg = e ? atoi(e) : 0;
+        return (lg <= 0 || lg >= 32) ? 0xffffffffu : (1u << lg);
+    }();
+    return sizeof(F) == sizeof(Fq2) ? v : 0xffffffffu;
+}
+
 template <class F>
 void msm_begin(MsmJob<F>& job) {
     const MsmBases<F>& bases = *job.bases;
@@ -330,43 +466,77 @@ void msm_begin(MsmJob<F>& job) {
     const size_t total = (size_t)bases.lay.W * m;             // upper bound on the number of entries
     SB_REQUIRE(total < ((size_t)1 << 31), "msm: too many (window, point) pairs for 31-bit table indices");
     ensure(sc.codes, total, stream); ensure(sc.sorted, total, stream);
-    ensure(sc.counts, B, stream); ensure(sc.offsets, B + 1, stream); ensure(sc.cursors, B, stream); ensure(sc.info, 8, stream);
-    for (int l = 0; l < MSM_MAX_LEVELS; l++) ensure(sc.plan[l], B + 1, stream);
+    ensure(sc.counts, B, stream); ensure(sc.offsets, B + 1, stream); ensure(sc.cursors, B, stream); ensure(sc.info, MSM_INFO_WORDS, stream);
+    PlanPtrs pp{};
+    pp.offsets = sc.offsets.get(); pp.cursors = sc.cursors.get(); pp.info = sc.info.get();
+    for (int l = 0; l < MSM_MAX_LEVELS; l++) { ensure(sc.plan[l], B + 1, stream); pp.plan[l] = sc.plan[l].get(); }
+    const uint32_t aff_min = msm_affine_min<F>();
+    const bool may_halve = total >= aff_min;
+    for (int r = 0; r < MSM_MAX_HALVINGS; r++) {
+        if (may_halve) ensure(sc.hplan[r], B + 1, stream);
+        pp.hplan[r] = sc.hplan[r].get();
+    }
     SB_CUDA(cudaMemsetAsync(sc.counts.get(), 0, B * sizeof(uint32_t), stream));
     SB_LAUNCH(k_msm_digits, grid_for(m, 256, 8), 256, 0, stream, job.scalars, m, bases.lay, sc.codes.get(), sc.counts.get());
-    SB_LAUNCH(k_scan_plan, 1, 1024, 0, stream, sc.counts.get(), B, sc.offsets.get(), sc.cursors.get(), sc.plan[0].get(), sc.plan[1].get(),
-              sc.plan[2].get(), sc.plan[3].get(), sc.info.get(), msm_l3_below());
-    SB_CUDA(cudaMemcpyAsync(job.info_host, sc.info.get(), 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    SB_LAUNCH(k_scan_plan, 1, 1024, 0, stream, sc.counts.get(), B, pp, msm_l3_below(), aff_min);
+    SB_CUDA(cudaMemcpyAsync(job.info_host, sc.info.get(), MSM_INFO_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     SB_LAUNCH(k_msm_scatter, grid_for(total, 256, 8), 256, 0, stream, sc.codes.get(), total, sc.cursors.get(), sc.sorted.get());
 }
 
-// Accumulation levels (chunks of S: level 0 mixed additions of table entries, later levels full additions of the
-// previous level's partial sums), then sum_k k B_k.  Everything was planned on the device in msm_begin; the
-// host only needs the item counts to size the grids.
+// Pairwise affine rounds (large G2 MSMs), accumulation levels (chunks of S: the first level adds affine points
+// into XYZZ partial sums, later levels add partial sums), then sum_k k B_k.  Everything was planned on the
+// device in msm_begin; the host only needs the item counts to size the grids.
 template <class F>
 void msm_finish(MsmJob<F>& job) {
     const MsmBases<F>& bases = *job.bases;
     MsmScratch<F>& sc = bases.scratch;
     cudaStream_t stream = job.stream;
     const uint32_t B = 1u << (bases.lay.c - 1);
-    const uint32_t S = job.info_host[2], levels = job.info_host[3];
+    const uint32_t S = job.info_host[2], levels = job.info_host[3], R = job.info_host[8];
     const uint32_t* items = job.info_host + 4;
-    SB_REQUIRE(levels >= 1 && levels <= (uint32_t)MSM_MAX_LEVELS && S >= 2, "msm: bad plan");
+    const uint32_t* htot = job.info_host + 9;
+    SB_REQUIRE(levels >= 1 && levels <= (uint32_t)MSM_MAX_LEVELS && S >= 2 && R <= (uint32_t)MSM_MAX_HALVINGS, "msm: bad plan");
+    // pairwise rounds
+    const AffinePt<F>* aff = nullptr;
+    const uint32_t* aff_off = nullptr;
+    if (R) {
+        ensure(sc.affA, std::max<uint32_t>(htot[0], 1), stream);
+        if (R > 1) ensure(sc.affB, std::max<uint32_t>(htot[1], 1), stream);
+        const uint32_t nth0 = (htot[0] + AFF_K - 1) / AFF_K;
+        ensure(sc.prefix, (size_t)std::max<uint32_t>(nth0, 1) * AFF_K, stream);
+        const uint32_t* in_off = sc.offsets.get();
+        for (uint32_t r = 0; r < R; r++) {
+            AffinePt<F>* outp = (r % 2 == 0) ? sc.affA.get() : sc.affB.get();
+            const uint32_t nth = (htot[r] + AFF_K - 1) / AFF_K;
+            const int grid = (int)((std::max<uint32_t>(nth, 1) + AFF_THREADS - 1) / AFF_THREADS);
+            if (r == 0)
+                SB_LAUNCH_NAMED(job.top ? SB_KNAME(F, "k_affine_round:top") : SB_KNAME(F, "k_affine_round"), (k_affine_round<F, true>), grid, AFF_THREADS, 0, stream,
+                                bases.tab.get(), sc.sorted.get(), aff, in_off, sc.hplan[r].get(), B, nth, sc.prefix.get(), outp);
+            else
+                SB_LAUNCH_NAMED(job.top ? SB_KNAME(F, "k_affine_round:top") : SB_KNAME(F, "k_affine_round"), (k_affine_round<F, false>), grid, AFF_THREADS, 0, stream,
+                                bases.tab.get(), sc.sorted.get(), aff, in_off, sc.hplan[r].get(), B, nth, sc.prefix.get(), outp);
+            aff = outp; in_off = sc.hplan[r].get();
+        }
+        aff_off = in_off;
+    }
     ensure(sc.ptsA, std::max<size_t>(items[0], 1), stream);
     if (levels > 1) ensure(sc.ptsB, std::max<size_t>(items[1], 1), stream);
-    const uint32_t* seg = sc.offsets.get();
+    const uint32_t* seg = R ? aff_off : sc.offsets.get();
     const XyzzPt<F>* in_pts = nullptr;
     const XyzzPt<F>* last_pts = nullptr;
     for (uint32_t l = 0; l < levels; l++) {
         XyzzPt<F>* outp = (l % 2 == 0) ? sc.ptsA.get() : sc.ptsB.get();
         const uint32_t* plan = sc.plan[l].get();
         const int grid = (int)((std::max<uint32_t>(items[l], 1) + ACC_THREADS - 1) / ACC_THREADS);
-        if (l == 0)
-            SB_LAUNCH_NAMED(job.top ? SB_KNAME(F, "k_seg_accum_mixed:top") : SB_KNAME(F, "k_seg_accum_mixed"), (k_seg_accum<F, true>), grid, ACC_THREADS, 0, stream,
-                            bases.tab.get(), sc.sorted.get(), in_pts, seg, plan, B, S, outp);
+        if (l == 0 && !R)
+            SB_LAUNCH_NAMED(job.top ? SB_KNAME(F, "k_seg_accum_mixed:top") : SB_KNAME(F, "k_seg_accum_mixed"), (k_seg_accum<F, 1>), grid, ACC_THREADS, 0, stream,
+                            bases.tab.get(), sc.sorted.get(), aff, in_pts, seg, plan, B, S, outp);
+        else if (l == 0)
+            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_affine"), (k_seg_accum<F, 2>), grid, ACC_THREADS, 0, stream,
+                            bases.tab.get(), sc.sorted.get(), aff, in_pts, seg, plan, B, S, outp);
         else
-            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, false>), grid, ACC_THREADS, 0, stream,
-                            bases.tab.get(), sc.sorted.get(), in_pts, seg, plan, B, S, outp);
+            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, 0>), grid, ACC_THREADS, 0, stream,
+                            bases.tab.get(), sc.sorted.get(), aff, in_pts, seg, plan, B, S, outp);
         last_pts = outp; seg = plan; in_pts = outp;
     }
     const uint32_t* last_plan = sc.plan[levels - 1].get();
@@ -381,7 +551,7 @@ void msm_finish(MsmJob<F>& job) {
 
 template <class F>
 void msm_run(const MsmBases<F>& bases, const Fr* scalars_dev, size_t m, XyzzPt<F>* out_dev, cudaStream_t stream) {
-    static thread_local PinnedBuf<uint32_t> info(8);
+    static thread_local PinnedBuf<uint32_t> info(MSM_INFO_WORDS);
     MsmJob<F> job;
     job.bases = &bases; job.scalars = scalars_dev; job.m = m; job.out = out_dev; job.stream = stream; job.info_host = info.get();
     msm_begin(job);

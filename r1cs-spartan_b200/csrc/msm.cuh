@@ -26,6 +26,8 @@ struct WinLayout {
 WinLayout msm_layout(size_t m);
 
 constexpr int MSM_MAX_LEVELS = 4;
+constexpr int MSM_MAX_HALVINGS = 8;      // batched-affine pairwise rounds before the XYZZ accumulation
+constexpr int MSM_INFO_WORDS = 20;       // entries, longest run, S, levels, items[4], R, halving totals[8], spare
 
 // Scratch of one MSM over one base table; kept with the table and reused by every proof (allocated on first
 // use, grown on demand), so that the steady state performs no device allocation at all.
@@ -33,6 +35,9 @@ template <class F>
 struct MsmScratch {
     DevBuf<uint32_t> codes, sorted, counts, offsets, cursors, info;
     DevBuf<uint32_t> plan[MSM_MAX_LEVELS];
+    DevBuf<uint32_t> hplan[MSM_MAX_HALVINGS];
+    DevBuf<AffinePt<F>> affA, affB;        // outputs of the pairwise rounds (ping-pong)
+    DevBuf<F> prefix;                      // per-thread prefix products of the simultaneous inversion
     DevBuf<XyzzPt<F>> ptsA, ptsB, block_out;
 };
 
@@ -54,7 +59,7 @@ struct MsmJob {
     size_t m = 0;
     XyzzPt<F>* out = nullptr;
     cudaStream_t stream = nullptr;
-    uint32_t* info_host = nullptr;     // pinned, 8 words: entries, longest run, S, levels, items per level (4)
+    uint32_t* info_host = nullptr;     // pinned, MSM_INFO_WORDS words (see k_scan_plan)
     bool top = false;                  // first (largest) level of an opening: its accumulation is profiled under its own name
 };
 template <class F> void msm_begin(MsmJob<F>& job);

@@ -502,7 +502,7 @@ static void open_add_jobs(sb_ctx* c, const sb_pp* pp, const Fr* q, G2Xyzz* res_d
         size_t k = jobs.size() - 1;
         j.bases = &pp->g2[i + 1]; j.scalars = q + half; j.m = half; j.out = res_dev + i;
         j.top = (i == 0 && pp->nv >= 8);
-        j.stream = c->serial_msm ? c->aux[0] : c->aux[k % sb_ctx::NAUX]; j.info_host = c->msm_info.get() + 8 * k;
+        j.stream = c->serial_msm ? c->aux[0] : c->aux[k % sb_ctx::NAUX]; j.info_host = c->msm_info.get() + MSM_INFO_WORDS * k;
     }
 }
 // Stage 3 -- run every queued job: one stream per job (largest first = highest priority, so the latency-bound
@@ -515,7 +515,7 @@ static void open_run_jobs(sb_ctx* c, std::vector<MsmJob<Fq2>>& jobs) {
     for (int s = 0; s < na; s++) SB_CUDA(cudaStreamWaitEvent(c->aux[s], c->ev_main, 0));
     for (auto& j : jobs) msm_begin(j);
     for (int s = 0; s < na; s++) SB_CUDA(cudaStreamSynchronize(c->aux[s]));
-    g_sb_d2h_bytes += 32 * jobs.size();
+    g_sb_d2h_bytes += 4 * MSM_INFO_WORDS * jobs.size();
     for (auto& j : jobs) msm_finish(j);
     for (int s = 0; s < na; s++) {
         SB_CUDA(cudaEventRecord(c->ev_aux[s], c->aux[s]));
@@ -849,7 +849,7 @@ sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
         SB_CUDA(cudaMemsetAsync(c->ticket.get(), 0, sizeof(unsigned int), c->stream));
         c->d_mail.alloc(sb_ctx::MAIL, c->stream);
         c->h_mail.alloc(sb_ctx::MAIL);
-        c->msm_info.alloc(8 * 64);
+        c->msm_info.alloc(MSM_INFO_WORDS * 64);
         int prio_least = 0, prio_greatest = 0;
         SB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
         for (int i = 0; i < sb_ctx::NAUX; i++) {

@@ -424,3 +424,16 @@ def test_full_size_prove_is_accepted(sb, oracle, gpu_ctx, log_n):
     if log_n <= 16:
         w_bad = cs.w.copy(); w_bad[12345 % len(w_bad)] = oracle.fr_rand(1, 1)[0]
         assert oracle.verify(ocs, vp, cs.v, sb.MLArgumentForR1CS.prove(pk, cs.v, w_bad, pp)) < 0
+
+
+def test_affine_pairwise_rounds_forced_on_small_inputs():
+    # The batched-affine pairwise rounds only switch on for MSMs with >= 2^20 entries; force them on (and the
+    # 3-level chunking off/on) for the small parity cases, in a fresh process because the thresholds are read once.
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in ({"SB_MSM_AFFINE_LOG2": "5"}, {"SB_MSM_AFFINE_LOG2": "3", "SB_MSM_L3_LOG2": "30"}):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
+                            "-k", "msm or commit or open or prove_bytes or interactive or adversarial"],
+                           env=env, cwd=root, capture_output=True, text=True, timeout=1200)
+        assert r.returncode == 0, (extra, r.stdout[-3000:], r.stderr[-2000:])
