@@ -41,6 +41,7 @@ constexpr int SB_SMS = 148;
 extern unsigned long long g_sb_launches;
 extern unsigned long long g_sb_h2d_bytes, g_sb_d2h_bytes;
 extern bool g_sb_prof_on;
+extern int g_sb_prof_tag;
 void sb_prof_begin(const char* name, cudaStream_t stream);
 void sb_prof_end(cudaStream_t stream);
 #define SB_LAUNCH_NAMED(name, kernel, grid, block, smem, stream, ...)  \

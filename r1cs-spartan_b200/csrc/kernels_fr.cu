@@ -10,10 +10,11 @@
 unsigned long long g_sb_launches = 0;
 unsigned long long g_sb_h2d_bytes = 0, g_sb_d2h_bytes = 0;
 bool g_sb_prof_on = false;
+int g_sb_prof_tag = -1;            // free-form tag attached to the records (the MSM code sets log2 of the job size)
 
 // ------------------------------------------------------------------ per-kernel CUDA-event profiler
 namespace {
-struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+struct ProfRec { const char* name; cudaEvent_t e0, e1; int tag; };
 std::vector<ProfRec> g_prof_recs;
 std::vector<cudaEvent_t> g_prof_pool;
 cudaEvent_t prof_event() {
@@ -22,12 +23,12 @@ cudaEvent_t prof_event() {
 }
 }  // namespace
 void sb_prof_begin(const char* name, cudaStream_t stream) {
-    ProfRec r{name, prof_event(), prof_event()};
+    ProfRec r{name, prof_event(), prof_event(), g_sb_prof_tag};
     cudaEventRecord(r.e0, stream);
     g_prof_recs.push_back(r);
 }
 void sb_prof_end(cudaStream_t stream) { cudaEventRecord(g_prof_recs.back().e1, stream); }
-// JSON array [[name, start_ms, end_ms], ...] relative to the first recorded launch; clears the records
+// JSON array [[name, start_ms, end_ms, tag], ...] relative to the first recorded launch; clears the records
 std::string sb_prof_timeline_collect() {
     std::string out = "[";
     if (!g_prof_recs.empty()) {
@@ -38,7 +39,7 @@ std::string sb_prof_timeline_collect() {
             float t0 = 0, t1 = 0;
             cudaEventElapsedTime(&t0, base, r.e0); cudaEventElapsedTime(&t1, base, r.e1);
             char buf[256];
-            snprintf(buf, sizeof buf, "%s[\"%s\", %.4f, %.4f]", first ? "" : ", ", r.name, t0, t1);
+            snprintf(buf, sizeof buf, "%s[\"%s\", %.4f, %.4f, %d]", first ? "" : ", ", r.name, t0, t1, r.tag);
             out += buf; first = false;
         }
         for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1); }

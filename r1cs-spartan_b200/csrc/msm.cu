@@ -54,20 +54,18 @@ __global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict__ scala
     }
 }
 
-// Chunk size and number of accumulation levels for a longest bucket run of `maxrun` entries: the smallest S
-// with S^levels >= maxrun; two levels while runs are short, more for adversarially skewed scalars.
-// `entries` small (a latency-bound MSM): one more level, i.e. shorter dependent chains and finer work items.
-__host__ __device__ inline void msm_chunking(uint32_t maxrun, uint32_t entries, uint32_t l3_below, uint32_t& S, uint32_t& levels) {
-    if (maxrun < 1) maxrun = 1;
-    levels = maxrun <= 1 ? 1 : maxrun <= (1u << 12) ? 2 : maxrun <= (1u << 18) ? 3 : 4;
-    if (levels == 2 && maxrun > 27 && entries < l3_below) levels = 3;
-    S = 2;
-    while (true) {
-        uint64_t pw = 1;
-        for (uint32_t i = 0; i < levels; i++) pw *= S;
-        if (pw >= maxrun) break;
-        S++;
-    }
+// Chunking of the bucket runs.  Level 0 (mixed additions of table entries, the throughput-bound part) works on
+// chunks of S0 entries; every further level sums chunks of S1 partial sums of the level below, until each
+// bucket is down to one point: levels = 1 + ceil(log_S1(ceil(maxrun / S0))).  S0 trades the number of partial
+// sums (entries / S0 full additions, 1.4x the cost of a mixed one, and as many 384-byte points written) against
+// the length of the dependent chain per thread; S1 is small because the later levels are pure latency: a run of
+// r partial sums costs S1 * log_S1(r) dependent additions (r = 2048: 21 with S1 = 3, 90 with two levels of 45;
+// measured at 2^17 constraints: S1 = 3: 15.7 ms, 4: 16.2, 8: 16.9, the old two/three equal levels: 18.0).
+__host__ __device__ inline uint32_t msm_levels(uint32_t maxrun, uint32_t s0, uint32_t s1) {
+    uint32_t levels = 1;
+    uint64_t cover = s0;
+    while (cover < maxrun && levels < (uint32_t)MSM_MAX_LEVELS) { cover *= s1; levels++; }
+    return levels;
 }
 
 __device__ inline uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t* sh, uint32_t& total) {
@@ -98,13 +96,13 @@ constexpr uint32_t AFF_TARGET_RUN = 16;      // pairwise rounds run until the lo
 //   R        pairwise (batched-affine) rounds: 0 when the MSM has fewer than aff_min entries, else the
 //            smallest R with ceil(maxrun / 2^R) <= AFF_TARGET_RUN
 //   hplan[r-1][b] = exclusive scan of ceil(count_b / 2^r), r = 1..R      (layout of the list after round r)
-//   S, levels     chunking of the runs that remain after the R rounds (counts c'_b = ceil(count_b / 2^R))
-//   plan[l][b]    = exclusive scan of ceil(c'_b / S^(l+1))                (chunk plan of accumulation level l)
-// info: entries, longest run, S, levels, items[0..3], R, totals of the R rounds.
-__global__ void __launch_bounds__(1024) k_scan_plan(const uint32_t* __restrict__ counts, uint32_t B, PlanPtrs pp, uint32_t l3_below,
+//   levels        chunking of the runs that remain after the R rounds (counts c'_b = ceil(count_b / 2^R))
+//   plan[l][b]    = exclusive scan of ceil(c'_b / (S0 S1^l))              (chunk plan of accumulation level l)
+// info: see MSM_INFO_WORDS.
+__global__ void __launch_bounds__(1024) k_scan_plan(const uint32_t* __restrict__ counts, uint32_t B, PlanPtrs pp, uint32_t s0, uint32_t s1,
                                                     uint32_t aff_min) {
     __shared__ uint32_t sh[1024];
-    __shared__ uint32_t sh_max, sh_S, sh_R;
+    __shared__ uint32_t sh_max, sh_levels, sh_R;
     const uint32_t tid = threadIdx.x;
     if (tid == 0) sh_max = 0;
     const uint32_t per = (B + 1023) / 1024;
@@ -121,11 +119,10 @@ __global__ void __launch_bounds__(1024) k_scan_plan(const uint32_t* __restrict__
         uint32_t R = 0;
         if (total >= aff_min) while (R < (uint32_t)MSM_MAX_HALVINGS && ((sh_max + (1u << R) - 1) >> R) > AFF_TARGET_RUN) R++;
         sh_R = R;
-        pp.info[0] = total; pp.info[1] = sh_max; pp.info[8] = R;
+        pp.info[0] = total; pp.info[1] = sh_max; pp.info[2] = s0; pp.info[4] = s1; pp.info[5] = R;
     }
     __syncthreads();
     const uint32_t R = sh_R;
-    uint32_t reduced_total = total;
     for (uint32_t r = 1; r <= R; r++) {
         const uint32_t add = (1u << r) - 1;
         uint32_t s = 0;
@@ -133,26 +130,22 @@ __global__ void __launch_bounds__(1024) k_scan_plan(const uint32_t* __restrict__
         uint32_t tot;
         uint32_t x = block_exclusive_scan_1024(s, sh, tot);
         for (uint32_t i = beg; i < end; i++) { pp.hplan[r - 1][i] = x; x += (counts[i] + add) >> r; }
-        if (tid == 0) { pp.hplan[r - 1][B] = tot; pp.info[9 + r - 1] = tot; }
-        reduced_total = tot;
+        if (tid == 0) { pp.hplan[r - 1][B] = tot; pp.info[MSM_INFO_HTOT + r - 1] = tot; }
     }
     if (tid == 0) {
-        uint32_t S, levels;
-        msm_chunking((sh_max + (1u << R) - 1) >> R, reduced_total, l3_below, S, levels);
-        sh_S = S;
-        pp.info[2] = S; pp.info[3] = levels;
+        sh_levels = msm_levels((sh_max + (1u << R) - 1) >> R, s0, s1);
+        pp.info[3] = sh_levels;
     }
     __syncthreads();
-    const uint32_t S = sh_S, radd = (1u << R) - 1;
-    uint64_t div = 1;
-    for (int l = 0; l < MSM_MAX_LEVELS; l++) {
-        div *= S;
+    const uint32_t levels = sh_levels, radd = (1u << R) - 1;
+    uint64_t div = s0;
+    for (uint32_t l = 0; l < levels; l++, div *= s1) {
         uint32_t s = 0;
         for (uint32_t i = beg; i < end; i++) s += (uint32_t)((((counts[i] + radd) >> R) + div - 1) / div);
         uint32_t tot;
         uint32_t x = block_exclusive_scan_1024(s, sh, tot);
         for (uint32_t i = beg; i < end; i++) { pp.plan[l][i] = x; x += (uint32_t)((((counts[i] + radd) >> R) + div - 1) / div); }
-        if (tid == 0) { pp.plan[l][B] = tot; pp.info[4 + l] = tot; }
+        if (tid == 0) { pp.plan[l][B] = tot; pp.info[MSM_INFO_ITEMS + l] = tot; }
     }
 }
 
@@ -182,7 +175,7 @@ template <class F, int MODE>
 __global__ void __launch_bounds__(ACC_THREADS) k_seg_accum(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
                                                            const AffinePt<F>* __restrict__ aff_in, const XyzzPt<F>* __restrict__ in_pts,
                                                            const uint32_t* __restrict__ seg_off, const uint32_t* __restrict__ chunk_start,
-                                                           uint32_t nseg, uint32_t S, XyzzPt<F>* __restrict__ out) {
+                                                           uint32_t nseg, uint32_t /*S*/, XyzzPt<F>* __restrict__ out) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= chunk_start[nseg]) return;
     uint32_t lo = 0, hi = nseg;                 // last b with chunk_start[b] <= p (skips empty runs)
@@ -190,8 +183,12 @@ __global__ void __launch_bounds__(ACC_THREADS) k_seg_accum(const AffinePt<F>* __
         uint32_t mid = (lo + hi) >> 1;
         if (__ldg(&chunk_start[mid]) <= p) lo = mid; else hi = mid;
     }
-    uint32_t beg = seg_off[lo] + (p - chunk_start[lo]) * S;
-    uint32_t end = min(beg + S, seg_off[lo + 1]);
+    // balanced split of the run into its planned number of chunks (each at most S long): the threads of a
+    // warp get chunks of nearly equal length instead of S, S, ..., remainder
+    const uint32_t j = p - chunk_start[lo], nch = chunk_start[lo + 1] - chunk_start[lo];
+    const uint32_t off = seg_off[lo], cnt = seg_off[lo + 1] - off;
+    uint32_t beg = off + (uint32_t)(((uint64_t)j * cnt) / nch);
+    uint32_t end = off + (uint32_t)(((uint64_t)(j + 1) * cnt) / nch);
     XyzzPt<F> acc = XyzzPt<F>::inf();
     for (uint32_t e = beg; e < end; e++) {
         if (MODE == 1) {
@@ -426,15 +423,19 @@ void msm_prepare(const AffinePt<F>* bases_dev, size_t m, MsmBases<F>& out, cudaS
     }
 }
 
-// MSMs with fewer entries than this use three accumulation levels instead of two (SB_MSM_L3_LOG2 overrides)
-static uint32_t msm_l3_below() {
-    static const uint32_t v = [] {
-        const char* e = getenv("SB_MSM_L3_LOG2");
-        int lg = e ? atoi(e) : 19;
-        return lg <= 0 ? 0u : lg >= 32 ? 0xffffffffu : (1u << lg);
-    }();
-    return v;
+// Chunk sizes of the accumulation levels (see msm_levels); SB_MSM_S0 / SB_MSM_S1 override
+static uint32_t msm_env_u32(const char* name, uint32_t dflt, uint32_t lo, uint32_t hi) {
+    const char* e = getenv(name);
+    long v = e ? atol(e) : (long)dflt;
+    return (uint32_t)std::min<long>(std::max<long>(v, lo), hi);
 }
+// S0 by size: throughput-bound jobs take long chunks (fewer partial sums), latency-bound ones short chains
+static uint32_t msm_s0(size_t entries) {
+    static const uint32_t v = msm_env_u32("SB_MSM_S0", 0, 0, 4096);
+    static const uint32_t big = msm_env_u32("SB_MSM_S0_BIG", 48, 2, 4096), small = msm_env_u32("SB_MSM_S0_SMALL", 24, 2, 4096);
+    return v >= 2 ? v : (entries >= ((size_t)1 << 21) ? big : small);
+}
+static uint32_t msm_s1() { static const uint32_t v = msm_env_u32("SB_MSM_S1", 3, 2, 4096); return v; }
 
 template <class T>
 static inline void ensure(DevBuf<T>& b, size_t n, cudaStream_t s) { if (b.n < n) b.alloc(n, s); }
@@ -462,6 +463,7 @@ void msm_begin(MsmJob<F>& job) {
     cudaStream_t stream = job.stream;
     const size_t m = job.m;
     SB_REQUIRE(m == bases.m, "msm: scalar count does not match the prepared bases");
+    if (g_sb_prof_on) { g_sb_prof_tag = 0; while (((size_t)2 << g_sb_prof_tag) <= m) g_sb_prof_tag++; }
     const uint32_t B = 1u << (bases.lay.c - 1);
     const size_t total = (size_t)bases.lay.W * m;             // upper bound on the number of entries
     SB_REQUIRE(total < ((size_t)1 << 31), "msm: too many (window, point) pairs for 31-bit table indices");
@@ -478,7 +480,7 @@ void msm_begin(MsmJob<F>& job) {
     }
     SB_CUDA(cudaMemsetAsync(sc.counts.get(), 0, B * sizeof(uint32_t), stream));
     SB_LAUNCH(k_msm_digits, grid_for(m, 256, 8), 256, 0, stream, job.scalars, m, bases.lay, sc.codes.get(), sc.counts.get());
-    SB_LAUNCH(k_scan_plan, 1, 1024, 0, stream, sc.counts.get(), B, pp, msm_l3_below(), aff_min);
+    SB_LAUNCH(k_scan_plan, 1, 1024, 0, stream, sc.counts.get(), B, pp, msm_s0(total), msm_s1(), aff_min);
     SB_CUDA(cudaMemcpyAsync(job.info_host, sc.info.get(), MSM_INFO_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     SB_LAUNCH(k_msm_scatter, grid_for(total, 256, 8), 256, 0, stream, sc.codes.get(), total, sc.cursors.get(), sc.sorted.get());
 }
@@ -492,10 +494,11 @@ void msm_finish(MsmJob<F>& job) {
     MsmScratch<F>& sc = bases.scratch;
     cudaStream_t stream = job.stream;
     const uint32_t B = 1u << (bases.lay.c - 1);
-    const uint32_t S = job.info_host[2], levels = job.info_host[3], R = job.info_host[8];
-    const uint32_t* items = job.info_host + 4;
-    const uint32_t* htot = job.info_host + 9;
-    SB_REQUIRE(levels >= 1 && levels <= (uint32_t)MSM_MAX_LEVELS && S >= 2 && R <= (uint32_t)MSM_MAX_HALVINGS, "msm: bad plan");
+    const uint32_t S0 = job.info_host[2], levels = job.info_host[3], S1 = job.info_host[4], R = job.info_host[5];
+    const uint32_t* items = job.info_host + MSM_INFO_ITEMS;
+    const uint32_t* htot = job.info_host + MSM_INFO_HTOT;
+    if (g_sb_prof_on) { g_sb_prof_tag = 0; while (((size_t)2 << g_sb_prof_tag) <= job.m) g_sb_prof_tag++; }
+    SB_REQUIRE(levels >= 1 && levels <= (uint32_t)MSM_MAX_LEVELS && S0 >= 2 && S1 >= 2 && R <= (uint32_t)MSM_MAX_HALVINGS, "msm: bad plan");
     // pairwise rounds
     const AffinePt<F>* aff = nullptr;
     const uint32_t* aff_off = nullptr;
@@ -530,23 +533,38 @@ void msm_finish(MsmJob<F>& job) {
         const int grid = (int)((std::max<uint32_t>(items[l], 1) + ACC_THREADS - 1) / ACC_THREADS);
         if (l == 0 && !R)
             SB_LAUNCH_NAMED(job.top ? SB_KNAME(F, "k_seg_accum_mixed:top") : SB_KNAME(F, "k_seg_accum_mixed"), (k_seg_accum<F, 1>), grid, ACC_THREADS, 0, stream,
-                            bases.tab.get(), sc.sorted.get(), aff, in_pts, seg, plan, B, S, outp);
+                            bases.tab.get(), sc.sorted.get(), aff, in_pts, seg, plan, B, S0, outp);
         else if (l == 0)
             SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_affine"), (k_seg_accum<F, 2>), grid, ACC_THREADS, 0, stream,
-                            bases.tab.get(), sc.sorted.get(), aff, in_pts, seg, plan, B, S, outp);
+                            bases.tab.get(), sc.sorted.get(), aff, in_pts, seg, plan, B, S0, outp);
         else
             SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, 0>), grid, ACC_THREADS, 0, stream,
-                            bases.tab.get(), sc.sorted.get(), aff, in_pts, seg, plan, B, S, outp);
+                            bases.tab.get(), sc.sorted.get(), aff, in_pts, seg, plan, B, S1, outp);
         last_pts = outp; seg = plan; in_pts = outp;
+        if (l == 0 && job.tail_stream && job.tail_event) {
+            SB_CUDA(cudaEventRecord(job.tail_event, stream));
+            SB_CUDA(cudaStreamWaitEvent(job.tail_stream, job.tail_event, 0));
+            stream = job.tail_stream;
+        }
     }
     const uint32_t* last_plan = sc.plan[levels - 1].get();
-    const uint32_t L = B >= 8 * RED_THREADS ? 8 : 1;
+    // buckets per thread in the first reduction stage: each thread pays 2 L additions for its running sums and
+    // ~1.5 log2(B) for the multiplication by its offset; small L = short chain, large L = less total work
+    // (measured: L = 2 wins below 2^18 points, L = 4 above; the old L = 8 loses everywhere)
+    static const uint32_t red_env = msm_env_u32("SB_MSM_RED_L", 0, 0, 64);
+    const uint32_t red_l = red_env ? red_env : (job.m >= ((size_t)1 << 18) ? 4u : 2u);
+    const uint32_t L = B >= red_l * RED_THREADS ? red_l : 1;
     const uint32_t nthreads = (B + L - 1) / L;
     const uint32_t nblocks = (nthreads + RED_THREADS - 1) / RED_THREADS;
     ensure(sc.block_out, nblocks, stream);
     const size_t smem = RED_THREADS * sizeof(XyzzPt<F>);
     SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce1"), (k_bucket_reduce1<F>), (int)nblocks, RED_THREADS, smem, stream, last_pts, last_plan, B, L, sc.block_out.get());
     SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce2"), (k_bucket_reduce2<F>), 1, RED_THREADS, smem, stream, sc.block_out.get(), nblocks, job.out);
+    if (stream != job.stream) {
+        SB_CUDA(cudaEventRecord(job.tail_event, stream));
+        SB_CUDA(cudaStreamWaitEvent(job.stream, job.tail_event, 0));
+    }
+    g_sb_prof_tag = -1;
 }
 
 template <class F>

@@ -25,9 +25,10 @@ struct WinLayout {
 };
 WinLayout msm_layout(size_t m);
 
-constexpr int MSM_MAX_LEVELS = 4;
+constexpr int MSM_MAX_LEVELS = 16;
 constexpr int MSM_MAX_HALVINGS = 8;      // batched-affine pairwise rounds before the XYZZ accumulation
-constexpr int MSM_INFO_WORDS = 20;       // entries, longest run, S, levels, items[4], R, halving totals[8], spare
+constexpr int MSM_INFO_WORDS = 32;       // entries, longest run, S0, levels, S1, R, halving totals[8] at 6, items[16] at 14, spare
+constexpr int MSM_INFO_HTOT = 6, MSM_INFO_ITEMS = 14;
 
 // Scratch of one MSM over one base table; kept with the table and reused by every proof (allocated on first
 // use, grown on demand), so that the steady state performs no device allocation at all.
@@ -61,6 +62,11 @@ struct MsmJob {
     cudaStream_t stream = nullptr;
     uint32_t* info_host = nullptr;     // pinned, MSM_INFO_WORDS words (see k_scan_plan)
     bool top = false;                  // first (largest) level of an opening: its accumulation is profiled under its own name
+    // Optional second (high-priority) stream + hand-over event: everything after the first accumulation level --
+    // the latency-bound part of the job -- is queued there, so that it is not dispatched behind the
+    // throughput-bound accumulation kernels of the other jobs; `stream` is joined to it again at the end.
+    cudaStream_t tail_stream = nullptr;
+    cudaEvent_t tail_event = nullptr;
 };
 template <class F> void msm_begin(MsmJob<F>& job);
 template <class F> void msm_finish(MsmJob<F>& job);   // job.stream must have been synchronised after msm_begin

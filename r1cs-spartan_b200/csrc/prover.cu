@@ -37,13 +37,16 @@ struct sb_ctx {
     // their size) run at the highest priority so that their short kernels always find a slot; the four large,
     // throughput-bound levels follow in decreasing size.
     static constexpr int NAUX = 32;
-    static constexpr int NBIG = 4;
-    cudaStream_t aux[NAUX] = {};
+    static constexpr int NBIG = 8;     // jobs 0..NBIG-1 of a ladder are the throughput-bound ones (2^-8 of the work is below)
+    cudaStream_t aux[NAUX] = {};       // one per MSM job of a ladder; [0, NBIG) low priority, the rest high
+    cudaStream_t tail[NBIG] = {};      // high priority: the latency-bound tails of the big jobs
+    cudaEvent_t ev_tail[NBIG] = {};
     cudaEvent_t ev_main = nullptr, ev_aux[NAUX] = {};
     PinnedBuf<uint32_t> msm_info;      // 8 words per ladder level
     cudaStream_t copy_stream = nullptr; // witness upload that overlaps the commitment (sharded sb_prove)
     cudaEvent_t ev_copy = nullptr;
     bool serial_msm = false;           // profiling aid: keep every MSM on the main stream
+    int n_tails = 0;                   // SB_MSM_TAILS: the n largest jobs of a ladder run their tails on high-priority streams
     RoundWs ws{};
     static constexpr int MAIL = 256;
     // mailbox slots
@@ -503,6 +506,7 @@ static void open_add_jobs(sb_ctx* c, const sb_pp* pp, const Fr* q, G2Xyzz* res_d
         j.bases = &pp->g2[i + 1]; j.scalars = q + half; j.m = half; j.out = res_dev + i;
         j.top = (i == 0 && pp->nv >= 8);
         j.stream = c->serial_msm ? c->aux[0] : c->aux[k % sb_ctx::NAUX]; j.info_host = c->msm_info.get() + MSM_INFO_WORDS * k;
+        if (!c->serial_msm && k < (size_t)c->n_tails) { j.tail_stream = c->tail[k]; j.tail_event = c->ev_tail[k]; }
     }
 }
 // Stage 3 -- run every queued job: one stream per job (largest first = highest priority, so the latency-bound
@@ -513,10 +517,19 @@ static void open_run_jobs(sb_ctx* c, std::vector<MsmJob<Fq2>>& jobs) {
     SB_CUDA(cudaEventRecord(c->ev_main, st));
     const int na = (int)std::min<size_t>(jobs.size(), sb_ctx::NAUX);
     for (int s = 0; s < na; s++) SB_CUDA(cudaStreamWaitEvent(c->aux[s], c->ev_main, 0));
+    // SB_MSM_ORDER: 2 (default) = wait per job, largest first (its accumulation starts while the smaller jobs
+    // are still sorting; 16.9 against 18.0 ms at 2^17); 0 = all sorts, one wait, accumulations largest first;
+    // 1 = accumulations smallest first (measured slower: the large jobs start late)
+    static const int order = getenv("SB_MSM_ORDER") ? atoi(getenv("SB_MSM_ORDER")) : 2;
     for (auto& j : jobs) msm_begin(j);
-    for (int s = 0; s < na; s++) SB_CUDA(cudaStreamSynchronize(c->aux[s]));
     g_sb_d2h_bytes += 4 * MSM_INFO_WORDS * jobs.size();
-    for (auto& j : jobs) msm_finish(j);
+    if (order == 2) {
+        for (auto& j : jobs) { SB_CUDA(cudaStreamSynchronize(j.stream)); msm_finish(j); }
+    } else {
+        for (int s = 0; s < na; s++) SB_CUDA(cudaStreamSynchronize(c->aux[s]));
+        if (order == 1) for (size_t k = jobs.size(); k-- > 0;) msm_finish(jobs[k]);
+        else for (auto& j : jobs) msm_finish(j);
+    }
     for (int s = 0; s < na; s++) {
         SB_CUDA(cudaEventRecord(c->ev_aux[s], c->aux[s]));
         SB_CUDA(cudaStreamWaitEvent(st, c->ev_aux[s], 0));
@@ -852,14 +865,22 @@ sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
         c->msm_info.alloc(MSM_INFO_WORDS * 64);
         int prio_least = 0, prio_greatest = 0;
         SB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        // Optional priorities (both OFF by default, see DESIGN.md "what was tried"): SB_MSM_TAILS=n queues the
+        // latency-bound tails (everything after the first accumulation level) of the n largest jobs of a ladder on
+        // high-priority streams; SB_MSM_SMALL_HI=1 runs the small jobs entirely at high priority.  Measured at
+        // 2^20: the tails then overlap the other jobs' accumulation as intended, but their CTAs (2 warps, 238
+        // registers, mostly idle lanes in the tree and double-and-add phases) hold a quarter of an SM each for
+        // milliseconds and the accumulation kernels lose more than the tails gain (70.5 against 66.6 ms).
+        c->n_tails = getenv("SB_MSM_TAILS") ? std::min(std::max(atoi(getenv("SB_MSM_TAILS")), 0), (int)sb_ctx::NBIG) : 0;
+        const bool small_hi = getenv("SB_MSM_SMALL_HI") && atoi(getenv("SB_MSM_SMALL_HI")) != 0;
+        const int prio_hi = prio_greatest;
         for (int i = 0; i < sb_ctx::NAUX; i++) {
-            // SB_STREAM_PRIORITIES=1: small (latency-bound) levels at the highest priority, the four large ones
-            // below them in decreasing size; default: one priority for all (measured faster)
-            static const bool use_prio = getenv("SB_STREAM_PRIORITIES") && atoi(getenv("SB_STREAM_PRIORITIES")) != 0;
-            int prio = !use_prio ? prio_least : (i >= sb_ctx::NBIG ? prio_greatest : prio_greatest + 1 + i);
-            if (prio > prio_least) prio = prio_least;
-            SB_CUDA(cudaStreamCreateWithPriority(&c->aux[i], cudaStreamNonBlocking, prio));
+            SB_CUDA(cudaStreamCreateWithPriority(&c->aux[i], cudaStreamNonBlocking, (small_hi && i >= sb_ctx::NBIG) ? prio_hi : prio_least));
             SB_CUDA(cudaEventCreateWithFlags(&c->ev_aux[i], cudaEventDisableTiming));
+        }
+        for (int i = 0; i < sb_ctx::NBIG; i++) {
+            SB_CUDA(cudaStreamCreateWithPriority(&c->tail[i], cudaStreamNonBlocking, prio_hi));
+            SB_CUDA(cudaEventCreateWithFlags(&c->ev_tail[i], cudaEventDisableTiming));
         }
         SB_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
         SB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -888,6 +909,10 @@ void sb_ctx_destroy(sb_ctx* c) {
     for (int i = 0; i < sb_ctx::NAUX; i++) {
         if (c->aux[i]) { cudaStreamSynchronize(c->aux[i]); cudaStreamDestroy(c->aux[i]); }
         if (c->ev_aux[i]) cudaEventDestroy(c->ev_aux[i]);
+    }
+    for (int i = 0; i < sb_ctx::NBIG; i++) {
+        if (c->tail[i]) { cudaStreamSynchronize(c->tail[i]); cudaStreamDestroy(c->tail[i]); }
+        if (c->ev_tail[i]) cudaEventDestroy(c->ev_tail[i]);
     }
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);

@@ -424,16 +424,25 @@ def test_full_size_prove_is_accepted(sb, oracle, gpu_ctx, log_n):
     if log_n <= 16:
         w_bad = cs.w.copy(); w_bad[12345 % len(w_bad)] = oracle.fr_rand(1, 1)[0]
         assert oracle.verify(ocs, vp, cs.v, sb.MLArgumentForR1CS.prove(pk, cs.v, w_bad, pp)) < 0
+    # the commitment scheme alone on a random table of the same size (commitment/mod.rs:66-83
+    # commit_open_verify_bench): commit, open at a random point, pairing check; a wrong value must fail
+    table = oracle.fr_rand(5 + log_n, 1 << log_n); point = oracle.fr_rand(6 + log_n, log_n)
+    _, com = sb.MLPolyCommit.commit(pp, table)
+    ev, (_, proofs) = sb.MLPolyCommit.open(pp, table, point)
+    assert oracle.pc_verify(vp, com, point, ev, proofs)
+    assert not oracle.pc_verify(vp, com, point, oracle.fr_rand(7, 1)[0], proofs)
 
 
-def test_affine_pairwise_rounds_forced_on_small_inputs():
-    # The batched-affine pairwise rounds only switch on for MSMs with >= 2^20 entries; force them on (and the
-    # 3-level chunking off/on) for the small parity cases, in a fresh process because the thresholds are read once.
+def test_msm_knobs_forced_on_small_inputs():
+    # The batched-affine pairwise rounds are off by default and the deep accumulation levels only appear with
+    # long bucket runs; force both on the small parity cases (tiny chunk sizes = many levels), in a fresh
+    # process because the knobs are read once.
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for extra in ({"SB_MSM_AFFINE_LOG2": "5"}, {"SB_MSM_AFFINE_LOG2": "3", "SB_MSM_L3_LOG2": "30"}):
+    for extra in ({"SB_MSM_AFFINE_LOG2": "5"}, {"SB_MSM_AFFINE_LOG2": "3", "SB_MSM_S0": "3", "SB_MSM_S1": "2"},
+                  {"SB_MSM_S0": "2", "SB_MSM_S1": "2", "SB_MSM_RED_L": "8", "SB_MSM_ORDER": "0"}):
         env = dict(os.environ, **extra)
         r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
-                            "-k", "msm or commit or open or prove_bytes or interactive or adversarial"],
+                            "-k", "msm_matches or structured or commit_and_open or prove_bytes or adversarial"],
                            env=env, cwd=root, capture_output=True, text=True, timeout=1200)
         assert r.returncode == 0, (extra, r.stdout[-3000:], r.stderr[-2000:])
