@@ -7,6 +7,7 @@ The directory name follows the project naming; Python code imports it as `r1cs_s
     api.py       ctypes mirror of the reference's prover-facing API
     workload.py  the reference's synthetic benchmark circuit
     dist.py      one-process-per-GPU plumbing (torch.distributed) for the sharded prover
+    wire.py      arkworks CanonicalSerialize layouts of Proof / IndexPK / PublicParameter (exchange with a Rust build)
 """
 from .api import (  # noqa: F401
     Context, CudaError, InvalidArgument, IndexPK, MLArgumentForR1CS, MLPolyCommit, MLProofForR1CS, PublicParameter,

@@ -406,6 +406,33 @@ def test_adversarial_scalars_do_not_serialise(sb, oracle, gpu_ctx):
     assert np.array_equal(sb.multi_scalar_mul(1, bases, s, ctx=gpu_ctx), oracle.msm_g1(bases, s))
 
 
+def test_wire_formats_carry_keys_and_proofs(sb, oracle, gpu_ctx):
+    # keys made on the GPU are written in the reference's key-cache layout
+    # (commitment/mod.rs:48-62, uncompressed), read back, uploaded with sb_pp_load, and must give the same proof;
+    # the proof itself parses into the reference's Proof fields and re-serializes to the same bytes.
+    from r1cs_spartan_b200 import wire
+    log_n = 6
+    cs = sb.SyntheticR1CS(8, (1 << log_n) - 8, 5, 4242)
+    g, h = oracle.generators()
+    pp = sb.MLPolyCommit.keygen(log_n, g, h, oracle.fr_rand(17, log_n), keep_all_levels=True, ctx=gpu_ctx)
+    pk = sb.MLArgumentForR1CS.index(*cs.mats, ctx=gpu_ctx)
+    proof = sb.MLArgumentForR1CS.prove(pk, cs.v, cs.w, pp)
+    pg = [pp.export(1, i) for i in range(log_n)]; ph = [pp.export(2, i) for i in range(log_n)]
+    cache = wire.key_cache_to_bytes([(dict(nv=log_n, powers_of_g=pg, powers_of_h=ph, g=g, h=h),
+                                      dict(nv=log_n, g=g, h=h, g_mask_random=pp.g_mask_random()))])
+    (kp, kv), = wire.key_cache_from_bytes(cache, check=True)
+    pp2 = sb.MLPolyCommit.load(log_n, kp["powers_of_g"][0], kp["powers_of_h"], kp["h"], ctx=gpu_ctx)
+    mats, ln = wire.index_from_bytes(wire.index_to_bytes(cs.mats, log_n))
+    pk2 = sb.MLArgumentForR1CS.index(*mats, ctx=gpu_ctx)
+    assert sb.MLArgumentForR1CS.prove(pk2, cs.v, cs.w, pp2) == proof
+    parsed = wire.Proof.from_bytes(proof)
+    assert parsed.to_bytes() == proof and parsed.commitment_nv == log_n
+    _, com = sb.MLPolyCommit.commit(pp, np.concatenate([cs.v, cs.w]))
+    assert np.array_equal(parsed.commitment, com)
+    vp = oracle.PP.verifier_only(log_n, kv["g"], kv["h"], kv["g_mask_random"])
+    assert oracle.verify(oracle.R1CS.from_csr(log_n, mats), vp, cs.v, proof) == 1
+
+
 @pytest.mark.parametrize("log_n", [16, 20])
 def test_full_size_prove_is_accepted(sb, oracle, gpu_ctx, log_n):
     # BASELINE.json's sizes (2^16, 2^20), where the literal CPU prover is too slow to be the checker: the
