@@ -175,7 +175,7 @@ template <class F, int MODE>
 __global__ void __launch_bounds__(ACC_THREADS) k_seg_accum(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
                                                            const AffinePt<F>* __restrict__ aff_in, const XyzzPt<F>* __restrict__ in_pts,
                                                            const uint32_t* __restrict__ seg_off, const uint32_t* __restrict__ chunk_start,
-                                                           uint32_t nseg, uint32_t /*S*/, XyzzPt<F>* __restrict__ out) {
+                                                           uint32_t nseg, uint32_t S, XyzzPt<F>* __restrict__ out) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= chunk_start[nseg]) return;
     uint32_t lo = 0, hi = nseg;                 // last b with chunk_start[b] <= p (skips empty runs)
@@ -187,8 +187,13 @@ __global__ void __launch_bounds__(ACC_THREADS) k_seg_accum(const AffinePt<F>* __
     // warp get chunks of nearly equal length instead of S, S, ..., remainder
     const uint32_t j = p - chunk_start[lo], nch = chunk_start[lo + 1] - chunk_start[lo];
     const uint32_t off = seg_off[lo], cnt = seg_off[lo + 1] - off;
-    uint32_t beg = off + (uint32_t)(((uint64_t)j * cnt) / nch);
-    uint32_t end = off + (uint32_t)(((uint64_t)(j + 1) * cnt) / nch);
+    uint32_t beg, end;
+    if (S & 0x80000000u) {                      // experiment knob SB_MSM_BALANCED=0: chunks of S, S, ..., remainder
+        beg = off + j * (S & 0x7fffffffu); end = min(beg + (S & 0x7fffffffu), off + cnt);
+    } else {
+        beg = off + (uint32_t)(((uint64_t)j * cnt) / nch);
+        end = off + (uint32_t)(((uint64_t)(j + 1) * cnt) / nch);
+    }
     XyzzPt<F> acc = XyzzPt<F>::inf();
     for (uint32_t e = beg; e < end; e++) {
         if (MODE == 1) {
@@ -494,11 +499,12 @@ void msm_finish(MsmJob<F>& job) {
     MsmScratch<F>& sc = bases.scratch;
     cudaStream_t stream = job.stream;
     const uint32_t B = 1u << (bases.lay.c - 1);
-    const uint32_t S0 = job.info_host[2], levels = job.info_host[3], S1 = job.info_host[4], R = job.info_host[5];
+    static const uint32_t unbalanced = msm_env_u32("SB_MSM_BALANCED", 1, 0, 1) ? 0u : 0x80000000u;
+    const uint32_t S0 = job.info_host[2] | unbalanced, levels = job.info_host[3], S1 = job.info_host[4] | unbalanced, R = job.info_host[5];
     const uint32_t* items = job.info_host + MSM_INFO_ITEMS;
     const uint32_t* htot = job.info_host + MSM_INFO_HTOT;
     if (g_sb_prof_on) { g_sb_prof_tag = 0; while (((size_t)2 << g_sb_prof_tag) <= job.m) g_sb_prof_tag++; }
-    SB_REQUIRE(levels >= 1 && levels <= (uint32_t)MSM_MAX_LEVELS && S0 >= 2 && S1 >= 2 && R <= (uint32_t)MSM_MAX_HALVINGS, "msm: bad plan");
+    SB_REQUIRE(levels >= 1 && levels <= (uint32_t)MSM_MAX_LEVELS && (S0 & 0x7fffffffu) >= 2 && (S1 & 0x7fffffffu) >= 2 && R <= (uint32_t)MSM_MAX_HALVINGS, "msm: bad plan");
     // pairwise rounds
     const AffinePt<F>* aff = nullptr;
     const uint32_t* aff_off = nullptr;

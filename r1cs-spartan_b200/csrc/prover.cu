@@ -15,6 +15,7 @@
 #include <chrono>
 #include <memory>
 #include <mutex>
+#include <thread>
 
 using sbhost::Bytes;
 
@@ -269,28 +270,42 @@ static sb_index* index_create(sb_ctx* c, uint32_t log_n, const sb_csr* mats[3]) 
         SB_REQUIRE(ix->nnz[k] == 0 || (m->col && m->val), "null col/val");
         for (size_t e = 0; e < ix->nnz[k]; e++) SB_REQUIRE(m->col[e] < n, "sparse index out of bound");
     }
-    // transcript prefix: feed(matrix_a), feed(matrix_b), feed(matrix_c)  (lib.rs:61-64)
-    {
-        Bytes buf; buf.reserve(1 << 20);
+    // transcript prefix: feed(matrix_a), feed(matrix_b), feed(matrix_c)  (lib.rs:61-64).  Blake2s is a serial
+    // chain over ~40 bytes per non-zero entry (the largest host-side cost of indexing), so it runs on its own
+    // thread while this one builds and uploads the plans; both only read the caller's arrays.
+    sb_index* ixp = ix.get();
+    std::thread hasher([ixp, mats, n] {
+        std::vector<uint8_t> buf((1 << 20) + 64);
+        size_t fill = 0;
+        auto put64 = [&](uint64_t v) { memcpy(buf.data() + fill, &v, 8); fill += 8; };      // little-endian host
         for (int k = 0; k < 3; k++) {
             const sb_csr* m = mats[k];
             const Fr* val = static_cast<const Fr*>(m->val);
-            buf.clear(); sbhost::put_u64(buf, n);
+            Fr last_m = Fr::zero(), last_c = Fr::zero();      // circuits repeat a few coefficients: convert once
+            put64(n);
             for (size_t r = 0; r < n; r++) {
-                sbhost::put_u64(buf, m->row_ptr[r + 1] - m->row_ptr[r]);
-                for (uint64_t e = m->row_ptr[r]; e < m->row_ptr[r + 1]; e++) { sbhost::put_fr(buf, val[e]); sbhost::put_u64(buf, m->col[e]); }
-                if (buf.size() >= (1 << 20)) { ix->fs_after_matrices.feed(buf); buf.clear(); }
+                put64(m->row_ptr[r + 1] - m->row_ptr[r]);
+                for (uint64_t e = m->row_ptr[r]; e < m->row_ptr[r + 1]; e++) {
+                    if (!(val[e] == last_m)) { last_m = val[e]; last_c = last_m.to_canonical(); }
+                    memcpy(buf.data() + fill, last_c.l, 32); fill += 32;
+                    put64(m->col[e]);
+                    if (fill >= (1 << 20)) { ixp->fs_after_matrices.feed(buf.data(), fill); fill = 0; }
+                }
+                if (fill >= (1 << 20)) { ixp->fs_after_matrices.feed(buf.data(), fill); fill = 0; }
             }
-            sbhost::put_u64(buf, n);      // num_constraints
-            ix->fs_after_matrices.feed(buf);
+            put64(n);      // num_constraints
+            ixp->fs_after_matrices.feed(buf.data(), fill); fill = 0;
         }
-    }
+    });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{hasher};
     // row plan: segments k nl + (row - lo) for the rows of this rank's slice
     {
         std::vector<uint64_t> seg_ptr(3 * nl + 1);
         std::vector<uint32_t> gather;
         std::vector<Fr> val;
-        size_t o = 0;
+        size_t o = 0, local_nnz = 0;
+        for (int k = 0; k < 3; k++) local_nnz += mats[k]->row_ptr[hi] - mats[k]->row_ptr[lo];
+        gather.reserve(local_nnz); val.reserve(local_nnz);
         for (int k = 0; k < 3; k++) {
             const sb_csr* m = mats[k];
             const Fr* v = static_cast<const Fr*>(m->val);
@@ -325,6 +340,7 @@ static sb_index* index_create(sb_ctx* c, uint32_t log_n, const sb_csr* mats[3]) 
         }
         build_plan(c, nl, seg_ptr, gather, val, ix->cols);
     }
+    hasher.join();
     return ix.release();
 }
 

@@ -28,6 +28,8 @@ class Blake2s256 {
         const uint8_t* p = static_cast<const uint8_t*>(data);
         while (len) {
             if (fill_ == 64) { count_ += 64; round_block(block_, false); fill_ = 0; }
+            // whole blocks straight from the input (the last block always stays buffered: it may be the final one)
+            while (fill_ == 0 && len > 64) { count_ += 64; round_block(p, false); p += 64; len -= 64; }
             size_t take = 64 - fill_; if (take > len) take = len;
             memcpy(block_ + fill_, p, take);
             fill_ += take; p += take; len -= take;
@@ -46,33 +48,37 @@ class Blake2s256 {
     static constexpr uint32_t kIV[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au,
                                         0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
     static inline uint32_t ror(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
-    static inline void mix(uint32_t* v, int a, int b, int c, int d, uint32_t x, uint32_t y) {
+    static inline __attribute__((always_inline)) void mix(uint32_t* v, int a, int b, int c, int d, uint32_t x, uint32_t y) {
         v[a] += v[b] + x; v[d] = ror(v[d] ^ v[a], 16);
         v[c] += v[d];     v[b] = ror(v[b] ^ v[c], 12);
         v[a] += v[b] + y; v[d] = ror(v[d] ^ v[a], 8);
         v[c] += v[d];     v[b] = ror(v[b] ^ v[c], 7);
     }
+    // one round with its message schedule as compile-time constants (the indices fold into register names)
+#define SB_B2_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15)       \
+    mix(v, 0, 4, 8, 12, m[s0], m[s1]);   mix(v, 1, 5, 9, 13, m[s2], m[s3]);                       \
+    mix(v, 2, 6, 10, 14, m[s4], m[s5]);  mix(v, 3, 7, 11, 15, m[s6], m[s7]);                      \
+    mix(v, 0, 5, 10, 15, m[s8], m[s9]);  mix(v, 1, 6, 11, 12, m[s10], m[s11]);                    \
+    mix(v, 2, 7, 8, 13, m[s12], m[s13]); mix(v, 3, 4, 9, 14, m[s14], m[s15]);
     void round_block(const uint8_t* blk, bool final_block) {
-        static const uint8_t sigma[10][16] = {
-            {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
-            {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
-            {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
-            {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
-            {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0}};
         uint32_t m[16], v[16];
-        for (int i = 0; i < 16; i++) memcpy(&m[i], blk + 4 * i, 4);      // little-endian host
+        memcpy(m, blk, 64);                                               // little-endian host
         for (int i = 0; i < 8; i++) { v[i] = h_[i]; v[8 + i] = kIV[i]; }
         v[12] ^= (uint32_t)count_; v[13] ^= (uint32_t)(count_ >> 32);
         if (final_block) v[14] = ~v[14];
-        for (int r = 0; r < 10; r++) {
-            const uint8_t* s = sigma[r];
-            mix(v, 0, 4, 8, 12, m[s[0]], m[s[1]]);   mix(v, 1, 5, 9, 13, m[s[2]], m[s[3]]);
-            mix(v, 2, 6, 10, 14, m[s[4]], m[s[5]]);  mix(v, 3, 7, 11, 15, m[s[6]], m[s[7]]);
-            mix(v, 0, 5, 10, 15, m[s[8]], m[s[9]]);  mix(v, 1, 6, 11, 12, m[s[10]], m[s[11]]);
-            mix(v, 2, 7, 8, 13, m[s[12]], m[s[13]]); mix(v, 3, 4, 9, 14, m[s[14]], m[s[15]]);
-        }
+        SB_B2_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
+        SB_B2_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3)
+        SB_B2_ROUND(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4)
+        SB_B2_ROUND(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8)
+        SB_B2_ROUND(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13)
+        SB_B2_ROUND(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9)
+        SB_B2_ROUND(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11)
+        SB_B2_ROUND(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10)
+        SB_B2_ROUND(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5)
+        SB_B2_ROUND(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0)
         for (int i = 0; i < 8; i++) h_[i] ^= v[i] ^ v[8 + i];
     }
+#undef SB_B2_ROUND
     uint32_t h_[8];
     uint64_t count_;
     uint8_t block_[64];
