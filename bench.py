@@ -258,6 +258,9 @@ def run_ours(args):
     ctx.prof_report()
     dt_serial = timed(resident, args.steps)
     prof = ctx.prof_report()
+    # one more serialised proof for the per-level split of the G2 accumulation (records carry log2 of the job size)
+    resident()
+    timeline = ctx.prof_timeline()
     ctx.prof_enable(False)
     ctx.set_serial_msm(False)
     assert all(p == proofs[0] for p in proofs), "proofs differ between steps"
@@ -311,6 +314,8 @@ def run_ours(args):
     fr_peak = 148 * 1024 * 1000 * 2 / fr_ms / 1e6
     extra["roofline_imad"] = imad_roofline(kernels, n, LOG_N, fq_peak, fr_peak)
     extra["roofline_imad"]["peak_fq_gmul_s"] = fq_peak
+    if world == 1:
+        extra["roofline_imad"]["g2_accum_by_level"] = g2_levels(timeline, LOG_N, fq_peak)
     extra["roofline_imad"]["peak_fr_gmul_s"] = fr_peak
     # sumcheck kernels alone, L2 flushed between launches
     sc = {}
@@ -418,6 +423,31 @@ def imad_roofline(kernels, n, ell, fq_peak, fr_peak):
         adds *= 2
         out["g2_accum_lower_levels"] = {"ms": k2["ms_per_step"], "fq_gmul_s": adds * 28 / k2["ms_per_step"] / 1e6}
         out["g2_accum_lower_levels"]["frac"] = out["g2_accum_lower_levels"]["fq_gmul_s"] / fq_peak
+    return out
+
+
+def g2_levels(timeline, ell, fq_peak):
+    """Serialised duration of the G2 mixed accumulation per ladder level (both openings) and its achieved Fq
+    products per second.  Levels below 2^14 points launch a handful of CTAs: alone they are latency-bound (a
+    chain of S0 dependent additions), in the real run they overlap the large levels, so their own fraction says
+    nothing about the kernel; they are reported as one group."""
+    per = {}
+    for name, t0, t1, tag in timeline:
+        if "k_seg_accum_mixed" in name and "Fq2" in name and tag >= 0:
+            per[tag] = per.get(tag, 0.0) + (t1 - t0)
+    out = {"levels": {}, "small_levels_below_2^14": {"ms": 0.0, "adds": 0}}
+    for tag, ms in sorted(per.items(), reverse=True):
+        c, W = msm_layout(1 << tag)
+        adds = 2 * W * (1 << tag)
+        if tag >= 14:
+            g = adds * 28 / ms / 1e6
+            out["levels"]["2^%d" % tag] = {"ms": ms, "window_bits": c, "windows": W, "fq_gmul_s": g, "frac": g / fq_peak}
+        else:
+            out["small_levels_below_2^14"]["ms"] += ms; out["small_levels_below_2^14"]["adds"] += adds
+    big_ms = sum(v["ms"] for v in out["levels"].values())
+    big_adds = sum(2 * msm_layout(1 << int(k[2:]))[1] * (1 << int(k[2:])) for k in out["levels"])
+    if big_ms:
+        out["levels_2^14_and_up"] = {"ms": big_ms, "fq_gmul_s": big_adds * 28 / big_ms / 1e6, "frac": big_adds * 28 / big_ms / 1e6 / fq_peak}
     return out
 
 
