@@ -370,7 +370,12 @@ def msm_layout(m):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the `ncu --set full` capture under profiles/
-NCU_TRAFFIC = {("k_seg_accum_mixed:top<Fq2>", 20): (2.167095e9 + 0.934841e9, "profiles/r01_ncu_g2_accum_top.txt")}
+NCU_TRAFFIC = {("k_seg_accum_mixed:top<Fq2>", 20): (2.213844e9 + 1.025013e9, "profiles/r01_ncu_g2_accum_top.txt")}
+
+
+def chunk_s0(entries):
+    """chunk length of the first accumulation level (msm_s0 in csrc/msm.cu)"""
+    return 48 if entries >= (1 << 21) else 24
 
 
 def algorithmic_bytes(name, n, ell, launches_per_step):
@@ -381,8 +386,7 @@ def algorithmic_bytes(name, n, ell, launches_per_step):
         m = n // 2
         c, W = msm_layout(m)
         entries = W * m
-        S = 19
-        return entries * (192 + 4) + (entries // S + (1 << (c - 1))) * 384
+        return entries * (192 + 4) + (entries // chunk_s0(entries) + (1 << (c - 1))) * 384
     if name == "k_seg_accum<Fq2,mixed>":
         # all ladder levels of both openings (levels of 2^(ell-1) .. 1 bases), averaged per launch
         total = 0
@@ -390,12 +394,12 @@ def algorithmic_bytes(name, n, ell, launches_per_step):
             m = 1 << k
             c, W = msm_layout(m)
             entries = W * m
-            total += entries * (192 + 4) + (entries // 8 + (1 << (c - 1))) * 384
+            total += entries * (192 + 4) + (entries // chunk_s0(entries) + (1 << (c - 1))) * 384
         return 2.0 * total / launches_per_step
     if name.startswith("k_seg_accum_mixed<Fq>"):
         c, W = msm_layout(n)
         entries = W * n
-        return entries * (96 + 4) + (entries // 32 + (1 << (c - 1))) * 192
+        return entries * (96 + 4) + (entries // chunk_s0(entries) + (1 << (c - 1))) * 192
     return None
 
 
