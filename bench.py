@@ -317,6 +317,13 @@ def run_ours(args):
     if world == 1:
         extra["roofline_imad"]["g2_accum_by_level"] = g2_levels(timeline, LOG_N, fq_peak)
     extra["roofline_imad"]["peak_fr_gmul_s"] = fr_peak
+    # the same dominant kernel against the roofline that actually bounds it (integer pipe), inside `roofline`
+    if roofline is not None:
+        top_lvl = extra["roofline_imad"].get("g2_accum_top_level")
+        if top_lvl:
+            roofline["integer_pipe"] = {"bound": "imad", "achieved": top_lvl["fq_gmul_s"], "peak": fq_peak, "unit": "G Fq-mul/s",
+                                        "frac": top_lvl["frac"], "of": "largest launch (28 Fq products per mixed addition in G2)",
+                                        "peak_source": "sb_mul_bench in this run (IMAD.WIDE issues at half rate: 148 SM x 32 lanes x clock)"}
     # sumcheck kernels alone, L2 flushed between launches
     sc = {}
     for which, nm, mults, bts in ((0, "sc1_fused_round", 12 / 4.0, 152.0), (1, "sc1_first_round", 6 / 2.0, (6 * 32 + 32) / 2.0), (2, "sc2_fused_round", 7 / 4.0, (8 * 32 + 4 * 32) / 4.0)):
