@@ -34,7 +34,7 @@ constexpr int MSM_INFO_HTOT = 6, MSM_INFO_ITEMS = 14;
 // use, grown on demand), so that the steady state performs no device allocation at all.
 template <class F>
 struct MsmScratch {
-    DevBuf<uint32_t> codes, sorted, counts, offsets, cursors, info;
+    DevBuf<uint32_t> codes, sorted, counts, offsets, cursors, info, perm, invperm;
     DevBuf<uint32_t> plan[MSM_MAX_LEVELS];
     DevBuf<uint32_t> hplan[MSM_MAX_HALVINGS];
     DevBuf<AffinePt<F>> affA, affB;        // outputs of the pairwise rounds (ping-pong)

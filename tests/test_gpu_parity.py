@@ -467,7 +467,7 @@ def test_msm_knobs_forced_on_small_inputs():
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for extra in ({"SB_MSM_AFFINE_LOG2": "5"}, {"SB_MSM_AFFINE_LOG2": "3", "SB_MSM_S0": "3", "SB_MSM_S1": "2"},
-                  {"SB_MSM_S0": "2", "SB_MSM_S1": "2", "SB_MSM_RED_L": "8", "SB_MSM_ORDER": "0"}):
+                  {"SB_MSM_S0": "2", "SB_MSM_S1": "2", "SB_MSM_RED_L": "8", "SB_MSM_ORDER": "0", "SB_MSM_SORTED": "0"}):
         env = dict(os.environ, **extra)
         r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
                             "-k", "msm_matches or structured or commit_and_open or prove_bytes or adversarial"],
