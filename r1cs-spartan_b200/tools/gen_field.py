@@ -217,19 +217,21 @@ def gen_redc(N, p):
 
 
 def gen_wide_op(N, kind, p):
-    """2N-limb r = a - b + p^2 ("subp2"), a - b ("sub"), or N-limb unreduced r = a + b ("addn")."""
+    """2N-limb r = a - b + p^2 ("subp2"), a - b + 2 p^2 ("sub2p2"), a - b ("sub"), a + b ("add2"), or N-limb
+    unreduced r = a + b ("addn")."""
     ins = []
-    if kind == "addn":
-        for k in range(N):
-            op = "add.cc" if k == 0 else ("addc.cc" if k < N - 1 else "addc")
+    if kind in ("addn", "add2"):
+        M = N if kind == "addn" else 2 * N
+        for k in range(M):
+            op = "add.cc" if k == 0 else ("addc.cc" if k < M - 1 else "addc")
             ins.append((op, "r%d" % k, "a%d" % k, "b%d" % k))
         return ins
     M = 2 * N
     for k in range(M):
         op = "sub.cc" if k == 0 else "subc.cc"
         ins.append((op, "r%d" % k, "a%d" % k, "b%d" % k))
-    if kind == "subp2":
-        P2 = limbs(p * p, M)
+    if kind in ("subp2", "sub2p2"):
+        P2 = limbs((1 if kind == "subp2" else 2) * p * p, M)
         for k in range(M):
             op = "add.cc" if k == 0 else "addc.cc"
             ins.append((op, "r%d" % k, "r%d" % k, hex(P2[k])))
@@ -440,7 +442,7 @@ def render_lazy(fname, f):
                                 [("t%d" % k, "t[%d]" % k) for k in range(2 * N)] + [("p%d" % k, "%s_MOD_C[%d]" % (U, k)) for k in range(N)] +
                                 [("pinv", "%s_MOD_C[%d]" % (U, N))],
                                 "uint32_t* __restrict__ r, const uint32_t* t"))
-    for kind, M in (("subp2", 2 * N), ("sub", 2 * N), ("addn", N)):
+    for kind, M in (("subp2", 2 * N), ("sub", 2 * N), ("addn", N), ("sub2p2", 2 * N), ("add2", 2 * N)):
         parts.append(render_general("%s_wide_%s_ptx" % (fname, kind), gen_wide_op(N, kind, p),
                                     [("r%d" % k, "r[%d]" % k) for k in range(M)],
                                     [("a%d" % k, "a[%d]" % k) for k in range(M)] + [("b%d" % k, "b[%d]" % k) for k in range(M)],
