@@ -334,6 +334,115 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>*
     }
 }
 
+// ---- cooperative variant (SB_MSM_AFFINE_COOP=1; prepared in round 1, NOT yet run on a GPU, hence off and not in the
+// test matrix): the inversion is shared by the whole CTA instead of one per thread.  Thread t owns K consecutive
+// output elements and reduces their denominators to one product a_t exactly as above; the CTA then computes the
+// inclusive prefix products I_t = a_0..a_t and suffix products U_t = a_t..a_{T-1} (Hillis-Steele in shared memory,
+// log2 T products per thread each), ONE thread inverts the total, and 1/a_t = total^-1 * I_{t-1} * U_{t+1}.  The
+// inversion share per addition drops from (Fermat inversion) / K to (2 log2 T + 2 products) / K plus one inversion
+// per T K additions, so K can be small (more threads, shorter chains): about 5M + 1S + 0.3M per addition against
+// the 8M + 2S of the mixed XYZZ addition.
+constexpr int AFFC_THREADS = 256;
+
+template <class F>
+__device__ F cta_batch_inverse(const F& a, F* sh) {
+    const uint32_t t = threadIdx.x, T = blockDim.x;
+    __shared__ F sh_total_inv;
+    sh[t] = a;
+    __syncthreads();
+    for (uint32_t off = 1; off < T; off <<= 1) {               // inclusive prefix products
+        F v = sh[t];
+        if (t >= off) v = F::mul(sh[t - off], v);
+        __syncthreads();
+        sh[t] = v;
+        __syncthreads();
+    }
+    const F before = t ? sh[t - 1] : F::one();
+    if (t == 0) sh_total_inv = F::inv(sh[T - 1]);
+    __syncthreads();
+    sh[t] = a;
+    __syncthreads();
+    for (uint32_t off = 1; off < T; off <<= 1) {               // inclusive suffix products
+        F v = sh[t];
+        if (t + off < T) v = F::mul(v, sh[t + off]);
+        __syncthreads();
+        sh[t] = v;
+        __syncthreads();
+    }
+    const F after = (t + 1 < T) ? sh[t + 1] : F::one();
+    const F r = F::mul(F::mul(sh_total_inv, before), after);
+    __syncthreads();                                            // sh is reused by the caller's next call
+    return r;
+}
+
+template <class F, bool FIRST>
+__global__ void __launch_bounds__(AFFC_THREADS) k_affine_round_coop(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
+                                                                    const AffinePt<F>* __restrict__ in_aff, const uint32_t* __restrict__ in_off,
+                                                                    const uint32_t* __restrict__ out_off, uint32_t B, uint32_t nthreads, uint32_t K,
+                                                                    F* __restrict__ prefix, AffinePt<F>* __restrict__ out_aff) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    F* sh = reinterpret_cast<F*>(smem_raw);
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = out_off[B];
+    const uint32_t p0 = t * K;
+    const bool active = t < nthreads && p0 < total;             // inactive threads still take part in the barriers
+    const uint32_t p1 = active ? min(p0 + K, total) : p0;
+    auto load_in = [&](uint32_t idx) -> AffinePt<F> {
+        if (FIRST) {
+            uint32_t ent = __ldg(&sorted[idx]);
+            AffinePt<F> q = ldg_elem(&tab[ent & 0x7fffffffu]);
+            if (ent & 0x80000000u) q.y = F::neg(q.y);
+            return q;
+        }
+        return ldg_elem(&in_aff[idx]);
+    };
+    uint32_t b = 0;
+    if (active) {
+        uint32_t lo = 0, hi = B;                                // bucket of p0: last b with out_off[b] <= p0
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&out_off[mid]) <= p0) lo = mid; else hi = mid;
+        }
+        b = lo;
+    }
+    F acc = F::one();
+    for (uint32_t p = p0; p < p1; p++) {                        // pass 1: prefix products of this thread's denominators
+        while (__ldg(&out_off[b + 1]) <= p) b++;
+        const uint32_t j = p - __ldg(&out_off[b]);
+        const uint32_t ib = __ldg(&in_off[b]), n_in = __ldg(&in_off[b + 1]) - ib;
+        const bool has2 = 2 * j + 1 < n_in;
+        AffinePt<F> P = load_in(ib + 2 * j), Q = has2 ? load_in(ib + 2 * j + 1) : P;
+        F d;
+        pair_classify(P, Q, has2, d);
+        st_elem(&prefix[(size_t)(p - p0) * nthreads + t], acc);
+        acc = F::mul(acc, d);
+    }
+    F inv = cta_batch_inverse<F>(acc, sh);                      // 1 / (product of this thread's denominators)
+    for (uint32_t p = p1; p-- > p0;) {                          // pass 2, backwards
+        while (__ldg(&out_off[b]) > p) b--;
+        const uint32_t j = p - __ldg(&out_off[b]);
+        const uint32_t ib = __ldg(&in_off[b]), n_in = __ldg(&in_off[b + 1]) - ib;
+        const bool has2 = 2 * j + 1 < n_in;
+        AffinePt<F> P = load_in(ib + 2 * j), Q = has2 ? load_in(ib + 2 * j + 1) : P;
+        F d;
+        const int kind = pair_classify(P, Q, has2, d);
+        F dinv = F::mul(inv, ldg_elem(&prefix[(size_t)(p - p0) * nthreads + t]));
+        inv = F::mul(inv, d);
+        AffinePt<F> r;
+        if (kind == PAIR_COPY_P) r = P;
+        else if (kind == PAIR_COPY_Q) r = Q;
+        else if (kind == PAIR_INF) r = AffinePt<F>::inf();
+        else {
+            F lam;
+            if (kind == PAIR_ADD) lam = F::mul(F::sub(Q.y, P.y), dinv);
+            else { F xx = F::sqr(P.x); lam = F::mul(F::add(F::dbl(xx), xx), dinv); }
+            r.x = F::sub(F::sub(F::sqr(lam), P.x), Q.x);
+            r.y = F::sub(F::mul(lam, F::sub(P.x, r.x)), P.y);
+        }
+        st_elem(&out_aff[p], r);
+    }
+}
+
 template <class F>
 __device__ XyzzPt<F> mul_small(const XyzzPt<F>& p, uint32_t k) {
     XyzzPt<F> acc = XyzzPt<F>::inf();
@@ -491,7 +600,8 @@ static inline void ensure(DevBuf<T>& b, size_t n, cudaStream_t s) { if (b.n < n)
 // (opening 34.3 ms against 26.2 ms) -- a thread's chain of AFF_K additions plus one Fermat inversion (~2e5
 // instructions) is milliseconds long, and the later rounds have too few threads to fill 148 SMs; a smaller AFF_K
 // makes the inversion share larger than the saving.  Kept (and parity-tested with the threshold forced down)
-// for instances large enough to amortise it and as the base for a cheaper inversion.
+// for instances large enough to amortise it and as the base for a cheaper inversion (k_affine_round_coop,
+// SB_MSM_AFFINE_COOP=1: one inversion per CTA; written at the end of round 1, not yet run on a GPU).
 template <class F>
 static uint32_t msm_affine_min() {
     static const uint32_t v = [] {
@@ -553,12 +663,27 @@ void msm_finish(MsmJob<F>& job) {
     if (R) {
         ensure(sc.affA, std::max<uint32_t>(htot[0], 1), stream);
         if (R > 1) ensure(sc.affB, std::max<uint32_t>(htot[1], 1), stream);
-        const uint32_t nth0 = (htot[0] + AFF_K - 1) / AFF_K;
-        ensure(sc.prefix, (size_t)std::max<uint32_t>(nth0, 1) * AFF_K, stream);
+        static const bool coop = msm_env_u32("SB_MSM_AFFINE_COOP", 0, 0, 1) != 0;
+        static const uint32_t coop_k = msm_env_u32("SB_MSM_AFFINE_K", 64, 1, 4096);
+        const uint32_t K = coop ? coop_k : (uint32_t)AFF_K;
+        const uint32_t nth0 = (htot[0] + K - 1) / K;
+        ensure(sc.prefix, (size_t)std::max<uint32_t>(nth0, 1) * K, stream);
         const uint32_t* in_off = sc.offsets.get();
         for (uint32_t r = 0; r < R; r++) {
             AffinePt<F>* outp = (r % 2 == 0) ? sc.affA.get() : sc.affB.get();
-            const uint32_t nth = (htot[r] + AFF_K - 1) / AFF_K;
+            const uint32_t nth = (htot[r] + K - 1) / K;
+            if (coop) {
+                const int cgrid = (int)((std::max<uint32_t>(nth, 1) + AFFC_THREADS - 1) / AFFC_THREADS);
+                const size_t csmem = AFFC_THREADS * sizeof(F);
+                if (r == 0)
+                    SB_LAUNCH_NAMED(SB_KNAME(F, "k_affine_round_coop"), (k_affine_round_coop<F, true>), cgrid, AFFC_THREADS, csmem, stream,
+                                    bases.tab.get(), sc.sorted.get(), aff, in_off, sc.hplan[r].get(), B, nth, K, sc.prefix.get(), outp);
+                else
+                    SB_LAUNCH_NAMED(SB_KNAME(F, "k_affine_round_coop"), (k_affine_round_coop<F, false>), cgrid, AFFC_THREADS, csmem, stream,
+                                    bases.tab.get(), sc.sorted.get(), aff, in_off, sc.hplan[r].get(), B, nth, K, sc.prefix.get(), outp);
+                aff = outp; in_off = sc.hplan[r].get();
+                continue;
+            }
             const int grid = (int)((std::max<uint32_t>(nth, 1) + AFF_THREADS - 1) / AFF_THREADS);
             if (r == 0)
                 SB_LAUNCH_NAMED(job.top ? SB_KNAME(F, "k_affine_round:top") : SB_KNAME(F, "k_affine_round"), (k_affine_round<F, true>), grid, AFF_THREADS, 0, stream,
