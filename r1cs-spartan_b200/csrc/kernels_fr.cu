@@ -304,7 +304,7 @@ static void launch_sc_round(const Fr* A, const Fr* B, const Fr* C, Fr* Ao, Fr* B
                             size_t m_in, Fr* out3, const RoundWs& ws, cudaStream_t stream) {
     bool fold = r_dev != nullptr;
     size_t h = fold ? m_in / 4 : m_in / 2;
-    int grid = grid_for(h, 256, 2);
+    int grid = grid_for(h, 256, ws.max_grid / SB_SMS > 1 ? ws.max_grid / SB_SMS : 1);   // 2 resident CTAs per SM by default
     if (grid > ws.max_grid) grid = ws.max_grid;
     if (fold) SB_LAUNCH_NAMED(KIND == 1 ? "k_sc_round<sc1,fold>" : "k_sc_round<sc2,fold>", (k_sc_round<KIND, true>), grid, 256, 0, stream, A, B, C, Ao, Bo, Co, E, r_dev, h, out3, ws.block_partials, ws.ticket);
     else SB_LAUNCH_NAMED(KIND == 1 ? "k_sc_round<sc1,first>" : "k_sc_round<sc2,first>", (k_sc_round<KIND, false>), grid, 256, 0, stream, A, B, C, Ao, Bo, Co, E, r_dev, h, out3, ws.block_partials, ws.ticket);

@@ -872,7 +872,14 @@ sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
         SB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
         uint64_t thresh = UINT64_MAX;
         SB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
-        c->ws.max_grid = SB_SMS * 2;
+        // grid cap of the sumcheck round kernels, in CTAs per SM.  2 = one resident wave (persistent, grid-stride).
+        // SB_SC_CTAS_PER_SM > 2 (experiment) launches more, smaller-work CTAs so that the
+        // partial last wave of a large round spreads over all SMs.
+        {
+            const char* e = getenv("SB_SC_CTAS_PER_SM");
+            int k = e ? atoi(e) : 2;
+            c->ws.max_grid = SB_SMS * (k < 1 ? 1 : k > 64 ? 64 : k);
+        }
         c->block_partials.alloc((size_t)c->ws.max_grid * 3, c->stream);
         c->ticket.alloc(1, c->stream);
         SB_CUDA(cudaMemsetAsync(c->ticket.get(), 0, sizeof(unsigned int), c->stream));

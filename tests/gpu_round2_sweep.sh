@@ -18,3 +18,5 @@ for K in 32 64 128; do
   echo "== coop affine timing K=$K (levels with >= 2^21 entries)"
   SB_MSM_AFFINE_LOG2=21 SB_MSM_AFFINE_COOP=1 SB_MSM_AFFINE_K=$K python tests/gpu_timeline.py 20 2>&1 | grep STEADY | cut -c1-200
 done
+# (3) sumcheck round kernels alone: more, finer CTAs for the large rounds (north-star target: >= 60 % of the IMAD ceiling at 2^20)
+for C in 2 4 8 16; do echo "== SB_SC_CTAS_PER_SM=$C"; SB_SC_CTAS_PER_SM=$C python tests/gpu_sc_kernels.py 2>&1 | grep -E "2\^20|2\^22"; done
