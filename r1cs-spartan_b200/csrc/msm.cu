@@ -7,9 +7,15 @@
 WinLayout msm_layout(size_t m) {
     int lg = 0;
     while (((size_t)1 << lg) < m) lg++;
-    int c = lg - 3;
+    // window bits: log2(m) - 3 balances the accumulation (m W additions) against the bucket reduction (~9 additions
+    // per bucket today).  SB_MSM_C_OFFSET / SB_MSM_C_MAX shift the rule for experiments (a cheaper reduction would
+    // favour one more bit); the layout is fixed when the bases are prepared, so the knobs only act at load time.
+    static const int c_off = getenv("SB_MSM_C_OFFSET") ? atoi(getenv("SB_MSM_C_OFFSET")) : -3;
+    static const int c_max = getenv("SB_MSM_C_MAX") ? atoi(getenv("SB_MSM_C_MAX")) : 16;
+    int c = lg + c_off;
     if (c < 4) c = 4;
-    if (c > 16) c = 16;
+    if (c > c_max) c = c_max;
+    if (c > 20) c = 20;
     WinLayout L{};
     L.c = c;
     const int top = c - 1, rest = 255 - top;

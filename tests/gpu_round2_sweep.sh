@@ -20,3 +20,8 @@ for K in 32 64 128; do
 done
 # (3) sumcheck round kernels alone: more, finer CTAs for the large rounds (north-star target: >= 60 % of the IMAD ceiling at 2^20)
 for C in 2 4 8 16; do echo "== SB_SC_CTAS_PER_SM=$C"; SB_SC_CTAS_PER_SM=$C python tests/gpu_sc_kernels.py 2>&1 | grep -E "2\^20|2\^22"; done
+# (4) one more window bit (fewer mixed additions, twice the buckets) and the first-level chunk size, now that the
+#     accumulation order is length-sorted
+for V in "SB_MSM_C_OFFSET=-2 SB_MSM_C_MAX=17" "SB_MSM_S0_BIG=32" "SB_MSM_S0_BIG=64" "SB_MSM_S0_BIG=96"; do
+  echo "== $V"; env $V python tests/gpu_timeline.py 20 2>&1 | grep STEADY | cut -c1-200
+done
