@@ -118,7 +118,7 @@ def extrapolate_cpu(phases, total_s, ls, lt):
     return est, {"commit_x": r_commit, "open_x": r_open, "sumcheck1_x": r_sc1, "linear_x": lin}
 
 
-def cpu_model(log_n_sample):
+def cpu_model():
     import platform
     try:
         model = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
@@ -127,35 +127,69 @@ def cpu_model(log_n_sample):
     return model
 
 
+def bench_trapdoor(log_n):
+    """the trapdoor both arms use for their public parameters (SplitMix64 seeds 99 + i, arkworks' Fr sampling rule)"""
+    import numpy as np
+    import r1cs_spartan_b200 as sb
+    return np.stack([sb.workload.mont_to_limbs([sb.workload.fr_rand_mont(sb.workload.SplitMix64(99 + i))])[0] for i in range(log_n)])
+
+
+def cpu_prove_full(log_n, opp=None, setup_threads=None):
+    """ONE real proof of the bench workload by the literal CPU restatement, single-threaded (the reference's
+    configuration, Cargo.toml:26).  opp: oracle parameters made elsewhere (our arm passes the GPU-made ones so that
+    the proof bytes can be compared); otherwise the oracle's own keygen runs first, untimed, on all host cores."""
+    from oracle import binding as ob
+    import r1cs_spartan_b200 as sb
+    from r1cs_spartan_b200.generators import G1_GENERATOR, G2_GENERATOR
+    cs = sb.SyntheticR1CS(NUM_PUBLIC, (1 << log_n) - NUM_PUBLIC, 0, 0x5EED0000 + log_n)
+    ocs = ob.R1CS.from_csr(log_n, cs.mats)
+    t_setup = time.perf_counter()
+    if opp is None:
+        ob.set_threads(setup_threads or os.cpu_count() or 1)
+        opp = ob.PP.keygen_with(log_n, G1_GENERATOR, G2_GENERATOR, bench_trapdoor(log_n))
+    ob.set_threads(1)                               # the timed part is one thread, always
+    setup_s = time.perf_counter() - t_setup
+    t0 = time.perf_counter()
+    proof, tr = ob.prove(ocs, opp, cs.v, cs.w)
+    dt = time.perf_counter() - t0
+    phases = {k: tr.time(k) for k in ("transcript_init", "prove1_commit", "prove2_open", "prove3_setup", "sumcheck1", "prove4",
+                                       "prove5_eval_on_x", "sumcheck2", "prove6_open")}
+    return dt, phases, proof, setup_s
+
+
 def run_reference(args):
+    """The reference arm: the reference's own prover cannot be built here (Rust over un-vendored arkworks git
+    dependencies, no cargo), so this times oracle/ -- its literal single-threaded C++ restatement -- on ONE REAL proof
+    of the very workload our arm proves (2^LOG_N constraints; about 4.5 minutes at 2^20).  Nothing is extrapolated:
+    `steps` is the number of proofs actually timed (1 unless SB_REF_STEPS says otherwise), whatever --steps asked."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_log = int(os.environ.get("SB_REF_SAMPLE_LOG_N", "13"))
-    scale = float(1 << (LOG_N - sample_log))
-    for _ in range(args.warmup):
-        cpu_prove_sample(sample_log)
-    times, ests = [], []
-    for _ in range(args.steps):
-        dt, phases, _ = cpu_prove_sample(sample_log)
-        times.append(dt)
-        ests.append(extrapolate_cpu(phases, dt, sample_log, LOG_N)[0])
-    ms_sample = 1e3 * sum(times) / len(times)
-    value = 1e3 * sum(ests) / len(ests)
-    sample = ("full prove of the same circuit at 2^%d constraints, %.0f ms per step, scaled to 2^%d per phase with the literal "
-              "algorithm's operation counts (MSM windows widen with n, the reference's first sumcheck grows like n l^2; a blanket "
-              "x%d would give %.0f ms); literal restatement of the reference (2 log n + 3 table sumcheck, duplicated-scalar G2 MSMs), "
-              "1 thread as in Cargo.toml:26 (no `parallel`)" % (sample_log, ms_sample, LOG_N, int(scale), ms_sample * scale))
+    import hashlib
+    steps = max(int(os.environ.get("SB_REF_STEPS", "1")), 1)
+    times, phases, proof, setup_s = [], None, None, 0.0
+    opp = None
+    for _ in range(steps):
+        dt, phases, proof, s_s = cpu_prove_full(LOG_N, opp)
+        times.append(dt); setup_s += s_s
+    value = 1e3 * sum(times) / len(times)
+    sample = ("%d full single-threaded proof(s) of the same workload (2^%d constraints) by the literal C++ restatement of the "
+              "reference (2 log n + 3 table sumcheck, duplicated-scalar G2 MSMs, arkworks' window rule); nothing extrapolated; "
+              "public parameters made by the restatement's own keygen on all host cores, untimed (%.1f s); --steps %d / --warmup %d "
+              "were requested, %d step(s) timed, no warm-up" % (steps, LOG_N, setup_s, args.steps, args.warmup, steps))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": value, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-        "dtype": "u32x8 Montgomery Fr / u32x12 Fq (CPU: u64 limbs)", "data": "synthetic",
-        "config": {"workload": workload_name(LOG_N), "timed_sample": "2^%d constraints" % sample_log},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": 0, "requested_steps": args.steps, "requested_warmup": args.warmup, "timed_steps": steps,
+        "ms_per_step": value, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64 limbs (4 x u64 Montgomery Fr, 6 x u64 Fq; exact integer arithmetic)", "data": "synthetic",
+        "same_config": True,
+        "config": {"workload": workload_name(LOG_N), "parallelism": "1 CPU thread (the reference never enables arkworks' `parallel`)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                         "host_cpu": cpu_model(sample_log), "host_cores_available": os.cpu_count()},
+                         "host_cpu": cpu_model(), "host_cores_available": os.cpu_count(), "phases_s": phases},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "proof_sha256": hashlib.sha256(proof).hexdigest(), "proof_bytes": len(proof),
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------- our arm
@@ -189,8 +223,11 @@ def run_ours(args):
     # generators: any r-torsion generators are a valid pp (the reference samples them); these are the ones the
     # tests use (G1: the standard generator; G2: derived in oracle/pymodel.py), written as Montgomery limbs
     from r1cs_spartan_b200.generators import G1_GENERATOR, G2_GENERATOR
-    trap = np.stack([sb.workload.mont_to_limbs([sb.workload.fr_rand_mont(sb.workload.SplitMix64(99 + i))])[0] for i in range(LOG_N)])
-    pp = sb.MLPolyCommit.keygen(LOG_N, G1_GENERATOR, G2_GENERATOR, trap, ctx=ctx)
+    trap = bench_trapdoor(LOG_N)
+    cpu_log = LOG_N if args.cpu_sample_log_n is None else args.cpu_sample_log_n
+    want_cpu = world == 1 and not args.no_cpu_baseline
+    # one GPU + CPU baseline at the full size: keep every parameter level so that the oracle can prove on the very same ones
+    pp = sb.MLPolyCommit.keygen(LOG_N, G1_GENERATOR, G2_GENERATOR, trap, keep_all_levels=(want_cpu and cpu_log == LOG_N), ctx=ctx)
     pk = sb.MLArgumentForR1CS.index(*cs.mats, ctx=ctx)
     wit = sb.Witness(pk, cs.v, cs.w)
     setup_s = time.perf_counter() - t_setup
@@ -203,19 +240,31 @@ def run_ours(args):
 
     step_log = []
 
-    def timed(fn, steps):
+    event_s = {}
+
+    def timed(fn, steps, tag=None):
+        """K steps bracketed by barrier + synchronize on both sides.  Every step ends with the proof bytes on the host, so
+        the device is idle at both brackets; the region is timed with CUDA events (recorded on torch's current stream while
+        nothing is queued: they stamp the device timeline) and with the host clock -- the two agree to microseconds, the
+        event time is the one reported.  Max over ranks."""
         barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
         t0 = time.perf_counter()
         for _ in range(steps):
             ts = time.perf_counter()
             fn()
             step_log.append(round(1e3 * (time.perf_counter() - ts), 3))
+        e1.record()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        dt_host = time.perf_counter() - t0
+        dt = e0.elapsed_time(e1) * 1e-3
         if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            t = torch.tensor([dt, dt_host], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            dt, dt_host = float(t[0].item()), float(t[1].item())
+        if tag:
+            event_s[tag] = {"cuda_events_s": dt, "host_clock_s": dt_host}
         return dt
 
     proofs, phase_log = [], []
@@ -235,19 +284,37 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         resident()
     e2e()
+    # ---- correctness evidence the driver can see: one hash per line, identical on every rank, and -- when the prover is
+    # sharded -- identical to the proof a plain single-GPU context makes for the same instance on rank 0's GPU
+    import hashlib
+    proof_sha = hashlib.sha256(proofs[0]).hexdigest()
+    sharded_check = None
+    if world > 1:
+        hashes = [None] * world
+        dist.all_gather_object(hashes, proof_sha)
+        assert all(h == hashes[0] for h in hashes), "ranks disagree on the proof: %s" % hashes
+        if rank == 0:
+            ctx1 = sb.Context(local_rank)
+            pp1 = sb.MLPolyCommit.keygen(LOG_N, G1_GENERATOR, G2_GENERATOR, trap, ctx=ctx1)
+            pk1 = sb.MLArgumentForR1CS.index(*cs.mats, ctx=ctx1)
+            single_proof = sb.MLArgumentForR1CS.prove(pk1, cs.v, cs.w, pp1)
+            assert single_proof == proofs[0], "the sharded proof differs from the single-GPU proof of the same instance"
+            sharded_check = {"ranks_agree": True, "equals_single_gpu_proof": True, "single_gpu_proof_sha256": hashlib.sha256(single_proof).hexdigest()}
+            pk1.close(); pp1.close(); del pk1, pp1
+        dist.barrier()
     # ---- timed region: K proofs with the witness resident in HBM
     sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("SB_NO_CLOCKS"):
         sampler.start()
     del phase_log[:]
     l0 = ctx.launch_count()
-    dt = timed(resident, args.steps)
+    dt = timed(resident, args.steps, "resident")
     launches = (ctx.launch_count() - l0) // args.steps
     steps_resident = list(step_log); del step_log[:]
     phases_resident = list(phase_log); del phase_log[:]
     # ---- e2e: host buffers in, proof bytes out
     h0, d0 = ctx.copy_counters()
-    dt_e2e = timed(e2e, args.steps)
+    dt_e2e = timed(e2e, args.steps, "e2e")
     h1, d1 = ctx.copy_counters()
     steps_e2e = list(step_log); del step_log[:]
     clocks = sampler.stop() if rank == 0 else None
@@ -333,17 +400,30 @@ def run_ours(args):
     extra["sumcheck_kernels"] = sc
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        sample_log = int(os.environ.get("SB_CPU_SAMPLE_LOG_N", "14"))
-        dtc, phases, _ = cpu_prove_sample(sample_log)
-        scale = 1 << (LOG_N - sample_log)
-        est_s, factors = extrapolate_cpu(phases, dtc, sample_log, LOG_N)
-        cpu = {"value": 1e3 * est_s, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "full prove at 2^%d constraints took %.2f s on 1 core (the reference is single-threaded, Cargo.toml:26); scaled to 2^%d "
-                         "per phase with the literal algorithm's operation counts (a blanket x%d would give %.0f ms)"
-                         % (sample_log, dtc, LOG_N, scale, 1e3 * dtc * scale),
-               "scaling_factors": factors,
-               "host_cpu": cpu_model(sample_log), "host_cores_available": os.cpu_count(), "sample_phases_s": phases}
+    if want_cpu:
+        from oracle import binding as ob
+        if cpu_log == LOG_N:
+            # ONE REAL single-threaded proof of the same instance on the same (GPU-made, exported) public parameters; its
+            # bytes must equal the GPU's.  About 4.5 minutes at 2^20; `--cpu-sample-log-n K` trades it for a 2^K sample + model.
+            opp = ob.PP.from_arrays(LOG_N, pp.export(1, 0), np.concatenate([pp.export(2, i) for i in range(LOG_N)], axis=0), G2_GENERATOR)
+            dtc, phases, cproof, _ = cpu_prove_full(LOG_N, opp)
+            assert cproof == proofs[0], "the CPU restatement's proof differs from the GPU proof"
+            cpu = {"value": 1e3 * dtc, "unit": UNIT, "cores": 1, "kind": "port", "same_config": True, "proof_bytes_equal_gpu": True,
+                   "sample": "one full proof of the same instance (2^%d constraints, same public parameters: the GPU-made ones, exported) by the "
+                             "literal C++ restatement of the reference on 1 core (the reference is single-threaded, Cargo.toml:26); nothing "
+                             "extrapolated; its proof bytes equal the GPU's" % LOG_N,
+                   "host_cpu": cpu_model(), "host_cores_available": os.cpu_count(), "phases_s": phases}
+        else:
+            dtc, phases, _ = cpu_prove_sample(cpu_log)
+            scale = 1 << (LOG_N - cpu_log)
+            est_s, factors = extrapolate_cpu(phases, dtc, cpu_log, LOG_N)
+            cpu = {"value": 1e3 * est_s, "unit": UNIT, "cores": 1, "kind": "port", "same_config": False, "extrapolated": True,
+                   "measured_sample_ms": 1e3 * dtc,
+                   "sample": "full prove at 2^%d constraints took %.2f s on 1 core (the reference is single-threaded, Cargo.toml:26); scaled to 2^%d "
+                             "per phase with the literal algorithm's operation counts (a blanket x%d would give %.0f ms)"
+                             % (cpu_log, dtc, LOG_N, scale, 1e3 * dtc * scale),
+                   "scaling_factors": factors,
+                   "host_cpu": cpu_model(), "host_cores_available": os.cpu_count(), "sample_phases_s": phases}
 
     line = {
         "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -351,7 +431,14 @@ def run_ours(args):
         "dtype": "u32 limbs (8 x u32 Montgomery Fr, 12 x u32 Fq; exact integer arithmetic)", "data": "synthetic",
         "config": {"workload": workload_name(LOG_N), "parallelism": "single GPU" if world == 1 else "hypercube sharded on the top %d variables" % (world.bit_length() - 1),
                    "l2": "working set (z, tables, 16x pre-shifted bases: > 4 GB) exceeds the 126 MB L2; no flush between steps",
+                   "collective": ("none (single GPU)" if world == 1 else
+                                  "data plane: per-round allgather of 96 B (and of one partial group element per MSM level) between the ranks' "
+                                  "HOST threads through a POSIX shared-memory mailbox (%s); the round results are Fiat-Shamir material that goes "
+                                  "through the host transcript anyway, so no device-side collective is on the path.  NCCL (torch.distributed) "
+                                  "only carries this script's barrier and its max-over-ranks timing reduction" % os.environ.get("SB_COMM", "shm")),
+                   "timing": "CUDA events around the K steps (device idle at both brackets), max over ranks; host clock alongside in timing_check",
                    "nnz": cs.nnz, "proof_bytes": len(proofs[0]), "setup_seconds_untimed": setup_s},
+        "proof_sha256": proof_sha, "sharded_check": sharded_check, "timing_check": event_s,
         "e2e": {"value": ms_e2e, "unit": UNIT, "h2d_bytes_per_step": (h1 - h0) // args.steps, "d2h_bytes_per_step": (d1 - d0) // args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
@@ -469,6 +556,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-log-n", type=int, default=None,
+                    help="CPU baseline on a 2^K sample scaled by the operation-count model instead of one real full-size proof")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

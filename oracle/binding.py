@@ -49,6 +49,12 @@ def lib():
     return _LIB
 
 
+def set_threads(k):
+    """TESTS ONLY: worker threads of the oracle's heavy loops (identical results for any k; see ec.hpp).  A CPU-baseline
+    timing must leave this at 1, the reference's configuration.  Returns the previous value."""
+    return int(lib().or_set_threads(C.c_int(int(k))))
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 

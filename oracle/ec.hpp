@@ -96,25 +96,37 @@ struct Jac {
 };
 
 // ark_ec batch_normalization_into_affine: Montgomery's simultaneous inversion
+// Worker threads of the heavy loops.  1 (the default) is the reference's configuration (Cargo.toml:26 never enables
+// `parallel`) and the only setting a CPU-baseline timing may use; or_set_threads(k > 1) is for the parity TESTS at the
+// full sizes (2^16, 2^20), where only the results matter -- every loop below is exact field / group arithmetic
+// whose result does not depend on the order of summation, so the bytes are identical for any thread count.
+static int g_oracle_threads = 1;
+
 template <typename F>
-static void batch_to_affine(const std::vector<Jac<F>>& in, std::vector<Affine<F>>& out) {
-    size_t n = in.size();
-    out.resize(n);
-    std::vector<F> prefix(n);
+static void batch_to_affine_range(const std::vector<Jac<F>>& in, std::vector<Affine<F>>& out, size_t lo, size_t hi) {
+    std::vector<F> prefix(hi - lo);
     F acc = F::one();
-    for (size_t i = 0; i < n; i++) {
-        prefix[i] = acc;
+    for (size_t i = lo; i < hi; i++) {
+        prefix[i - lo] = acc;
         if (!in[i].is_inf()) acc = F::mul(acc, in[i].Z);
     }
     F inv = F::inv(acc);
-    for (size_t i = n; i-- > 0;) {
+    for (size_t i = hi; i-- > lo;) {
         if (in[i].is_inf()) { out[i] = Affine<F>::inf(); continue; }
-        F zi = F::mul(inv, prefix[i]);
+        F zi = F::mul(inv, prefix[i - lo]);
         inv = F::mul(inv, in[i].Z);
         F zi2 = F::sqr(zi);
         out[i].x = F::mul(in[i].X, zi2);
         out[i].y = F::mul(in[i].Y, F::mul(zi2, zi));
     }
+}
+template <typename F>
+static void batch_to_affine(const std::vector<Jac<F>>& in, std::vector<Affine<F>>& out) {
+    size_t n = in.size();
+    out.resize(n);
+    const size_t parts = (g_oracle_threads > 1 && n >= 4096) ? (size_t)g_oracle_threads : 1;
+#pragma omp parallel for num_threads(g_oracle_threads) if (parts > 1) schedule(static)
+    for (size_t k = 0; k < parts; k++) batch_to_affine_range(in, out, n * k / parts, n * (k + 1) / parts);
 }
 
 // UPSTREAM ark_ec::msm::VariableBaseMSM::multi_scalar_mul (late-2020 shape): scalars are canonical
@@ -128,8 +140,12 @@ static Jac<F> msm_pippenger(const Affine<F>* bases, const uint64_t* scalars /* n
     int c = n < 32 ? 3 : ark_ln_without_floats(n) + 2;
     const int num_bits = 255;
     Jac<F> total = Jac<F>::inf();
-    std::vector<Jac<F>> window_sums;
-    for (int w_start = 0; w_start < num_bits; w_start += c) {
+    const int n_windows = (num_bits + c - 1) / c;
+    std::vector<Jac<F>> window_sums(n_windows);
+    // the windows are independent of one another (upstream runs them in a plain loop without `parallel`)
+#pragma omp parallel for num_threads(g_oracle_threads) if (g_oracle_threads > 1 && n >= 256) schedule(dynamic, 1)
+    for (int wi = 0; wi < n_windows; wi++) {
+        const int w_start = wi * c;
         Jac<F> res = Jac<F>::inf();
         std::vector<Jac<F>> buckets((size_t(1) << c) - 1, Jac<F>::inf());
         for (size_t i = 0; i < n; i++) {
@@ -152,7 +168,7 @@ static Jac<F> msm_pippenger(const Affine<F>* bases, const uint64_t* scalars /* n
             running = Jac<F>::add(running, buckets[b]);
             res = Jac<F>::add(res, running);
         }
-        window_sums.push_back(res);
+        window_sums[wi] = res;
     }
     // lowest window + sum_{w>0} 2^{cw} * window_w, Horner from the top
     Jac<F> acc = Jac<F>::inf();
@@ -184,6 +200,7 @@ static void fixed_base_mul(const Affine<F>& g, const uint64_t* scalars /* n x 4 
     std::vector<Affine<F>> tab;
     batch_to_affine(tabj, tab);
     std::vector<Jac<F>> res(n);
+#pragma omp parallel for num_threads(g_oracle_threads) if (g_oracle_threads > 1 && n >= 256) schedule(static)
     for (size_t i = 0; i < n; i++) {
         const uint64_t* s = scalars + 4 * i;
         Jac<F> acc = Jac<F>::inf();

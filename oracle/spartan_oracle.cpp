@@ -103,6 +103,13 @@ static void ser_index_info(Bytes& o, size_t max_multiplicands, size_t num_variab
 static void mle_fold(std::vector<Fr>& t, const Fr& r) {
     size_t half = t.size() / 2;
     Fr omr = Fr::sub(Fr::R1, r);
+    if (g_oracle_threads > 1 && half >= 512) {       // test-only threading (see g_oracle_threads): out of place
+        std::vector<Fr> o(half);
+#pragma omp parallel for num_threads(g_oracle_threads) schedule(static)
+        for (size_t b = 0; b < half; b++) o[b] = Fr::add(Fr::mul(t[2 * b], omr), Fr::mul(t[2 * b + 1], r));
+        t.swap(o);
+        return;
+    }
     for (size_t b = 0; b < half; b++)
         t[b] = Fr::add(Fr::mul(t[2 * b], omr), Fr::mul(t[2 * b + 1], r));
     t.resize(half);
@@ -115,7 +122,8 @@ static Fr mle_eval_at(std::vector<Fr> t, const std::vector<Fr>& point) {
 // src/data_structures/eq.rs:5-20
 static std::vector<std::vector<Fr>> eq_extension(const std::vector<Fr>& t) {
     size_t dim = t.size();
-    std::vector<std::vector<Fr>> result;
+    std::vector<std::vector<Fr>> result(dim);
+#pragma omp parallel for num_threads(g_oracle_threads) if (g_oracle_threads > 1 && dim >= 8) schedule(dynamic, 1)
     for (size_t i = 0; i < dim; i++) {
         std::vector<Fr> poly; poly.reserve(size_t(1) << dim);
         for (size_t x = 0; x < (size_t(1) << dim); x++) {
@@ -124,18 +132,18 @@ static std::vector<std::vector<Fr>> eq_extension(const std::vector<Fr>& t) {
             Fr ti_xi = Fr::mul(ti, xi);
             poly.push_back(Fr::add(Fr::sub(Fr::sub(Fr::add(ti_xi, ti_xi), xi), ti), Fr::R1));
         }
-        result.push_back(std::move(poly));
+        result[i] = std::move(poly);
     }
     return result;
 }
 
 // src/data_structures/r1cs_reader.rs:75-85
 static std::vector<Fr> sum_over_y(const Matrix& m, const std::vector<Fr>& z) {
-    std::vector<Fr> out; out.reserve(m.size());
-    for (auto& row : m) {
+    std::vector<Fr> out(m.size());
+    for (size_t x = 0; x < m.size(); x++) {
         Fr acc = Fr::ZERO;
-        for (auto& e : row) acc = Fr::add(acc, Fr::mul(e.first, z[e.second]));
-        out.push_back(acc);
+        for (auto& e : m[x]) acc = Fr::add(acc, Fr::mul(e.first, z[e.second]));
+        out[x] = acc;
     }
     return out;
 }
@@ -183,7 +191,19 @@ struct MLSumcheckProver {
         round++;
         size_t half = size_t(1) << (nv - round);
         std::vector<Fr> sums(max_multiplicands + 1, Fr::ZERO);
-        for (size_t b = 0; b < half; b++) {
+        if (g_oracle_threads > 1 && half >= 256) {       // test-only threading: per-thread partial sums, added in order
+            const int T = g_oracle_threads;
+            std::vector<std::vector<Fr>> part(T, std::vector<Fr>(max_multiplicands + 1, Fr::ZERO));
+#pragma omp parallel for num_threads(T) schedule(static)
+            for (int k = 0; k < T; k++) round_range(half * k / T, half * (k + 1) / T, part[k]);
+            for (int k = 0; k < T; k++) for (size_t t = 0; t <= max_multiplicands; t++) sums[t] = Fr::add(sums[t], part[k][t]);
+            return sums;
+        }
+        round_range(0, half, sums);
+        return sums;
+    }
+    void round_range(size_t b_lo, size_t b_hi, std::vector<Fr>& sums) const {
+        for (size_t b = b_lo; b < b_hi; b++) {
             Fr t_as_field = Fr::ZERO;
             for (size_t t = 0; t <= max_multiplicands; t++) {
                 Fr one_minus_t = Fr::sub(Fr::R1, t_as_field);
@@ -198,7 +218,6 @@ struct MLSumcheckProver {
                 t_as_field = Fr::add(t_as_field, Fr::R1);
             }
         }
-        return sums;
     }
 };
 
@@ -269,11 +288,13 @@ static Fr pc_open(const PublicParameter& pp, const std::vector<Fr>& poly, const 
         q[k].assign(size_t(1) << (k - 1), Fr::ZERO);
         r[k - 1].assign(size_t(1) << (k - 1), Fr::ZERO);
         Fr omp = Fr::sub(Fr::R1, point_at_k);
+#pragma omp parallel for num_threads(g_oracle_threads) if (g_oracle_threads > 1 && k >= 10) schedule(static)
         for (size_t b = 0; b < (size_t(1) << (k - 1)); b++) {
             q[k][b] = Fr::sub(r[k][(b << 1) + 1], r[k][b << 1]);
             r[k - 1][b] = Fr::add(Fr::mul(r[k][b << 1], omp), Fr::mul(r[k][(b << 1) + 1], point_at_k));
         }
         std::vector<uint64_t> scalars((size_t(4)) << k);
+#pragma omp parallel for num_threads(g_oracle_threads) if (g_oracle_threads > 1 && k >= 10) schedule(static)
         for (size_t x = 0; x < (size_t(1) << k); x++) q[k][x >> 1].to_canonical(&scalars[4 * x]);
         proofs.push_back(msm_pippenger<Fq2>(pp.powers_of_h[i].data(), scalars.data(), size_t(1) << k).to_affine());
         r[k].clear(); r[k].shrink_to_fit();
@@ -459,8 +480,11 @@ static int prove(const R1CS& cs, const PublicParameter& pp, const std::vector<Fr
     std::vector<Fr> m_comb(n, Fr::ZERO);
     {
         const Matrix* ms[3] = {&cs.a, &cs.b, &cs.c}; Fr rk[3] = {r_a, r_b, r_c};
+        std::vector<Fr> ev[3];
+#pragma omp parallel for num_threads(g_oracle_threads < 3 ? g_oracle_threads : 3) if (g_oracle_threads > 1) schedule(static, 1)
+        for (int k = 0; k < 3; k++) ev[k] = eval_on_x(*ms[k], r_x);
         for (int k = 0; k < 3; k++) {
-            std::vector<Fr> t = eval_on_x(*ms[k], r_x);
+            std::vector<Fr> t = std::move(ev[k]);
             for (auto& x : t) x = Fr::mul(x, rk[k]);                 // .multiply(r_k)
             for (size_t i = 0; i < n; i++) m_comb[i] = Fr::add(m_comb[i], t[i]);
             std::vector<std::vector<Fr>> prod; prod.push_back(std::move(t)); prod.push_back(z);
@@ -752,6 +776,8 @@ static G2Affine g2_generator() {
 extern "C" {
 
 int or_init() { ff_init_all(); return 0; }
+// test-only: worker threads of the heavy loops (see g_oracle_threads in ec.hpp); returns the previous value
+int or_set_threads(int k) { int old = g_oracle_threads; g_oracle_threads = k < 1 ? 1 : k; return old; }
 
 void or_fr_binop(int op, const Fr* a, const Fr* b, Fr* out, size_t n) {
     ff_init_all();

@@ -317,3 +317,32 @@ def test_prove_then_verify_accepts_and_rejects(oracle):
     assert oracle.verify(cs, pp, v, proof[:-1]) == 0              # truncated proof
     flipped = bytearray(proof); flipped[8 + 48 + 5] ^= 1          # z_rv_0
     assert oracle.verify(cs, pp, v, bytes(flipped)) <= 0
+
+
+def test_oracle_threading_does_not_change_a_byte(oracle):
+    # the full-size GPU parity tests (2^16, 2^20) run the literal prover's heavy loops on all host cores
+    # (oracle.set_threads, test-only); exact arithmetic makes the result independent of the thread count --
+    # checked here on proof bytes, every traced intermediate, keygen, commit and open
+    import r1cs_spartan_b200 as sb
+    log_n = 11
+    cs = sb.SyntheticR1CS(32, (1 << log_n) - 32, 0, 0x5EED0000 + log_n)
+    ocs = oracle.R1CS.from_csr(log_n, cs.mats)
+    g, h = oracle.generators()
+    t = oracle.fr_rand(77, log_n)
+    assert oracle.set_threads(1) == 1          # the default is the reference's configuration: one thread
+    pp1 = oracle.PP.keygen_with(log_n, g, h, t)
+    p1, tr1 = oracle.prove(ocs, pp1, cs.v, cs.w)
+    table = oracle.fr_rand(5, 1 << log_n); point = oracle.fr_rand(6, log_n)
+    c1, o1 = pp1.commit(table), pp1.open(table, point)
+    oracle.set_threads(5)
+    try:
+        pp5 = oracle.PP.keygen_with(log_n, g, h, t)
+        p5, tr5 = oracle.prove(ocs, pp5, cs.v, cs.w)
+        c5, o5 = pp5.commit(table), pp5.open(table, point)
+    finally:
+        oracle.set_threads(1)
+    assert p1 == p5
+    for k in ("az", "bz", "cz", "sc1_evals", "sc2_evals", "vabc", "m_comb", "commitment", "open1_proofs", "open2_proofs", "r_x", "r_y"):
+        assert tr1.blob(k) == tr5.blob(k), k
+    assert np.array_equal(pp1.g2_all(), pp5.g2_all()) and np.array_equal(pp1.g1(0), pp5.g1(0)) and np.array_equal(pp1.g_mask(), pp5.g_mask())
+    assert np.array_equal(c1, c5) and np.array_equal(o1[0], o5[0]) and np.array_equal(o1[1], o5[1])

@@ -292,21 +292,7 @@ def _prove_both(sb, oracle, ctx, log_n, num_public, density, seed):
 def test_prove_bytes_and_trace_match_oracle(sb, oracle, gpu_ctx, log_n, num_public, density):
     proof, tr, oproof, otr = _prove_both(sb, oracle, gpu_ctx, log_n, num_public, density, 0x5EED0000 + log_n)
     assert len(proof) == len(oproof)
-    # intermediates first, so that a mismatch is reported at the earliest stage
-    assert np.array_equal(tr.commitment, np.frombuffer(otr.blob("commitment"), dtype=np.uint64))
-    assert np.array_equal(tr.r_v, otr.fr("r_v"))
-    assert np.array_equal(tr.z_rv_0, otr.fr("z_rv_0")[0])
-    assert np.array_equal(tr.open1_proofs.reshape(-1), np.frombuffer(otr.blob("open1_proofs"), dtype=np.uint64))
-    assert np.array_equal(tr.tor, otr.fr("tor"))
-    assert np.array_equal(tr.az, otr.fr("az")) and np.array_equal(tr.bz, otr.fr("bz")) and np.array_equal(tr.cz, otr.fr("cz"))
-    assert np.array_equal(tr.sc1_evals.reshape(-1, 4), otr.fr("sc1_evals"))
-    assert np.array_equal(tr.r_x, otr.fr("r_x"))
-    assert np.array_equal(tr.vabc, otr.fr("vabc"))
-    assert np.array_equal(tr.r_abc, otr.fr("r_abc"))
-    assert np.array_equal(tr.sc2_evals.reshape(-1, 4), otr.fr("sc2_evals"))
-    assert np.array_equal(tr.r_y, otr.fr("r_y"))
-    assert np.array_equal(tr.z_ry, otr.fr("z_ry")[0])
-    assert np.array_equal(tr.open2_proofs.reshape(-1), np.frombuffer(otr.blob("open2_proofs"), dtype=np.uint64))
+    _assert_trace_equal(tr, otr)     # intermediates first, so that a mismatch is reported at the earliest stage
     assert proof == oproof
 
 
@@ -433,31 +419,77 @@ def test_wire_formats_carry_keys_and_proofs(sb, oracle, gpu_ctx):
     assert oracle.verify(oracle.R1CS.from_csr(log_n, mats), vp, cs.v, proof) == 1
 
 
+def _assert_trace_equal(tr, otr):
+    """every intermediate the reference's prover produces, earliest stage first (BASELINE.json configs 2 and 3)"""
+    assert np.array_equal(tr.commitment, np.frombuffer(otr.blob("commitment"), dtype=np.uint64)), "commitment"
+    assert np.array_equal(tr.r_v, otr.fr("r_v")), "r_v"
+    assert np.array_equal(tr.z_rv_0, otr.fr("z_rv_0")[0]), "z(r_v, 0)"
+    assert np.array_equal(tr.open1_proofs.reshape(-1), np.frombuffer(otr.blob("open1_proofs"), dtype=np.uint64)), "first opening"
+    assert np.array_equal(tr.tor, otr.fr("tor")), "tor"
+    assert np.array_equal(tr.az, otr.fr("az")), "Az"
+    assert np.array_equal(tr.bz, otr.fr("bz")), "Bz"
+    assert np.array_equal(tr.cz, otr.fr("cz")), "Cz"
+    assert np.array_equal(tr.sc1_evals.reshape(-1, 4), otr.fr("sc1_evals")), "first sumcheck messages"
+    assert np.array_equal(tr.r_x, otr.fr("r_x")), "r_x"
+    assert np.array_equal(tr.vabc, otr.fr("vabc")), "va vb vc"
+    assert np.array_equal(tr.r_abc, otr.fr("r_abc")), "r_a r_b r_c"
+    assert np.array_equal(tr.sc2_evals.reshape(-1, 4), otr.fr("sc2_evals")), "second sumcheck messages"
+    assert np.array_equal(tr.r_y, otr.fr("r_y")), "r_y"
+    assert np.array_equal(tr.z_ry, otr.fr("z_ry")[0]), "z(r_y)"
+    assert np.array_equal(tr.open2_proofs.reshape(-1), np.frombuffer(otr.blob("open2_proofs"), dtype=np.uint64)), "second opening"
+
+
 @pytest.mark.parametrize("log_n", [16, 20])
-def test_full_size_prove_is_accepted(sb, oracle, gpu_ctx, log_n):
-    # BASELINE.json's sizes (2^16, 2^20), where the literal CPU prover is too slow to be the checker: the
-    # size-independent property is prove -> verify (benchmark.rs:35-47) with the CPU pairing verifier, whose
-    # parameters are the g^{t_i} of the GPU keygen, and a proof for a corrupted witness must be rejected.
+def test_full_size_prove_is_bit_exact_and_accepted(sb, oracle, gpu_ctx, log_n):
+    # BASELINE.json configs 2 (2^16) and 3 (2^20, the north-star size): the benchmark circuit of benchmark.rs:63-65
+    # proved on the GPU and by the literal CPU restatement on THE SAME public parameters, compared bit for bit on
+    # Az/Bz/Cz, every message of both sumchecks, va/vb/vc, the commitment, both openings, every challenge and the
+    # proof bytes.  The oracle is given the GPU-made parameters (the GPU keygen itself is checked level by level
+    # against the oracle's literal setup.rs in test_keygen_matches_oracle) and runs its heavy loops on all host
+    # cores -- test-only threading, the bytes do not depend on it (tests/test_cpu_oracle.py checks that).
+    import os
     cs = sb.SyntheticR1CS(32, (1 << log_n) - 32, 0, 0x5EED0000 + log_n)
     g, h = oracle.generators()
     t = oracle.fr_rand(2024 + log_n, log_n)
-    pp = sb.MLPolyCommit.keygen(log_n, g, h, t, ctx=gpu_ctx)
+    pp = sb.MLPolyCommit.keygen(log_n, g, h, t, keep_all_levels=True, ctx=gpu_ctx)
     pk = sb.MLArgumentForR1CS.index(*cs.mats, ctx=gpu_ctx)
-    proof = sb.MLArgumentForR1CS.prove(pk, cs.v, cs.w, pp)
+    proof, tr = sb.MLArgumentForR1CS.prove(pk, cs.v, cs.w, pp, trace=True)
     assert len(proof) == sb.load_library().sb_proof_size(log_n)
     ocs = oracle.R1CS.from_csr(log_n, cs.mats)
+    # prove -> verify (benchmark.rs:35-47) with the CPU pairing verifier on the g^{t_i} of the GPU keygen
     vp = oracle.PP.verifier_only(log_n, g, h, pp.g_mask_random())
     assert oracle.verify(ocs, vp, cs.v, proof) == 1
     if log_n <= 16:
         w_bad = cs.w.copy(); w_bad[12345 % len(w_bad)] = oracle.fr_rand(1, 1)[0]
         assert oracle.verify(ocs, vp, cs.v, sb.MLArgumentForR1CS.prove(pk, cs.v, w_bad, pp)) < 0
-    # the commitment scheme alone on a random table of the same size (commitment/mod.rs:66-83
-    # commit_open_verify_bench): commit, open at a random point, pairing check; a wrong value must fail
+    # the literal prover on the same parameters
+    opp = oracle.PP.from_arrays(log_n, pp.export(1, 0), np.concatenate([pp.export(2, i) for i in range(log_n)], axis=0), h)
+    old = oracle.set_threads(int(os.environ.get("SB_ORACLE_THREADS", os.cpu_count() or 1)))
+    try:
+        oproof, otr = oracle.prove(ocs, opp, cs.v, cs.w)
+    finally:
+        oracle.set_threads(old)
+    _assert_trace_equal(tr, otr)
+    assert proof == oproof
+    # the witness kept in HBM (bench.py's `value` arm) gives the same bytes
+    wit = sb.Witness(pk, cs.v, cs.w)
+    assert sb.MLArgumentForR1CS.prove(pk, None, None, pp, witness=wit) == proof
+    # BASELINE.json config 4 on one GPU: the commitment scheme alone on a random table of the same size
+    # (commitment/mod.rs:66-83 commit_open_verify_bench): commit and open equal the oracle's, the pairing check
+    # accepts, a wrong value fails
     table = oracle.fr_rand(5 + log_n, 1 << log_n); point = oracle.fr_rand(6 + log_n, log_n)
     _, com = sb.MLPolyCommit.commit(pp, table)
     ev, (_, proofs) = sb.MLPolyCommit.open(pp, table, point)
     assert oracle.pc_verify(vp, com, point, ev, proofs)
     assert not oracle.pc_verify(vp, com, point, oracle.fr_rand(7, 1)[0], proofs)
+    if log_n <= 16:
+        old = oracle.set_threads(int(os.environ.get("SB_ORACLE_THREADS", os.cpu_count() or 1)))
+        try:
+            assert np.array_equal(com, opp.commit(table))
+            oev, oproofs = opp.open(table, point)
+        finally:
+            oracle.set_threads(old)
+        assert np.array_equal(ev, oev) and np.array_equal(proofs, oproofs)
 
 
 def test_msm_knobs_forced_on_small_inputs():
