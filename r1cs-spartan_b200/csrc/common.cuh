@@ -44,13 +44,21 @@ extern bool g_sb_prof_on;
 extern int g_sb_prof_tag;
 void sb_prof_begin(const char* name, cudaStream_t stream);
 void sb_prof_end(cudaStream_t stream);
-#define SB_LAUNCH_NAMED(name, kernel, grid, block, smem, stream, ...)  \
-    do {                                                               \
-        if (g_sb_prof_on) sb_prof_begin(name, stream);                 \
-        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
-        if (g_sb_prof_on) sb_prof_end(stream);                         \
-        g_sb_launches++;                                               \
-        SB_CUDA(cudaGetLastError());                                   \
+#if defined(SB_EMUL)
+// tests/emul (CUDA-on-CPU test shim, never part of the product build): the launch runs the kernel's threads on the host
+#define SB_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch(dim3(grid), dim3(block), (smem), [&] { kernel(__VA_ARGS__); })
+#define SB_DYN_SMEM(name) unsigned char* name = emu::g_block->dyn_smem
+#else
+#define SB_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define SB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+#define SB_LAUNCH_NAMED(name, kernel, grid, block, smem, stream, ...)                \
+    do {                                                                             \
+        if (g_sb_prof_on) sb_prof_begin(name, stream);                               \
+        SB_KERNEL_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__);            \
+        if (g_sb_prof_on) sb_prof_end(stream);                                       \
+        g_sb_launches++;                                                             \
+        SB_CUDA(cudaGetLastError());                                                 \
     } while (0)
 #define SB_LAUNCH(kernel, grid, block, smem, stream, ...) SB_LAUNCH_NAMED(#kernel, kernel, grid, block, smem, stream, __VA_ARGS__)
 // kernel names for the two instantiations of the group templates

@@ -1,16 +1,24 @@
-// msm.cuh -- Pippenger bucket MSM over G1 / G2 with pre-shifted fixed bases, plus the fixed-base
+// msm.cuh -- batched Pippenger bucket MSM over G1 / G2 with pre-shifted fixed bases, plus the fixed-base
 // scalar multiplication used by keygen.
 //
 // Replaces upstream ark_ec::msm::VariableBaseMSM::multi_scalar_mul as called from
-// src/commitment/commit.rs:25 (G1) and src/commitment/open.rs:49 (G2), and
+// src/commitment/commit.rs:25 (G1) and src/commitment/open.rs:49 (G2, once per level of an opening), and
 // ark_ec::msm::FixedBaseMSM::multi_scalar_mul as called from src/commitment/setup.rs:61-70.
 //
-// Design (DESIGN.md "MSM"): the bases are the public parameters, fixed for the life of the handle,
-// so at load time every base P_i is expanded into its window multiples 2^(c w) P_i (affine).  With
-// those, every signed c-bit digit of every scalar lands in ONE shared set of 2^(c-1) buckets and
-// the usual per-window Horner recombination (255 serial doublings) disappears: the MSM is
-//     digits -> counting sort by (window, bucket) -> one thread per (window, bucket) accumulates
-//     mixed additions -> windows merged per bucket -> sum_k k B_k by chunked running sums.
+// Design (DESIGN.md "MSM"):
+//  * The bases are the public parameters, fixed for the life of the handle, so at load time every base P_i is
+//    expanded into its window multiples 2^(shift_w) P_i (affine).  With those, every signed digit of every scalar
+//    lands in ONE shared set of 2^(c-1) buckets and the per-window Horner recombination (255 serial doublings)
+//    disappears.
+//  * An opening needs one MSM per level of the quotient pyramid (open.rs:37-51): sizes 2^(nv-1), 2^(nv-2), ..., 1.
+//    They are independent and individually latency-bound below ~2^14 points, so they are run as ONE pipeline: an
+//    MsmGroup is a list of SLOTS (one MSM each, own bases / window layout / output point) whose buckets are laid
+//    side by side in one index space; digits -> plan -> scatter -> chunked accumulation -> bucket reduction each
+//    run ONCE over all slots.  A proof is three such pipelines (commit, two openings) instead of 41 MSMs.
+//  * No host synchronisation inside a pipeline: everything the later kernels need (entry count, number of
+//    accumulation levels, chunk plans) is computed on the device by k_scan_plan and read from device memory; the
+//    host launches grids sized by upper bounds it can compute from the slot sizes alone, and a fixed number of
+//    accumulation levels (unused levels exit at once).
 #pragma once
 #include "common.cuh"
 
@@ -25,58 +33,56 @@ struct WinLayout {
 };
 WinLayout msm_layout(size_t m);
 
-constexpr int MSM_MAX_LEVELS = 16;
-constexpr int MSM_MAX_HALVINGS = 8;      // batched-affine pairwise rounds before the XYZZ accumulation
-constexpr int MSM_INFO_WORDS = 32;       // entries, longest run, S0, levels, S1, R, halving totals[8] at 6, items[16] at 14, spare
-constexpr int MSM_INFO_HTOT = 6, MSM_INFO_ITEMS = 14;
+constexpr int MSM_MAX_SLOTS = 32;
+constexpr int MSM_MAX_LEVELS = 8;        // accumulation levels a pipeline launches (levels the plan does not use exit at once)
+constexpr int MSM_INFO_WORDS = 32;       // see k_scan_plan: entries, longest run, S0, levels, S1, items[MSM_MAX_LEVELS] at 8
+constexpr int MSM_INFO_ITEMS = 8;
 
-// Scratch of one MSM over one base table; kept with the table and reused by every proof (allocated on first
-// use, grown on demand), so that the steady state performs no device allocation at all.
+// One MSM of a group: m points, its own window layout, its own range of the shared table / bucket / reduction spaces.
+struct MsmSlot {
+    uint32_t m;          // points (= scalars)
+    uint32_t mbase;      // first global point index (prefix sum of m over the slots)
+    uint32_t ebase;      // table: tab[ebase + w * m + i] = 2^(shift[w]) * P_i; the same index space numbers the entries
+    uint32_t bbase;      // first bucket; the slot owns nb = 2^(c-1) buckets
+    uint32_t nb;
+    uint32_t red_l;      // buckets per thread in the first reduction stage
+    uint32_t rbase;      // first CTA of the first reduction stage; the slot owns rblocks CTAs
+    uint32_t rblocks;
+    WinLayout lay;
+};
+
+// Scratch of one group; kept with the tables and reused by every proof (allocated when the group is prepared),
+// so that the steady state performs no device allocation at all.
 template <class F>
 struct MsmScratch {
     DevBuf<uint32_t> codes, sorted, counts, offsets, cursors, info, perm, invperm;
     DevBuf<uint32_t> plan[MSM_MAX_LEVELS];
-    DevBuf<uint32_t> hplan[MSM_MAX_HALVINGS];
-    DevBuf<AffinePt<F>> affA, affB;        // outputs of the pairwise rounds (ping-pong)
-    DevBuf<F> prefix;                      // per-thread prefix products of the simultaneous inversion
     DevBuf<XyzzPt<F>> ptsA, ptsB, block_out;
 };
 
 template <class F>
-struct MsmBases {
-    DevBuf<AffinePt<F>> tab;   // [W][m]: tab[w * m + i] = 2^(shift[w]) * P_i
-    size_t m = 0;
-    WinLayout lay{};
+struct MsmGroup {
+    DevBuf<AffinePt<F>> tab;         // every slot's pre-shifted table, back to back (MsmSlot::ebase)
+    std::vector<MsmSlot> slots;
+    DevBuf<MsmSlot> slots_dev;
+    uint32_t mtot = 0, etot = 0, btot = 0, rtot = 0;
+    uint32_t s0 = 0;                 // chunk length of the first accumulation level (fixed when the group is prepared)
+    uint32_t items_bound[MSM_MAX_LEVELS] = {};   // upper bounds on the chunk count of every level (grid sizes)
     mutable MsmScratch<F> scratch;
+    size_t nslots() const { return slots.size(); }
 };
 
-// One MSM in flight: phase A (digits, counting sort, run statistics) and phase B (chunked accumulation,
-// bucket reduction) are separate so that a whole ladder of MSMs can be queued on several streams with a
-// single host synchronisation in between.
-template <class F>
-struct MsmJob {
-    const MsmBases<F>* bases = nullptr;
-    const Fr* scalars = nullptr;
-    size_t m = 0;
-    XyzzPt<F>* out = nullptr;
-    cudaStream_t stream = nullptr;
-    uint32_t* info_host = nullptr;     // pinned, MSM_INFO_WORDS words (see k_scan_plan)
-    bool top = false;                  // first (largest) level of an opening: its accumulation is profiled under its own name
-    // Optional second (high-priority) stream + hand-over event: everything after the first accumulation level --
-    // the latency-bound part of the job -- is queued there, so that it is not dispatched behind the
-    // throughput-bound accumulation kernels of the other jobs; `stream` is joined to it again at the end.
-    cudaStream_t tail_stream = nullptr;
-    cudaEvent_t tail_event = nullptr;
-};
-template <class F> void msm_begin(MsmJob<F>& job);
-template <class F> void msm_finish(MsmJob<F>& job);   // job.stream must have been synchronised after msm_begin
+// per-slot scalar arrays of one run (Montgomery Fr on the device); passed to the digit kernel by value
+struct MsmScalarPtrs { const Fr* p[MSM_MAX_SLOTS]; };
 
-// expand affine bases (device) into their window multiples
+// Expand the affine bases of every slot (device arrays, bases_dev[j] has m[j] points) into the group's tables and
+// allocate its scratch.  Synchronous with respect to `stream` only.
 template <class F>
-void msm_prepare(const AffinePt<F>* bases_dev, size_t m, MsmBases<F>& out, cudaStream_t stream);
-// out_dev <- sum_i scalars[i] * P_i   (scalars: Montgomery Fr on the device; result XYZZ on the device)
+void msm_group_prepare(const std::vector<const AffinePt<F>*>& bases_dev, const std::vector<size_t>& m, MsmGroup<F>& out, cudaStream_t stream);
+// Queue the whole pipeline on `stream`: out_dev[j] <- sum_i scalars[j][i] * P_{j,i} (XYZZ) for every slot j.
+// Nothing is synchronised; the caller reads out_dev in stream order.
 template <class F>
-void msm_run(const MsmBases<F>& bases, const Fr* scalars_dev, size_t m, XyzzPt<F>* out_dev, cudaStream_t stream);
+void msm_group_run(const MsmGroup<F>& g, const MsmScalarPtrs& scalars, XyzzPt<F>* out_dev, cudaStream_t stream, const char* tag = nullptr);
 
 // out[i] = scalars[i] * g for n scalars (device, Montgomery), affine results (device)
 template <class F>

@@ -33,21 +33,15 @@ struct sb_ctx {
     DevBuf<unsigned int> ticket;
     DevBuf<Fr> d_mail;                 // device scratch for scalars going in / results coming out
     PinnedBuf<Fr> h_mail;
-    // auxiliary streams: the ladder of G2 MSMs of one opening runs concurrently on these
-    // one stream per ladder level.  Levels 4.. (small, latency-bound: ~4 ms of dependent point additions whatever
-    // their size) run at the highest priority so that their short kernels always find a slot; the four large,
-    // throughput-bound levels follow in decreasing size.
-    static constexpr int NAUX = 32;
-    static constexpr int NBIG = 8;     // jobs 0..NBIG-1 of a ladder are the throughput-bound ones (2^-8 of the work is below)
-    cudaStream_t aux[NAUX] = {};       // one per MSM job of a ladder; [0, NBIG) low priority, the rest high
-    cudaStream_t tail[NBIG] = {};      // high priority: the latency-bound tails of the big jobs
-    cudaEvent_t ev_tail[NBIG] = {};
+    // auxiliary streams: an opening may be split into several MSM groups (pipelines) that run concurrently, so that the
+    // latency-bound end of one (later accumulation levels, bucket reduction) hides behind the throughput-bound
+    // accumulation of the next; the sharded prover's tail opening is one more group
+    static constexpr int NAUX = 4;
+    cudaStream_t aux[NAUX] = {};
     cudaEvent_t ev_main = nullptr, ev_aux[NAUX] = {};
-    PinnedBuf<uint32_t> msm_info;      // 8 words per ladder level
     cudaStream_t copy_stream = nullptr; // witness upload that overlaps the commitment (sharded sb_prove)
     cudaEvent_t ev_copy = nullptr;
-    bool serial_msm = false;           // profiling aid: keep every MSM on the main stream
-    int n_tails = 0;                   // SB_MSM_TAILS: the n largest jobs of a ladder run their tails on high-priority streams
+    bool serial_msm = false;           // profiling aid: keep every MSM group on the main stream
     RoundWs ws{};
     static constexpr int MAIL = 256;
     // mailbox slots
@@ -97,8 +91,12 @@ struct sb_pp {
     sb_ctx* ctx = nullptr;
     uint32_t nv = 0;            // variables handled by g1 / g2 below
     uint32_t nv_total = 0;      // variables of the whole polynomial
-    MsmBases<Fq> g1;                              // powers_of_g[0] (slice)
-    std::vector<MsmBases<Fq2>> g2;                // g2[L] = powers_of_h[L] (slice) for L = 1..nv-1, g2[nv] = {last base}
+    MsmGroup<Fq> g1;                              // one slot: powers_of_g[0] (slice)
+    // The opening ladder: slot i (= proof element i, open.rs:49) is the MSM over powers_of_h[i+1] (slice)
+    // for i < nv - 1 and over {last base} for i = nv - 1.  The slots are spread over one or more groups, each one
+    // pipeline (group k holds ladder slots [g2_first[k], g2_first[k+1])).
+    std::vector<std::unique_ptr<MsmGroup<Fq2>>> g2;
+    std::vector<uint32_t> g2_first;
     std::unique_ptr<sb_pp> tail;
     G1Aff g_host; G2Aff h_host;                   // the caller's generators (h goes into every opening proof)
     bool have_g = false;
@@ -345,16 +343,38 @@ static sb_index* index_create(sb_ctx* c, uint32_t log_n, const sb_csr* mats[3]) 
 }
 
 // ====================================================================== public parameters
+// How the nv slots of an opening ladder are grouped into pipelines.  SB_MSM_SPLIT=k (default 2): up to k groups of
+// roughly equal work -- the ladder halves from slot to slot, so group 0 = {slot 0} carries half of it, group 1 = {slot 1}
+// a quarter, ..., the last group takes the rest.  Small ladders (< 2^12 points) stay one group.
+static std::vector<uint32_t> ladder_split(uint32_t nv) {
+    static const int k_env = getenv("SB_MSM_SPLIT") ? atoi(getenv("SB_MSM_SPLIT")) : 2;
+    static const int min_nv = getenv("SB_MSM_SPLIT_MIN_NV") ? atoi(getenv("SB_MSM_SPLIT_MIN_NV")) : 12;   // (tests force splits on small ladders)
+    int k = std::min(std::max(k_env, 1), (int)sb_ctx::NAUX);
+    if ((int)nv < min_nv) k = 1;
+    std::vector<uint32_t> first;
+    for (int i = 0; i < k && (uint32_t)i < nv; i++) first.push_back((uint32_t)i);
+    first.push_back(nv);
+    return first;
+}
+
 // expand device-resident affine levels into the MSM tables of one parameter set
 static void pp_prepare(sb_ctx* c, sb_pp* pp, const G1Aff* g1_level0_dev, const std::vector<const G2Aff*>& g2_levels_dev /* index L, 1..nv-1 */,
                        const G2Aff& last_base) {
-    uint32_t nv = pp->nv;
-    if (g1_level0_dev) msm_prepare<Fq>(g1_level0_dev, (size_t)1 << nv, pp->g1, c->stream);
-    pp->g2.resize(nv + 1);
-    for (uint32_t L = 1; L < nv; L++) msm_prepare<Fq2>(g2_levels_dev[L], (size_t)1 << (nv - L), pp->g2[L], c->stream);
+    const uint32_t nv = pp->nv;
+    if (g1_level0_dev) msm_group_prepare<Fq>({g1_level0_dev}, {(size_t)1 << nv}, pp->g1, c->stream);
     DevBuf<G2Aff> hdev(1, c->stream);
     SB_CUDA(cudaMemcpyAsync(hdev.get(), &last_base, sizeof(G2Aff), cudaMemcpyHostToDevice, c->stream));
-    msm_prepare<Fq2>(hdev.get(), 1, pp->g2[nv], c->stream);
+    pp->g2_first = ladder_split(nv);
+    pp->g2.clear();
+    for (size_t k = 0; k + 1 < pp->g2_first.size(); k++) {
+        std::vector<const G2Aff*> bases; std::vector<size_t> ms;
+        for (uint32_t i = pp->g2_first[k]; i < pp->g2_first[k + 1]; i++) {
+            if (i + 1 < nv) { bases.push_back(g2_levels_dev[i + 1]); ms.push_back((size_t)1 << (nv - i - 1)); }
+            else { bases.push_back(hdev.get()); ms.push_back(1); }
+        }
+        pp->g2.emplace_back(new MsmGroup<Fq2>);
+        msm_group_prepare<Fq2>(bases, ms, *pp->g2.back(), c->stream);
+    }
     ctx_sync(c);
 }
 
@@ -484,7 +504,9 @@ static sb_pp* pp_keygen(sb_ctx* c, uint32_t nv, const void* g, const void* h, co
 static G1Aff commit_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full) {
     DevBuf<G1Xyzz> out(1, c->stream);
     const size_t nl = (size_t)1 << pp->nv;
-    msm_run<Fq>(pp->g1, z_dev_full + (size_t)c->rank * nl, nl, out.get(), c->stream);
+    MsmScalarPtrs sp{};
+    sp.p[0] = z_dev_full + (size_t)c->rank * nl;
+    msm_group_run<Fq>(pp->g1, sp, out.get(), c->stream);
     G1Xyzz mine; fetch_xyzz(c, out.get(), 1, &mine);
     if (!c->sharded()) return xyzz_to_affine_host(mine);
     std::vector<G1Xyzz> all(c->world);
@@ -512,43 +534,29 @@ static void open_folds(sb_ctx* c, uint32_t nv, const Fr* table_dev, int point_sl
     }
     SB_CUDA(cudaMemcpyAsync(c->d_mail.get() + out_slot, cur, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
 }
-// Stage 2 -- the nv MSMs of one parameter set as jobs; they are independent of one another.
-static void open_add_jobs(sb_ctx* c, const sb_pp* pp, const Fr* q, G2Xyzz* res_dev, std::vector<MsmJob<Fq2>>& jobs) {
-    for (uint32_t i = 0; i < pp->nv; i++) {
-        size_t half = (size_t)1 << (pp->nv - i - 1);
-        jobs.emplace_back();
-        MsmJob<Fq2>& j = jobs.back();
-        size_t k = jobs.size() - 1;
-        j.bases = &pp->g2[i + 1]; j.scalars = q + half; j.m = half; j.out = res_dev + i;
-        j.top = (i == 0 && pp->nv >= 8);
-        j.stream = c->serial_msm ? c->aux[0] : c->aux[k % sb_ctx::NAUX]; j.info_host = c->msm_info.get() + MSM_INFO_WORDS * k;
-        if (!c->serial_msm && k < (size_t)c->n_tails) { j.tail_stream = c->tail[k]; j.tail_event = c->ev_tail[k]; }
-    }
-}
-// Stage 3 -- run every queued job: one stream per job (largest first = highest priority, so the latency-bound
-// tails of the small ones hide behind the throughput-bound accumulation of the large ones), one host
-// synchronisation between the sorting phase and the accumulation phase.
-static void open_run_jobs(sb_ctx* c, std::vector<MsmJob<Fq2>>& jobs) {
+// Stage 2 -- the nv MSMs of one parameter set: every group of the ladder is one pipeline, queued without any host
+// synchronisation.  Group 0 runs on the main stream, the others on auxiliary streams (first_aux, first_aux + 1, ..)
+// that wait for the folds and are joined to the main stream again.
+static void open_queue_msms(sb_ctx* c, const sb_pp* pp, const Fr* q, G2Xyzz* res_dev, int first_aux, bool main_too) {
     cudaStream_t st = c->stream;
-    SB_CUDA(cudaEventRecord(c->ev_main, st));
-    const int na = (int)std::min<size_t>(jobs.size(), sb_ctx::NAUX);
-    for (int s = 0; s < na; s++) SB_CUDA(cudaStreamWaitEvent(c->aux[s], c->ev_main, 0));
-    // SB_MSM_ORDER: 2 (default) = wait per job, largest first (its accumulation starts while the smaller jobs
-    // are still sorting; 16.9 against 18.0 ms at 2^17); 0 = all sorts, one wait, accumulations largest first;
-    // 1 = accumulations smallest first (measured slower: the large jobs start late)
-    static const int order = getenv("SB_MSM_ORDER") ? atoi(getenv("SB_MSM_ORDER")) : 2;
-    for (auto& j : jobs) msm_begin(j);
-    g_sb_d2h_bytes += 4 * MSM_INFO_WORDS * jobs.size();
-    if (order == 2) {
-        for (auto& j : jobs) { SB_CUDA(cudaStreamSynchronize(j.stream)); msm_finish(j); }
-    } else {
-        for (int s = 0; s < na; s++) SB_CUDA(cudaStreamSynchronize(c->aux[s]));
-        if (order == 1) for (size_t k = jobs.size(); k-- > 0;) msm_finish(jobs[k]);
-        else for (auto& j : jobs) msm_finish(j);
-    }
-    for (int s = 0; s < na; s++) {
-        SB_CUDA(cudaEventRecord(c->ev_aux[s], c->aux[s]));
-        SB_CUDA(cudaStreamWaitEvent(st, c->ev_aux[s], 0));
+    const size_t ng = pp->g2.size();
+    for (size_t k = 0; k < ng; k++) {
+        MsmScalarPtrs sp{};
+        const uint32_t i0 = pp->g2_first[k];
+        for (uint32_t i = i0; i < pp->g2_first[k + 1]; i++) sp.p[i - i0] = q + ((size_t)1 << (pp->nv - i - 1));
+        cudaStream_t s = st;
+        int a = -1;
+        if (!c->serial_msm && !(k == 0 && main_too)) {
+            a = (first_aux + (int)k - (main_too ? 1 : 0)) % sb_ctx::NAUX;
+            s = c->aux[a];
+            SB_CUDA(cudaEventRecord(c->ev_main, st));
+            SB_CUDA(cudaStreamWaitEvent(s, c->ev_main, 0));
+        }
+        msm_group_run<Fq2>(*pp->g2[k], sp, res_dev + i0, s);
+        if (a >= 0) {
+            SB_CUDA(cudaEventRecord(c->ev_aux[a], s));
+            SB_CUDA(cudaStreamWaitEvent(st, c->ev_aux[a], 0));
+        }
     }
 }
 
@@ -566,11 +574,11 @@ static void open_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full, const Fr*
     SB_REQUIRE(total <= 64, "nv too large for the mailbox");
     h2d_fr(c, sb_ctx::SLOT_VEC2, point_host, total);
     DevBuf<G2Xyzz> res(total, st);
-    DevBuf<Fr> tt, t0, t1, tq;                      // tail scratch (must outlive the jobs)
-    std::vector<MsmJob<Fq2>> jobs;
-    jobs.reserve(total);
+    DevBuf<Fr> tt, t0, t1, tq;                      // tail scratch (must outlive the queued kernels: freed in stream order)
     open_folds(c, loc, z_dev_full + (size_t)c->rank * nl, sb_ctx::SLOT_VEC2, r0, r1, q, sb_ctx::SLOT_OUT);
-    open_add_jobs(c, pp, q.get(), res.get(), jobs);
+    // sharded: the local pipelines go to auxiliary streams at once, so that the main stream is free for the exchange of
+    // the folded values and the (tiny) tail opening, which then overlap them
+    open_queue_msms(c, pp, q.get(), res.get(), 0, !c->sharded());
     if (c->sharded()) {
         Fr folded; d2h_fr(c, sb_ctx::SLOT_OUT, &folded, 1);
         std::vector<Fr> tail_tab(G);
@@ -580,9 +588,8 @@ static void open_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full, const Fr*
         g_sb_h2d_bytes += G * sizeof(Fr);
         open_folds(c, g, tt.get(), sb_ctx::SLOT_VEC2 + loc, t0, t1, tq, sb_ctx::SLOT_OUT);
         ctx_sync(c);                                // tail_tab (host) is read by the async copy above
-        open_add_jobs(c, pp->tail.get(), tq.get(), res.get() + loc, jobs);
+        open_queue_msms(c, pp->tail.get(), tq.get(), res.get() + loc, (int)pp->g2.size(), true);
     }
-    open_run_jobs(c, jobs);
     std::vector<G2Xyzz> pts(total);
     fetch_xyzz(c, res.get(), total, pts.data());
     d2h_fr(c, sb_ctx::SLOT_OUT, eval_out, 1);
@@ -885,25 +892,9 @@ sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
         SB_CUDA(cudaMemsetAsync(c->ticket.get(), 0, sizeof(unsigned int), c->stream));
         c->d_mail.alloc(sb_ctx::MAIL, c->stream);
         c->h_mail.alloc(sb_ctx::MAIL);
-        c->msm_info.alloc(MSM_INFO_WORDS * 64);
-        int prio_least = 0, prio_greatest = 0;
-        SB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-        // Optional priorities (both OFF by default, see DESIGN.md "what was tried"): SB_MSM_TAILS=n queues the
-        // latency-bound tails (everything after the first accumulation level) of the n largest jobs of a ladder on
-        // high-priority streams; SB_MSM_SMALL_HI=1 runs the small jobs entirely at high priority.  Measured at
-        // 2^20: the tails then overlap the other jobs' accumulation as intended, but their CTAs (2 warps, 238
-        // registers, mostly idle lanes in the tree and double-and-add phases) hold a quarter of an SM each for
-        // milliseconds and the accumulation kernels lose more than the tails gain (70.5 against 66.6 ms).
-        c->n_tails = getenv("SB_MSM_TAILS") ? std::min(std::max(atoi(getenv("SB_MSM_TAILS")), 0), (int)sb_ctx::NBIG) : 0;
-        const bool small_hi = getenv("SB_MSM_SMALL_HI") && atoi(getenv("SB_MSM_SMALL_HI")) != 0;
-        const int prio_hi = prio_greatest;
         for (int i = 0; i < sb_ctx::NAUX; i++) {
-            SB_CUDA(cudaStreamCreateWithPriority(&c->aux[i], cudaStreamNonBlocking, (small_hi && i >= sb_ctx::NBIG) ? prio_hi : prio_least));
+            SB_CUDA(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
             SB_CUDA(cudaEventCreateWithFlags(&c->ev_aux[i], cudaEventDisableTiming));
-        }
-        for (int i = 0; i < sb_ctx::NBIG; i++) {
-            SB_CUDA(cudaStreamCreateWithPriority(&c->tail[i], cudaStreamNonBlocking, prio_hi));
-            SB_CUDA(cudaEventCreateWithFlags(&c->ev_tail[i], cudaEventDisableTiming));
         }
         SB_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
         SB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -932,10 +923,6 @@ void sb_ctx_destroy(sb_ctx* c) {
     for (int i = 0; i < sb_ctx::NAUX; i++) {
         if (c->aux[i]) { cudaStreamSynchronize(c->aux[i]); cudaStreamDestroy(c->aux[i]); }
         if (c->ev_aux[i]) cudaEventDestroy(c->ev_aux[i]);
-    }
-    for (int i = 0; i < sb_ctx::NBIG; i++) {
-        if (c->tail[i]) { cudaStreamSynchronize(c->tail[i]); cudaStreamDestroy(c->tail[i]); }
-        if (c->ev_tail[i]) cudaEventDestroy(c->ev_tail[i]);
     }
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
@@ -1027,17 +1014,19 @@ sb_status sb_msm(sb_ctx* ctx, int group, const void* bases, const void* scalars,
     DevBuf<Fr> sd(n, st);
     SB_CUDA(cudaMemcpyAsync(sd.get(), scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
     if (group == 1) {
-        DevBuf<G1Aff> bd(n, st); MsmBases<Fq> mb; DevBuf<G1Xyzz> o(1, st);
+        DevBuf<G1Aff> bd(n, st); MsmGroup<Fq> mb; DevBuf<G1Xyzz> o(1, st);
         SB_CUDA(cudaMemcpyAsync(bd.get(), bases, n * sizeof(G1Aff), cudaMemcpyHostToDevice, st));
-        msm_prepare<Fq>(bd.get(), n, mb, st);
-        msm_run<Fq>(mb, sd.get(), n, o.get(), st);
+        msm_group_prepare<Fq>({bd.get()}, {n}, mb, st);
+        MsmScalarPtrs sp{}; sp.p[0] = sd.get();
+        msm_group_run<Fq>(mb, sp, o.get(), st);
         G1Aff r = fetch_affine<Fq>(ctx, o.get());
         memcpy(out_affine, &r, sizeof r);
     } else {
-        DevBuf<G2Aff> bd(n, st); MsmBases<Fq2> mb; DevBuf<G2Xyzz> o(1, st);
+        DevBuf<G2Aff> bd(n, st); MsmGroup<Fq2> mb; DevBuf<G2Xyzz> o(1, st);
         SB_CUDA(cudaMemcpyAsync(bd.get(), bases, n * sizeof(G2Aff), cudaMemcpyHostToDevice, st));
-        msm_prepare<Fq2>(bd.get(), n, mb, st);
-        msm_run<Fq2>(mb, sd.get(), n, o.get(), st);
+        msm_group_prepare<Fq2>({bd.get()}, {n}, mb, st);
+        MsmScalarPtrs sp{}; sp.p[0] = sd.get();
+        msm_group_run<Fq2>(mb, sp, o.get(), st);
         G2Aff r = fetch_affine<Fq2>(ctx, o.get());
         memcpy(out_affine, &r, sizeof r);
     }

@@ -1,0 +1,76 @@
+"""CPU tests of the PRODUCT's own CUDA sources under the CUDA-on-CPU test shim (tests/emul/).
+
+tests/emul/build.sh compiles r1cs-spartan_b200/csrc/*.cu, unchanged, with g++ against tests/emul/cuda_runtime.h: every
+kernel launch runs its CUDA threads as host threads.  That executes the index logic of every kernel (MSM digits /
+plan / scatter / chunked accumulation / bucket reduction over multi-slot groups, sparse-product plans, sumcheck folds
+and reductions) and the complete host driver -- single-GPU and hypercube-sharded -- against the CPU oracle, here, without
+a GPU.  What it does NOT cover is the PTX field arithmetic (the portable C++ path of field.cuh runs instead); the -m gpu
+tests do that on the device.  The emulation library is test infrastructure: it lives under tests/, refuses to create a
+context unless SB_EMUL_TESTS=1, and the product never builds or loads it.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL = os.path.join(ROOT, "tests", "emul")
+LIB = os.path.join(EMUL, "libsb_emul_TESTONLY.so")
+
+
+@pytest.fixture(scope="module")
+def emul_env():
+    if not (os.path.exists("/usr/bin/g++") or shutil.which("g++")):
+        pytest.skip("no host compiler")
+    subprocess.check_call([os.path.join(EMUL, "build.sh")])
+    return dict(os.environ, SB_EMUL_TESTS="1", SB_LIB_PATH=LIB)
+
+
+def _pytest_gpu_subset(env, k, extra=None, timeout=1500):
+    e = dict(env, **(extra or {}))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q", "-k", k],
+                       env=e, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, (extra, r.stdout[-3000:], r.stderr[-2000:])
+    assert " passed" in r.stdout and "skipped" not in r.stdout.splitlines()[-1], r.stdout[-500:]
+
+
+def test_emulated_library_refuses_to_run_outside_the_tests(emul_env):
+    env = {k: v for k, v in emul_env.items() if k != "SB_EMUL_TESTS"}
+    r = subprocess.run([sys.executable, "-c", "import r1cs_spartan_b200 as sb; sb.Context(0)"], env=env, cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr
+
+
+def test_product_kernels_match_oracle_under_emulation(emul_env):
+    # the stage tests and small complete proofs of tests/test_gpu_parity.py, through the C ABI of the emulated build
+    _pytest_gpu_subset(emul_env, "eq_table or sum_over_y or eval_on_x or synthetic_circuit or keygen or pp_load or msm_matches or structured "
+                                 "or adversarial or commit_and_open or padded or interactive or invalid_arguments or resident "
+                                 "or prove_bytes_and_trace_match_oracle[3 or prove_bytes_and_trace_match_oracle[6 or prove_bytes_and_trace_match_oracle[8")
+
+
+@pytest.mark.parametrize("knobs", [
+    {"SB_MSM_S0": "2", "SB_MSM_S1": "2", "SB_MSM_LEVELS": "2"},                       # two launched levels: the device must raise S1
+    {"SB_MSM_S0": "3", "SB_MSM_S1": "2", "SB_MSM_LEVELS": "8", "SB_MSM_SORTED": "0", "SB_MSM_RED_L": "8"},
+    {"SB_MSM_SPLIT": "3", "SB_MSM_SPLIT_MIN_NV": "2", "SB_MSM_S0": "5"},                # opening ladders split into three pipelines
+])
+def test_msm_pipeline_knobs_under_emulation(emul_env, knobs):
+    _pytest_gpu_subset(emul_env, "msm_matches or structured or adversarial or commit_and_open or padded or prove_bytes_and_trace_match_oracle[6", knobs)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_prover_under_emulation(emul_env, world, oracle):
+    # the hypercube-sharded prover, one process per (emulated) GPU, shared-memory exchange: proof bytes and every traced
+    # intermediate equal the oracle's on every rank; sharded keygen and sliced sb_pp_load both
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_gpu_multi as tm
+    old = {k: os.environ.get(k) for k in ("SB_EMUL_TESTS", "SB_LIB_PATH", "SB_EMUL_DEVICES")}
+    os.environ.update(SB_EMUL_TESTS="1", SB_LIB_PATH=LIB, SB_EMUL_DEVICES="8")
+    try:
+        tm._run(world, [(3, 4, 0, False), (5, 8, 30, True), (7, 32, 0, False)] if world == 2 else [(4, 4, 0, True), (6, 8, 0, False)], backend="gloo")
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v

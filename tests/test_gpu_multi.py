@@ -15,14 +15,18 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, cases, q):
+def _worker(rank, world, port, cases, q, backend="nccl"):
+    # backend "gloo" = the CUDA-on-CPU emulation build (tests/test_emul_cpu.py): same product code, host threads for kernels
     try:
         sys.path.insert(0, ROOT)
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
         import torch
         import torch.distributed as dist
-        torch.cuda.set_device(rank)
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        if backend == "nccl":
+            torch.cuda.set_device(rank)
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        else:
+            dist.init_process_group("gloo", rank=rank, world_size=world)
         import r1cs_spartan_b200 as sb
         from r1cs_spartan_b200 import dist as sbdist
         from oracle import binding as ob
@@ -64,15 +68,15 @@ def _worker(rank, world, port, cases, q):
         q.put((rank, "FAIL: " + traceback.format_exc()))
 
 
-def _run(world, cases):
+def _run(world, cases, backend="nccl"):
     import torch
-    if torch.cuda.device_count() < world:
+    if backend == "nccl" and torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, cases, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cases, q, backend)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=900) for _ in procs]
