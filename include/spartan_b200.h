@@ -57,6 +57,9 @@ typedef struct {
     int rank;
     int world;
     int (*allgather)(void* user, const void* send, void* recv, size_t bytes);
+    /* optional (may be NULL): called by every rank at the start of every library call on the context, so that an
+     * exchange layer with sequence numbers can re-align ranks after a call that failed on some of them */
+    int (*barrier)(void* user);
     void* user;
 } sb_comm;
 
@@ -64,6 +67,8 @@ typedef struct {
  * microsecond; the payloads are at most a few hundred bytes and already on the host).  `name` is a shm name
  * ("/something") shared by all ranks; exactly one rank passes create != 0 and must do so before the others attach. */
 sb_status sb_comm_shm_open(const char* name, int rank, int world, int create, sb_comm* out);
+/* The same mailbox in process memory for `world` contexts driven by threads of one process; fills out[0..world). */
+sb_status sb_comm_local_open(int world, sb_comm* out);
 void sb_comm_shm_close(sb_comm* comm);
 
 /* ---- context ---------------------------------------------------------------------------------- */

@@ -31,7 +31,7 @@ EXPORTS = [
     "sb_prover_second_sumcheck_round", "sb_prover_sixth_round", "sb_prover_export_abc", "sb_phase_name", "sb_prove",
     "sb_proof_size", "sb_field_binop", "sb_mul_bench", "sb_kernel_bench",
     "sb_witness_upload", "sb_witness_destroy", "sb_prove_resident", "sb_copy_counters", "sb_prof_enable", "sb_prof_report",
-    "sb_set_serial_msm", "sb_prof_timeline", "sb_comm_shm_open", "sb_comm_shm_close",
+    "sb_set_serial_msm", "sb_prof_timeline", "sb_comm_shm_open", "sb_comm_shm_close", "sb_comm_local_open",
 ]
 
 
@@ -48,10 +48,11 @@ class CsrStruct(C.Structure):
 
 
 COMM_ALLGATHER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+COMM_BARRIER = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
 
 class CommStruct(C.Structure):
-    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("allgather", COMM_ALLGATHER), ("user", C.c_void_p)]
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("allgather", COMM_ALLGATHER), ("barrier", COMM_BARRIER), ("user", C.c_void_p)]
 
 
 class TraceStruct(C.Structure):

@@ -111,6 +111,27 @@ struct PinnedBuf {
     T* get() const { return p; }
 };
 
+// Pinned host memory mapped into the device address space: kernels write small results (and a sequence flag) straight
+// into it and the host polls, instead of a cudaMemcpyAsync + cudaStreamSynchronize pair per result.
+template <class T>
+struct MappedBuf {
+    T* h = nullptr;    // host address
+    T* d = nullptr;    // the same memory as the device sees it
+    size_t n = 0;
+    MappedBuf() {}
+    MappedBuf(const MappedBuf&) = delete;
+    MappedBuf& operator=(const MappedBuf&) = delete;
+    void alloc(size_t count) {
+        release(); n = count;
+        if (!count) return;
+        SB_CUDA(cudaHostAlloc((void**)&h, count * sizeof(T), cudaHostAllocMapped | cudaHostAllocPortable));
+        SB_CUDA(cudaHostGetDevicePointer((void**)&d, (void*)h, 0));
+        memset((void*)h, 0, count * sizeof(T));
+    }
+    void release() { if (h) { cudaFreeHost((void*)h); h = nullptr; d = nullptr; } n = 0; }
+    ~MappedBuf() { release(); }
+};
+
 static inline int grid_for(size_t work_items, int block, int ctas_per_sm) {
     size_t need = (work_items + block - 1) / block;
     size_t cap = (size_t)SB_SMS * ctas_per_sm;

@@ -90,8 +90,12 @@ SB_D Fr warp_reduce_fr(Fr v) {
 }
 
 // Block tree reduction of K accumulators, then grid-level finish by the last CTA to arrive.
+// `out` may be device memory or mapped pinned host memory; when `flag` is given (mapped pinned host memory) the last
+// CTA publishes `seq` there after the results, system-wide fenced, and the host polls it instead of synchronising the
+// stream (a sumcheck round is a few microseconds of kernel: the cudaMemcpyAsync + cudaStreamSynchronize pair that used
+// to fetch its 96 bytes cost more than the round itself).
 template <int K>
-SB_D void reduce_finish(Fr (&acc)[K], Fr* out, Fr* block_partials, unsigned int* ticket) {
+SB_D void reduce_finish(Fr (&acc)[K], Fr* out, Fr* block_partials, unsigned int* ticket, volatile uint32_t* flag, uint32_t seq) {
     __shared__ Fr sh[K][32];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
@@ -138,7 +142,10 @@ SB_D void reduce_finish(Fr (&acc)[K], Fr* out, Fr* block_partials, unsigned int*
             v = warp_reduce_fr(v);
             if (lane == 0) st_elem(&out[k], v);
         }
-        if (lane == 0) *ticket = 0;     // self-reset for the next launch on this stream
+        if (lane == 0) {
+            *ticket = 0;                // self-reset for the next launch on this stream
+            if (flag) { __threadfence_system(); *flag = seq; }
+        }
     }
 }
 
@@ -254,12 +261,10 @@ void launch_segsum(Fr* out, Fr* partials, const SegItem* items, uint32_t n_items
 template <int KIND, bool FOLD>
 __global__ void __launch_bounds__(256, 2)
 k_sc_round(const Fr* __restrict__ A, const Fr* __restrict__ B, const Fr* __restrict__ C, Fr* __restrict__ Ao, Fr* __restrict__ Bo,
-           Fr* __restrict__ Co, const Fr* __restrict__ E, const Fr* __restrict__ r_ptr, size_t h /* pairs after the fold */,
-           Fr* out3, Fr* block_partials, unsigned int* ticket) {
+           Fr* __restrict__ Co, const Fr* __restrict__ E, const Fr r /* the challenge, a kernel argument: no upload */, size_t h /* pairs after the fold */,
+           Fr* out3, Fr* block_partials, unsigned int* ticket, volatile uint32_t* flag, uint32_t seq) {
     Fr acc[3];
     acc[0] = Fr::zero(); acc[1] = Fr::zero(); acc[2] = Fr::zero();
-    Fr r;
-    if (FOLD) r = ldg_elem(r_ptr);
     for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < h; b += (size_t)gridDim.x * blockDim.x) {
         Fr a0, a1, b0, b1, c0, c1;
         if (FOLD) {
@@ -296,37 +301,40 @@ k_sc_round(const Fr* __restrict__ A, const Fr* __restrict__ B, const Fr* __restr
             acc[2] = Fr::add(acc[2], Fr::mul(a2, b2));
         }
     }
-    reduce_finish<3>(acc, out3, block_partials, ticket);
+    reduce_finish<3>(acc, out3, block_partials, ticket, flag, seq);
 }
 
 template <int KIND>
-static void launch_sc_round(const Fr* A, const Fr* B, const Fr* C, Fr* Ao, Fr* Bo, Fr* Co, const Fr* E, const Fr* r_dev,
-                            size_t m_in, Fr* out3, const RoundWs& ws, cudaStream_t stream) {
-    bool fold = r_dev != nullptr;
+static void launch_sc_round(const Fr* A, const Fr* B, const Fr* C, Fr* Ao, Fr* Bo, Fr* Co, const Fr* E, const Fr* r_host,
+                            size_t m_in, const RoundOut& o, const RoundWs& ws, cudaStream_t stream) {
+    const bool fold = r_host != nullptr;
+    const Fr r = fold ? *r_host : Fr::zero();
     size_t h = fold ? m_in / 4 : m_in / 2;
     int grid = grid_for(h, 256, ws.max_grid / SB_SMS > 1 ? ws.max_grid / SB_SMS : 1);   // 2 resident CTAs per SM by default
     if (grid > ws.max_grid) grid = ws.max_grid;
-    if (fold) SB_LAUNCH_NAMED(KIND == 1 ? "k_sc_round<sc1,fold>" : "k_sc_round<sc2,fold>", (k_sc_round<KIND, true>), grid, 256, 0, stream, A, B, C, Ao, Bo, Co, E, r_dev, h, out3, ws.block_partials, ws.ticket);
-    else SB_LAUNCH_NAMED(KIND == 1 ? "k_sc_round<sc1,first>" : "k_sc_round<sc2,first>", (k_sc_round<KIND, false>), grid, 256, 0, stream, A, B, C, Ao, Bo, Co, E, r_dev, h, out3, ws.block_partials, ws.ticket);
+    if (fold) SB_LAUNCH_NAMED(KIND == 1 ? "k_sc_round<sc1,fold>" : "k_sc_round<sc2,fold>", (k_sc_round<KIND, true>), grid, 256, 0, stream, A, B, C, Ao, Bo, Co, E, r, h, o.out, ws.block_partials, ws.ticket, o.flag, o.seq);
+    else SB_LAUNCH_NAMED(KIND == 1 ? "k_sc_round<sc1,first>" : "k_sc_round<sc2,first>", (k_sc_round<KIND, false>), grid, 256, 0, stream, A, B, C, Ao, Bo, Co, E, r, h, o.out, ws.block_partials, ws.ticket, o.flag, o.seq);
 }
-void launch_sc1_round(const Fr* A, const Fr* B, const Fr* C, Fr* Ao, Fr* Bo, Fr* Co, const Fr* E, const Fr* r_dev,
-                      size_t m_in, Fr* out3, const RoundWs& ws, cudaStream_t stream) {
-    launch_sc_round<1>(A, B, C, Ao, Bo, Co, E, r_dev, m_in, out3, ws, stream);
+void launch_sc1_round(const Fr* A, const Fr* B, const Fr* C, Fr* Ao, Fr* Bo, Fr* Co, const Fr* E, const Fr* r_host,
+                      size_t m_in, const RoundOut& o, const RoundWs& ws, cudaStream_t stream) {
+    launch_sc_round<1>(A, B, C, Ao, Bo, Co, E, r_host, m_in, o, ws, stream);
 }
-void launch_sc2_round(const Fr* M, const Fr* Z, Fr* Mo, Fr* Zo, const Fr* r_dev, size_t m_in, Fr* out3,
+void launch_sc2_round(const Fr* M, const Fr* Z, Fr* Mo, Fr* Zo, const Fr* r_host, size_t m_in, const RoundOut& o,
                       const RoundWs& ws, cudaStream_t stream) {
-    launch_sc_round<2>(M, Z, nullptr, Mo, Zo, nullptr, nullptr, r_dev, m_in, out3, ws, stream);
+    launch_sc_round<2>(M, Z, nullptr, Mo, Zo, nullptr, nullptr, r_host, m_in, o, ws, stream);
 }
 
-__global__ void k_final_fold3(const Fr* A, const Fr* B, const Fr* C, int ntab, const Fr* r_ptr, Fr* out) {
-    int k = threadIdx.x;
-    if (k >= ntab) return;
-    const Fr* T = k == 0 ? A : k == 1 ? B : C;
-    Fr r = *r_ptr, x0 = T[0], x1 = T[1];
-    out[k] = Fr::add(x0, Fr::mul(r, Fr::sub(x1, x0)));
+__global__ void k_final_fold3(const Fr* A, const Fr* B, const Fr* C, int ntab, const Fr r, Fr* out, volatile uint32_t* flag, uint32_t seq) {
+    if (threadIdx.x != 0) return;           // three multiplications: one thread, so that the flag follows its own stores
+    for (int k = 0; k < ntab; k++) {
+        const Fr* T = k == 0 ? A : k == 1 ? B : C;
+        Fr x0 = T[0], x1 = T[1];
+        st_elem(&out[k], Fr::add(x0, Fr::mul(r, Fr::sub(x1, x0))));
+    }
+    if (flag) { __threadfence_system(); *flag = seq; }
 }
-void launch_final_fold3(const Fr* A, const Fr* B, const Fr* C, int ntab, const Fr* r_dev, Fr* out, cudaStream_t stream) {
-    SB_LAUNCH(k_final_fold3, 1, 32, 0, stream, A, B, C, ntab, r_dev, out);
+void launch_final_fold3(const Fr* A, const Fr* B, const Fr* C, int ntab, const Fr* r_host, const RoundOut& o, cudaStream_t stream) {
+    SB_LAUNCH(k_final_fold3, 1, 32, 0, stream, A, B, C, ntab, *r_host, o.out, o.flag, o.seq);
 }
 
 // ------------------------------------------------------------------ opening fold

@@ -37,16 +37,24 @@ struct RoundWs {
     unsigned int* ticket;    // zero-initialised, self-resetting
     int max_grid;
 };
+// Where a round leaves its result: `out` (3 Fr; device memory or mapped pinned host memory) and, optionally, a flag
+// word in mapped pinned host memory that receives `seq` once the result is visible to the host (see reduce_finish).
+struct RoundOut {
+    Fr* out;
+    volatile uint32_t* flag;
+    uint32_t seq;
+};
 // Sumcheck 1 round (replaces upstream prove_round as driven by ahp/prover.rs:199-207):
-//   if r != nullptr: fold A,B,C (m_in entries each) with *r into Ao,Bo,Co (m_in/2 entries), then
-//   S(t) = sum_b E[b] (A(t,b) B(t,b) - C(t,b)), t = 0,1,2 over the (possibly folded) tables; out3 <- S.
-void launch_sc1_round(const Fr* A, const Fr* B, const Fr* C, Fr* Ao, Fr* Bo, Fr* Co, const Fr* E, const Fr* r_dev,
-                      size_t m_in, Fr* out3, const RoundWs& ws, cudaStream_t stream);
+//   if r_host != nullptr: fold A,B,C (m_in entries each) with *r_host (HOST pointer: the challenge travels as a kernel
+//   argument) into Ao,Bo,Co (m_in/2 entries), then
+//   S(t) = sum_b E[b] (A(t,b) B(t,b) - C(t,b)), t = 0,1,2 over the (possibly folded) tables; o.out <- S.
+void launch_sc1_round(const Fr* A, const Fr* B, const Fr* C, Fr* Ao, Fr* Bo, Fr* Co, const Fr* E, const Fr* r_host,
+                      size_t m_in, const RoundOut& o, const RoundWs& ws, cudaStream_t stream);
 // Sumcheck 2 round (ahp/prover.rs:258-266): S(t) = sum_b M(t,b) Z(t,b)
-void launch_sc2_round(const Fr* M, const Fr* Z, Fr* Mo, Fr* Zo, const Fr* r_dev, size_t m_in, Fr* out3,
+void launch_sc2_round(const Fr* M, const Fr* Z, Fr* Mo, Fr* Zo, const Fr* r_host, size_t m_in, const RoundOut& o,
                       const RoundWs& ws, cudaStream_t stream);
 // out[k] = T_k[0] + r (T_k[1] - T_k[0]) for up to 3 two-entry tables (final fold; prover.rs:217-219)
-void launch_final_fold3(const Fr* A, const Fr* B, const Fr* C, int ntab, const Fr* r_dev, Fr* out, cudaStream_t stream);
+void launch_final_fold3(const Fr* A, const Fr* B, const Fr* C, int ntab, const Fr* r_host, const RoundOut& o, cudaStream_t stream);
 // open.rs:42-45: q[b] = in[2b+1] - in[2b]; r_out[b] = in[2b] + p (in[2b+1] - in[2b])
 void launch_open_fold(const Fr* in, Fr* r_out, Fr* q_out, const Fr* p_dev, size_t half, cudaStream_t stream);
 // elementwise self-test helpers: out = a (op) b with the PTX path; op 0 add, 1 sub, 2 mul, 3 mul_portable

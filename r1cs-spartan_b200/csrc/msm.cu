@@ -96,99 +96,179 @@ __host__ __device__ inline uint32_t msm_pick_s1(uint32_t maxrun, uint32_t s0, ui
     return s1;
 }
 
-__device__ inline uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t* sh, uint32_t& total) {
-    const uint32_t tid = threadIdx.x;
-    sh[tid] = v;
-    __syncthreads();
-    for (uint32_t off = 1; off < 1024; off <<= 1) {
-        uint32_t t = tid >= off ? sh[tid - off] : 0;
-        __syncthreads();
-        sh[tid] += t;
-        __syncthreads();
-    }
-    uint32_t incl = sh[tid];
-    total = sh[1023];
-    __syncthreads();
-    return incl - v;
-}
-
 struct PlanPtrs {
     uint32_t* offsets; uint32_t* cursors; uint32_t* info;
     uint32_t* perm; uint32_t* invperm;          // bucket order of the accumulation (nullptr: natural order)
     uint32_t* plan[MSM_MAX_LEVELS];
 };
+// per-CTA aggregates the plan kernels hand to one another
+struct PlanWs {
+    uint32_t* cta_sum;     // [nC]            entries of the CTA's buckets
+    uint32_t* cta_max;     // [nC]            longest run among them
+    uint32_t* cta_hist;    // [nC][s0 + 1]    buckets per first-level chunk length
+    uint32_t* cta_lsum;    // [levels][nC]    chunks per level of the CTA's positions
+};
+constexpr int PLAN_T = 256, PLAN_V = 4, PLAN_TILE = PLAN_T * PLAN_V;   // a CTA plans 1024 consecutive buckets / positions
 
-// One CTA: exclusive scan of the B bucket counters of the whole group (-> offsets, cursors), the run statistics, and
-// every plan the accumulation needs, all chosen on the device:
-//   S1, levels    chunking of the runs (see msm_levels / msm_pick_s1)
-//   perm/invperm  accumulation order of the buckets: by decreasing chunk length of the first level
-//   plan[l][k]    = exclusive scan over that order of ceil(count / (S0 S1^l))   (chunk plan of accumulation level l)
-// info: [0] entries, [1] longest run, [2] S0, [3] levels, [4] S1, [MSM_INFO_ITEMS + l] chunks of level l.
-__global__ void __launch_bounds__(1024) k_scan_plan(const uint32_t* __restrict__ counts, uint32_t B, PlanPtrs pp, uint32_t s0, uint32_t s1_min,
-                                                    uint32_t nlaunch) {
-    __shared__ uint32_t sh[1024];
-    __shared__ uint32_t sh_max, sh_levels, sh_s1;
-    const uint32_t tid = threadIdx.x;
-    if (tid == 0) sh_max = 0;
-    const uint32_t per = (B + 1023) / 1024;
-    const uint32_t beg = min(tid * per, B), end = min(beg + per, B);
-    uint32_t sum = 0, mx = 0;
-    for (uint32_t i = beg; i < end; i++) { uint32_t cnt = counts[i]; sum += cnt; mx = max(mx, cnt); }
+// first-level chunk length of a run of c entries: ceil(c / ceil(c / s0)) <= s0 (0 for an empty bucket)
+__host__ __device__ inline uint32_t plan_key(uint32_t c, uint32_t s0) {
+    const uint32_t nch = (c + s0 - 1) / s0;
+    return nch ? (c + nch - 1) / nch : 0;
+}
+// sum (and max) of one value per thread over a CTA of PLAN_T threads; every thread gets the results
+__device__ inline void plan_block_sum3(uint32_t& a, uint32_t& b, uint32_t& mx, uint32_t* sh /* 3 * PLAN_T */) {
+    const uint32_t t = threadIdx.x;
+    sh[t] = a; sh[PLAN_T + t] = b; sh[2 * PLAN_T + t] = mx;
     __syncthreads();
-    atomicMax(&sh_max, mx);
-    uint32_t total;
-    uint32_t run = block_exclusive_scan_1024(sum, sh, total);
-    for (uint32_t i = beg; i < end; i++) { pp.offsets[i] = run; pp.cursors[i] = run; run += counts[i]; }
-    if (tid == 0) {
-        pp.offsets[B] = total;
-        const uint32_t s1 = msm_pick_s1(sh_max, s0, s1_min, nlaunch);
-        sh_s1 = s1;
-        sh_levels = msm_levels(sh_max, s0, s1);
-        pp.info[0] = total; pp.info[1] = sh_max; pp.info[2] = s0; pp.info[3] = sh_levels; pp.info[4] = s1;
+    for (uint32_t off = PLAN_T / 2; off > 0; off >>= 1) {
+        if (t < off) {
+            sh[t] += sh[t + off]; sh[PLAN_T + t] += sh[PLAN_T + t + off];
+            sh[2 * PLAN_T + t] = max(sh[2 * PLAN_T + t], sh[2 * PLAN_T + t + off]);
+        }
+        __syncthreads();
     }
+    a = sh[0]; b = sh[PLAN_T]; mx = sh[2 * PLAN_T];
     __syncthreads();
-    const uint32_t levels = sh_levels, s1 = sh_s1;
-    // Accumulation order of the buckets: by decreasing chunk length of the first level (counting sort; key =
-    // ceil(c_b / ceil(c_b / S0)) <= S0).  Thread p of the accumulation kernel takes chunk p in this order, so
-    // the 32 lanes of a warp run loops of (almost) equal length instead of whatever neighbouring buckets hold,
-    // and the shortest chunks -- not the longest -- are the ones left when the grid drains.
-    __shared__ uint32_t sh_hist[1026];
-    const bool sorted = pp.perm != nullptr && s0 <= 1024;
+}
+// exclusive scan of one value per thread over the CTA
+__device__ inline uint32_t plan_block_exscan(uint32_t v, uint32_t* sh /* PLAN_T */) {
+    const uint32_t t = threadIdx.x;
+    sh[t] = v;
+    __syncthreads();
+    for (uint32_t off = 1; off < (uint32_t)PLAN_T; off <<= 1) {
+        uint32_t x = t >= off ? sh[t - off] : 0;
+        __syncthreads();
+        sh[t] += x;
+        __syncthreads();
+    }
+    const uint32_t r = sh[t] - v;
+    __syncthreads();
+    return r;
+}
+
+// The plan of a pipeline, computed on the device by four small multi-CTA kernels (the single-CTA version of round 1
+// walked 2^16 counters a dozen times with dependent loads: 0.45 ms per MSM; these take a few microseconds each):
+//   A  per CTA: entries, longest run, histogram of first-level chunk lengths
+//   C  offsets / cursors (exclusive scan of the counters), the run statistics -> S1, levels (info), and the accumulation
+//      order of the buckets: by decreasing chunk length of the first level (counting sort on the histograms) --
+//      thread p of the accumulation kernel takes chunk p in this order, so the 32 lanes of a warp run loops of
+//      (almost) equal length and the shortest chunks are the ones left when the grid drains
+//   D  per CTA of positions in that order: chunks per level
+//   F  plan[l][k] = exclusive scan over that order of ceil(count / (S0 S1^l))   (chunk plan of accumulation level l)
+// info: [0] entries, [1] longest run, [2] S0, [3] levels, [4] S1, [MSM_INFO_ITEMS + l] chunks of level l.
+__global__ void __launch_bounds__(PLAN_T) k_plan_a(const uint32_t* __restrict__ counts, uint32_t B, uint32_t s0, PlanWs ws) {
+    __shared__ uint32_t hist[1025];
+    __shared__ uint32_t sh[3 * PLAN_T];
+    const uint32_t t = threadIdx.x;
+    for (uint32_t k = t; k <= s0; k += PLAN_T) hist[k] = 0;
+    __syncthreads();
+    uint32_t sum = 0, zero = 0, mx = 0;
+    const uint32_t b0 = blockIdx.x * PLAN_TILE + t * PLAN_V;
+#pragma unroll
+    for (int v = 0; v < PLAN_V; v++) {
+        const uint32_t b = b0 + v;
+        if (b < B) {
+            const uint32_t c = __ldg(&counts[b]);
+            sum += c; mx = max(mx, c);
+            atomicAdd(&hist[plan_key(c, s0)], 1u);
+        }
+    }
+    plan_block_sum3(sum, zero, mx, sh);
+    if (t == 0) { ws.cta_sum[blockIdx.x] = sum; ws.cta_max[blockIdx.x] = mx; }
+    for (uint32_t k = t; k <= s0; k += PLAN_T) ws.cta_hist[(size_t)blockIdx.x * (s0 + 1) + k] = hist[k];
+}
+
+__global__ void __launch_bounds__(PLAN_T) k_plan_c(const uint32_t* __restrict__ counts, uint32_t B, uint32_t s0, uint32_t s1_min, uint32_t nlaunch,
+                                                   PlanWs ws, PlanPtrs pp) {
+    __shared__ uint32_t pos[1025];       // per chunk length: next position in the accumulation order for this CTA's buckets
+    __shared__ uint32_t tot[1025];
+    __shared__ uint32_t sh[3 * PLAN_T];
+    const uint32_t t = threadIdx.x, nC = gridDim.x, blk = blockIdx.x;
+    // entries before this CTA, entries in total, longest run (every CTA derives them from the per-CTA aggregates)
+    uint32_t before = 0, total = 0, mx = 0;
+    for (uint32_t c = t; c < nC; c += PLAN_T) {
+        const uint32_t s = ws.cta_sum[c];
+        total += s; if (c < blk) before += s;
+        mx = max(mx, ws.cta_max[c]);
+    }
+    plan_block_sum3(before, total, mx, sh);
+    if (blk == 0 && t == 0) {
+        const uint32_t s1 = msm_pick_s1(mx, s0, s1_min, nlaunch);
+        pp.offsets[B] = total;
+        pp.info[0] = total; pp.info[1] = mx; pp.info[2] = s0; pp.info[3] = msm_levels(mx, s0, s1); pp.info[4] = s1;
+    }
+    const bool sorted = pp.perm != nullptr;
     if (sorted) {
-        for (uint32_t k = tid; k <= s0; k += 1024) sh_hist[k] = 0;
-        __syncthreads();
-        for (uint32_t i = beg; i < end; i++) {
-            const uint32_t c = counts[i], nch = (c + s0 - 1) / s0;
-            atomicAdd(&sh_hist[nch ? (c + nch - 1) / nch : 0], 1u);
+        // buckets of chunk length k: tot[k] in the whole group, pos[k] of them in the CTAs before this one
+        for (uint32_t k = t; k <= s0; k += PLAN_T) {
+            uint32_t all = 0, below = 0;
+            for (uint32_t c = 0; c < nC; c++) {
+                const uint32_t h = ws.cta_hist[(size_t)c * (s0 + 1) + k];
+                all += h; if (c < blk) below += h;
+            }
+            tot[k] = all; pos[k] = below;
         }
         __syncthreads();
-        if (tid == 0) {
-            uint32_t run2 = 0;
-            for (int k = (int)s0; k >= 0; k--) { const uint32_t h = sh_hist[k]; sh_hist[k] = run2; run2 += h; }
+        if (t == 0) {        // longest chunks first
+            uint32_t run = 0;
+            for (int k = (int)s0; k >= 0; k--) { pos[k] += run; run += tot[k]; }
         }
         __syncthreads();
-        for (uint32_t i = beg; i < end; i++) {
-            const uint32_t c = counts[i], nch = (c + s0 - 1) / s0;
-            const uint32_t pos = atomicAdd(&sh_hist[nch ? (c + nch - 1) / nch : 0], 1u);
-            pp.perm[pos] = i; pp.invperm[i] = pos;
+    }
+    uint32_t c[PLAN_V], sum = 0;
+    const uint32_t b0 = blk * PLAN_TILE + t * PLAN_V;
+#pragma unroll
+    for (int v = 0; v < PLAN_V; v++) { c[v] = (b0 + v < B) ? __ldg(&counts[b0 + v]) : 0; sum += c[v]; }
+    uint32_t run = before + plan_block_exscan(sum, sh);
+#pragma unroll
+    for (int v = 0; v < PLAN_V; v++) {
+        const uint32_t b = b0 + v;
+        if (b < B) {
+            pp.offsets[b] = run; pp.cursors[b] = run; run += c[v];
+            if (sorted) {
+                const uint32_t p = atomicAdd(&pos[plan_key(c[v], s0)], 1u);
+                pp.perm[p] = b; pp.invperm[b] = p;
+            }
         }
-        __threadfence();
-        __syncthreads();
+    }
+}
+
+// D (WRITE = false): chunks per level of this CTA's positions -> ws.cta_lsum;  F (WRITE = true): the chunk plans
+template <bool WRITE>
+__global__ void __launch_bounds__(PLAN_T) k_plan_levels(const uint32_t* __restrict__ counts, uint32_t B, PlanWs ws, PlanPtrs pp) {
+    __shared__ uint32_t sh[3 * PLAN_T];
+    const uint32_t t = threadIdx.x, nC = gridDim.x, blk = blockIdx.x;
+    const uint32_t s0 = pp.info[2], levels = pp.info[3], s1 = pp.info[4];
+    uint32_t c[PLAN_V];
+    const uint32_t k0 = blk * PLAN_TILE + t * PLAN_V;
+#pragma unroll
+    for (int v = 0; v < PLAN_V; v++) {
+        const uint32_t k = k0 + v;
+        c[v] = k < B ? __ldg(&counts[pp.perm ? pp.perm[k] : k]) : 0;
     }
     uint64_t div = s0;
     for (uint32_t l = 0; l < levels; l++, div *= s1) {
-        uint32_t s = 0;
-        for (uint32_t k = beg; k < end; k++) {
-            const uint32_t i = sorted ? pp.perm[k] : k;
-            s += (uint32_t)((counts[i] + div - 1) / div);
+        uint32_t n[PLAN_V], sum = 0;
+#pragma unroll
+        for (int v = 0; v < PLAN_V; v++) { n[v] = (uint32_t)((c[v] + div - 1) / div); sum += n[v]; }
+        if (!WRITE) {
+            uint32_t z0 = 0, z1 = 0;
+            plan_block_sum3(sum, z0, z1, sh);
+            if (t == 0) ws.cta_lsum[(size_t)l * nC + blk] = sum;
+        } else {
+            uint32_t before = 0, total = 0, z = 0;
+            for (uint32_t cc = t; cc < nC; cc += PLAN_T) {
+                const uint32_t s = ws.cta_lsum[(size_t)l * nC + cc];
+                total += s; if (cc < blk) before += s;
+            }
+            plan_block_sum3(before, total, z, sh);
+            uint32_t run = before + plan_block_exscan(sum, sh);
+#pragma unroll
+            for (int v = 0; v < PLAN_V; v++) {
+                if (k0 + v < B) { pp.plan[l][k0 + v] = run; run += n[v]; }
+            }
+            if (blk == 0 && t == 0) { pp.plan[l][B] = total; pp.info[MSM_INFO_ITEMS + l] = total; }
         }
-        uint32_t tot;
-        uint32_t x = block_exclusive_scan_1024(s, sh, tot);
-        for (uint32_t k = beg; k < end; k++) {
-            const uint32_t i = sorted ? pp.perm[k] : k;
-            pp.plan[l][k] = x; x += (uint32_t)((counts[i] + div - 1) / div);
-        }
-        if (tid == 0) { pp.plan[l][B] = tot; pp.info[MSM_INFO_ITEMS + l] = tot; }
     }
 }
 
@@ -382,7 +462,7 @@ static uint32_t msm_env_u32(const char* name, uint32_t dflt, uint32_t lo, uint32
     return (uint32_t)std::min<long>(std::max<long>(v, lo), hi);
 }
 // S0 by size: throughput-bound groups take long chunks (fewer partial sums), latency-bound ones short chains
-static uint32_t msm_s0(size_t entries) {
+static uint32_t msm_s0(size_t entries) {      // (at most 1024: the plan kernels keep one histogram bin per chunk length in shared memory)
     static const uint32_t v = msm_env_u32("SB_MSM_S0", 0, 0, 1024);
     static const uint32_t big = msm_env_u32("SB_MSM_S0_BIG", 48, 2, 1024), small = msm_env_u32("SB_MSM_S0_SMALL", 24, 2, 1024);
     return v >= 2 ? v : (entries >= ((size_t)1 << 22) ? big : small);
@@ -449,6 +529,11 @@ void msm_group_prepare(const std::vector<const AffinePt<F>*>& bases_dev, const s
     sc.codes.alloc(etot, stream); sc.sorted.alloc(etot, stream);
     sc.counts.alloc(btot, stream); sc.offsets.alloc(btot + 1, stream); sc.cursors.alloc(btot, stream); sc.info.alloc(MSM_INFO_WORDS, stream);
     sc.perm.alloc(btot, stream); sc.invperm.alloc(btot, stream);
+    {
+        const size_t nC = (btot + PLAN_TILE - 1) / PLAN_TILE;
+        sc.cta_sum.alloc(nC, stream); sc.cta_max.alloc(nC, stream); sc.cta_hist.alloc(nC * (out.s0 + 1), stream);
+        sc.cta_lsum.alloc(nC * MSM_MAX_LEVELS, stream);
+    }
     for (uint32_t l = 0; l < msm_nlaunch(); l++) sc.plan[l].alloc(btot + 1, stream);
     sc.ptsA.alloc(std::max<uint32_t>(out.items_bound[0], 1), stream);
     sc.ptsB.alloc(std::max<uint32_t>(out.items_bound[1], 1), stream);
@@ -469,7 +554,12 @@ void msm_group_run(const MsmGroup<F>& g, const MsmScalarPtrs& scalars, XyzzPt<F>
     if (g_sb_prof_on) { g_sb_prof_tag = 0; while (((size_t)2 << g_sb_prof_tag) <= g.mtot) g_sb_prof_tag++; }
     SB_CUDA(cudaMemsetAsync(sc.counts.get(), 0, (size_t)B * sizeof(uint32_t), stream));
     SB_LAUNCH(k_msm_digits, grid_for(g.mtot, 256, 8), 256, 0, stream, scalars, g.slots_dev.get(), J, g.mtot, sc.codes.get(), sc.counts.get());
-    SB_LAUNCH(k_scan_plan, 1, 1024, 0, stream, sc.counts.get(), B, pp, g.s0, msm_s1_min(), nlaunch);
+    PlanWs ws{sc.cta_sum.get(), sc.cta_max.get(), sc.cta_hist.get(), sc.cta_lsum.get()};
+    const int nC = (int)((B + PLAN_TILE - 1) / PLAN_TILE);
+    SB_LAUNCH(k_plan_a, nC, PLAN_T, 0, stream, sc.counts.get(), B, g.s0, ws);
+    SB_LAUNCH(k_plan_c, nC, PLAN_T, 0, stream, sc.counts.get(), B, g.s0, msm_s1_min(), nlaunch, ws, pp);
+    SB_LAUNCH_NAMED("k_plan_levels<sum>", (k_plan_levels<false>), nC, PLAN_T, 0, stream, sc.counts.get(), B, ws, pp);
+    SB_LAUNCH_NAMED("k_plan_levels<write>", (k_plan_levels<true>), nC, PLAN_T, 0, stream, sc.counts.get(), B, ws, pp);
     SB_LAUNCH(k_msm_scatter, grid_for(g.etot, 256, 8), 256, 0, stream, sc.codes.get(), (size_t)g.etot, sc.cursors.get(), sc.sorted.get());
     for (uint32_t l = 0; l < nlaunch; l++) {
         XyzzPt<F>* outp = (l % 2 == 0) ? sc.ptsA.get() : sc.ptsB.get();

@@ -57,6 +57,7 @@ template <class F>
 struct MsmScratch {
     DevBuf<uint32_t> codes, sorted, counts, offsets, cursors, info, perm, invperm;
     DevBuf<uint32_t> plan[MSM_MAX_LEVELS];
+    DevBuf<uint32_t> cta_sum, cta_max, cta_hist, cta_lsum;     // per-CTA aggregates of the plan kernels
     DevBuf<XyzzPt<F>> ptsA, ptsB, block_out;
 };
 

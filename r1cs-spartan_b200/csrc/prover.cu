@@ -12,6 +12,7 @@
 #include "msm.cuh"
 #include "transcript.h"
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <memory>
 #include <mutex>
@@ -33,6 +34,11 @@ struct sb_ctx {
     DevBuf<unsigned int> ticket;
     DevBuf<Fr> d_mail;                 // device scratch for scalars going in / results coming out
     PinnedBuf<Fr> h_mail;
+    // results of the sumcheck rounds: written by the round kernel's last CTA straight into mapped pinned host memory,
+    // followed by a sequence flag the host polls (no copy, no stream synchronisation per round)
+    MappedBuf<Fr> round_out;           // 4 Fr
+    MappedBuf<uint32_t> round_flag;    // one word (own allocation: own cache line)
+    uint32_t round_seq = 0;
     // auxiliary streams: an opening may be split into several MSM groups (pipelines) that run concurrently, so that the
     // latency-bound end of one (later accumulation levels, bucket reduction) hides behind the throughput-bound
     // accumulation of the next; the sharded prover's tail opening is one more group
@@ -51,6 +57,12 @@ struct sb_ctx {
     static constexpr int SLOT_VEC = 16;    // tau / point vectors (<= 64 Fr)
     static constexpr int SLOT_VEC2 = 96;
 
+    // re-align the exchange layer at the start of every library call (see sb_comm::barrier)
+    void comm_epoch() {
+        if (!sharded() || !comm.barrier) return;
+        int rc = comm.barrier(comm.user);
+        if (rc != 0) throw SbError(SB_ECOMM, "exchange barrier failed with code " + std::to_string(rc));
+    }
     // the one collective the sharded prover needs: every rank contributes `bytes` bytes
     void allgather(const void* send, void* recv, size_t bytes) {
         if (!sharded()) { memcpy(recv, send, bytes); return; }
@@ -157,6 +169,28 @@ static void d2h_fr(sb_ctx* c, int slot, Fr* dst, size_t count) {
     ctx_sync(c);
     memcpy(dst, c->h_mail.get() + slot, count * sizeof(Fr));
     g_sb_d2h_bytes += count * sizeof(Fr);
+}
+
+// ---- round results through the mapped mailbox
+static RoundOut round_begin(sb_ctx* c) {
+    RoundOut o;
+    o.out = c->round_out.d; o.flag = c->round_flag.d; o.seq = ++c->round_seq;
+    return o;
+}
+// wait for the kernel that was given `o` to publish its result; polls the flag, and looks at the stream now and then so
+// that a failed launch surfaces as an error instead of a hang
+static void round_wait(sb_ctx* c, const RoundOut& o, Fr* dst, size_t count) {
+    volatile uint32_t* f = c->round_flag.h;
+    for (uint64_t spins = 0; *f != o.seq; spins++) {
+        if ((spins & 0xffff) == 0xffff) {
+            cudaError_t e = cudaStreamQuery(c->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) SB_CUDA(e);
+            if (e == cudaSuccess && *f != o.seq) throw SbError(SB_EINTERNAL, "sumcheck round finished without publishing its result");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    memcpy(dst, (const void*)c->round_out.h, count * sizeof(Fr));
+    g_sb_d2h_bytes += count * sizeof(Fr) + 4;
 }
 
 // host: many XYZZ points -> affine with one simultaneous inversion
@@ -540,6 +574,7 @@ static void open_folds(sb_ctx* c, uint32_t nv, const Fr* table_dev, int point_sl
 static void open_queue_msms(sb_ctx* c, const sb_pp* pp, const Fr* q, G2Xyzz* res_dev, int first_aux, bool main_too) {
     cudaStream_t st = c->stream;
     const size_t ng = pp->g2.size();
+    SB_CUDA(cudaEventRecord(c->ev_main, st));      // the folds are queued: every group may start from here
     for (size_t k = 0; k < ng; k++) {
         MsmScalarPtrs sp{};
         const uint32_t i0 = pp->g2_first[k];
@@ -549,7 +584,6 @@ static void open_queue_msms(sb_ctx* c, const sb_pp* pp, const Fr* q, G2Xyzz* res
         if (!c->serial_msm && !(k == 0 && main_too)) {
             a = (first_aux + (int)k - (main_too ? 1 : 0)) % sb_ctx::NAUX;
             s = c->aux[a];
-            SB_CUDA(cudaEventRecord(c->ev_main, st));
             SB_CUDA(cudaStreamWaitEvent(s, c->ev_main, 0));
         }
         msm_group_run<Fq2>(*pp->g2[k], sp, res_dev + i0, s);
@@ -696,16 +730,15 @@ static void prover_third_round(sb_prover* p, const Fr* tor) {
 static void sc_round_device(sb_prover* p, int kind, const Fr* v_msg, Fr* S) {
     sb_ctx* c = p->ctx; cudaStream_t st = c->stream;
     const uint32_t j = p->round;
-    const Fr* r_dev = nullptr;
-    if (v_msg) { h2d_fr(c, sb_ctx::SLOT_R, v_msg, 1); r_dev = c->d_mail.get() + sb_ctx::SLOT_R; }
-    Fr* out3 = c->d_mail.get() + sb_ctx::SLOT_OUT;
     const int ntab = kind == 1 ? 3 : 2;
+    if (v_msg) g_sb_h2d_bytes += sizeof(Fr);       // the challenge travels to the device as a kernel argument
     if (c->sharded() && !p->in_tail && j == p->loc) {
         // last local fold (2 entries -> 1 per table), then gather the slices
-        launch_final_fold3(p->curA, p->curB, p->curC, ntab, r_dev, out3, st);
+        RoundOut o = round_begin(c);
+        launch_final_fold3(p->curA, p->curB, p->curC, ntab, v_msg, o, st);
         Fr mine[3], zero = Fr::zero();
         mine[2] = zero;
-        d2h_fr(c, sb_ctx::SLOT_OUT, mine, ntab);
+        round_wait(c, o, mine, ntab);
         const int G = c->world;
         std::vector<Fr> all(3 * G), tabs(3 * G, zero);
         c->allgather(mine, all.data(), 3 * sizeof(Fr));
@@ -716,26 +749,27 @@ static void sc_round_device(sb_prover* p, int kind, const Fr* v_msg, Fr* S) {
         p->curA = p->tail_tabs.get(); p->curB = p->tail_tabs.get() + G; p->curC = kind == 1 ? p->tail_tabs.get() + 2 * G : nullptr;
         p->cur_m = (size_t)G;
         const Fr* E = p->tail_pyr.get() + p->cur_m / 2;
-        if (kind == 1) launch_sc1_round(p->curA, p->curB, p->curC, nullptr, nullptr, nullptr, E, nullptr, p->cur_m, out3, c->ws, st);
-        else launch_sc2_round(p->curA, p->curB, nullptr, nullptr, nullptr, p->cur_m, out3, c->ws, st);
-        ctx_sync(c);                               // tabs (host) is read by the async copy above
-        d2h_fr(c, sb_ctx::SLOT_OUT, S, 3);
+        o = round_begin(c);
+        if (kind == 1) launch_sc1_round(p->curA, p->curB, p->curC, nullptr, nullptr, nullptr, E, nullptr, p->cur_m, o, c->ws, st);
+        else launch_sc2_round(p->curA, p->curB, nullptr, nullptr, nullptr, p->cur_m, o, c->ws, st);
+        round_wait(c, o, S, 3);                    // the kernel has run: the async copy from `tabs` (host) before it is done too
         return;
     }
     const Fr* pyr = p->in_tail ? p->tail_pyr.get() : p->pyr.get();
+    RoundOut o = round_begin(c);
     if (!v_msg) {
-        if (kind == 1) launch_sc1_round(p->curA, p->curB, p->curC, nullptr, nullptr, nullptr, pyr + p->cur_m / 2, nullptr, p->cur_m, out3, c->ws, st);
-        else launch_sc2_round(p->curA, p->curB, nullptr, nullptr, nullptr, p->cur_m, out3, c->ws, st);
+        if (kind == 1) launch_sc1_round(p->curA, p->curB, p->curC, nullptr, nullptr, nullptr, pyr + p->cur_m / 2, nullptr, p->cur_m, o, c->ws, st);
+        else launch_sc2_round(p->curA, p->curB, nullptr, nullptr, nullptr, p->cur_m, o, c->ws, st);
     } else {
         size_t mo = p->cur_m / 2;
         Fr* base = p->in_tail ? (p->into_ping ? p->tail_ping.get() : p->tail_pong.get()) : (p->into_ping ? p->ping.get() : p->pong.get());
         Fr* Ao = base; Fr* Bo = base + mo; Fr* Co = base + 2 * mo;
         // after the fold the tables have mo entries -> mo/2 pairs weighted by the pyramid level of size mo/2
-        if (kind == 1) launch_sc1_round(p->curA, p->curB, p->curC, Ao, Bo, Co, pyr + std::max<size_t>(mo / 2, 1), r_dev, p->cur_m, out3, c->ws, st);
-        else launch_sc2_round(p->curA, p->curB, Ao, Bo, r_dev, p->cur_m, out3, c->ws, st);
+        if (kind == 1) launch_sc1_round(p->curA, p->curB, p->curC, Ao, Bo, Co, pyr + std::max<size_t>(mo / 2, 1), v_msg, p->cur_m, o, c->ws, st);
+        else launch_sc2_round(p->curA, p->curB, Ao, Bo, v_msg, p->cur_m, o, c->ws, st);
         p->curA = Ao; p->curB = Bo; p->curC = kind == 1 ? Co : nullptr; p->cur_m = mo; p->into_ping = !p->into_ping;
     }
-    d2h_fr(c, sb_ctx::SLOT_OUT, S, 3);
+    round_wait(c, o, S, 3);
     if (c->sharded() && !p->in_tail) {
         const int G = c->world;
         std::vector<Fr> all(3 * G);
@@ -786,14 +820,15 @@ static void prover_sc1_round(sb_prover* p, const Fr* v_msg, Fr* out_evals) {
 static void sc_final_fold(sb_prover* p, const Fr* last, int ntab, Fr* out) {
     sb_ctx* c = p->ctx; cudaStream_t st = c->stream;
     SB_REQUIRE(p->round == p->log_n, "sumcheck not finished");
-    h2d_fr(c, sb_ctx::SLOT_R, last, 1);
+    g_sb_h2d_bytes += sizeof(Fr);
     if (c->sharded() && !p->in_tail) {
         // log_n == loc cannot happen on a sharded context (glog >= 1), so the tables are the tail tables here
         throw SbError(SB_EINTERNAL, "sharded sumcheck ended outside the tail phase");
     }
     SB_REQUIRE(p->cur_m == 2, "sumcheck tables not fully folded");
-    launch_final_fold3(p->curA, p->curB, p->curC, ntab, c->d_mail.get() + sb_ctx::SLOT_R, c->d_mail.get() + sb_ctx::SLOT_OUT, st);
-    d2h_fr(c, sb_ctx::SLOT_OUT, out, ntab);
+    RoundOut o = round_begin(c);
+    launch_final_fold3(p->curA, p->curB, p->curC, ntab, last, o, st);
+    round_wait(c, o, out, ntab);
 }
 
 static void prover_fourth_round(sb_prover* p, const Fr* last, Fr* vabc) {
@@ -831,7 +866,8 @@ static void prover_sc2_round(sb_prover* p, const Fr* v_msg, Fr* out3_host) {
 #define SB_API_BEGIN(ctxptr)        \
     sb_ctx* _c = (ctxptr);          \
     try {                           \
-        if (_c) SB_CUDA(cudaSetDevice(_c->device));
+        if (_c) SB_CUDA(cudaSetDevice(_c->device)); \
+        if (_c) _c->comm_epoch();
 #define SB_API_END                                                        \
         return SB_OK;                                                     \
     } catch (const SbError& e) {                                          \
@@ -892,6 +928,7 @@ sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
         SB_CUDA(cudaMemsetAsync(c->ticket.get(), 0, sizeof(unsigned int), c->stream));
         c->d_mail.alloc(sb_ctx::MAIL, c->stream);
         c->h_mail.alloc(sb_ctx::MAIL);
+        c->round_out.alloc(4); c->round_flag.alloc(16);
         for (int i = 0; i < sb_ctx::NAUX; i++) {
             SB_CUDA(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
             SB_CUDA(cudaEventCreateWithFlags(&c->ev_aux[i], cudaEventDisableTiming));
@@ -919,6 +956,7 @@ void sb_ctx_destroy(sb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->block_partials.release(); c->ticket.release(); c->d_mail.release(); c->h_mail.release();
+    c->round_out.release(); c->round_flag.release();
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < sb_ctx::NAUX; i++) {
         if (c->aux[i]) { cudaStreamSynchronize(c->aux[i]); cudaStreamDestroy(c->aux[i]); }
@@ -1414,21 +1452,22 @@ sb_status sb_kernel_bench(sb_ctx* ctx, int which, uint32_t log_m, int reps, int 
     SB_CUDA(cudaMemsetAsync(in.get(), 0x11, 3 * m * sizeof(Fr), st));
     SB_CUDA(cudaMemsetAsync(e.get(), 0x07, m * sizeof(Fr), st));
     Fr r = Fr::from_u32(12345);
-    h2d_fr(ctx, sb_ctx::SLOT_R, &r, 1);
     const size_t flush_bytes = (size_t)256 << 20;
     DevBuf<uint4> fl(flush_l2 ? flush_bytes / 16 : 1, st);
     cudaEvent_t e0, e1;
     SB_CUDA(cudaEventCreate(&e0)); SB_CUDA(cudaEventCreate(&e1));
     double total = 0;
-    const Fr* rd = ctx->d_mail.get() + sb_ctx::SLOT_R;
-    Fr* o3 = ctx->d_mail.get() + sb_ctx::SLOT_OUT;
+    const Fr* rd = &r;                              // host pointer: the challenge is a kernel argument
+    DevBuf<Fr> pd(1, st);                           // the opening fold still reads its point from device memory
+    SB_CUDA(cudaMemcpyAsync(pd.get(), &r, sizeof(Fr), cudaMemcpyHostToDevice, st));
+    RoundOut o3{ctx->d_mail.get() + sb_ctx::SLOT_OUT, nullptr, 0};
     for (int rep = -3; rep < reps; rep++) {     // 3 warm-up launches
         if (flush_l2) SB_LAUNCH(k_flush_l2, SB_SMS * 4, 256, 0, st, fl.get(), flush_bytes / 16);
         SB_CUDA(cudaEventRecord(e0, st));
         if (which == 0) launch_sc1_round(in.get(), in.get() + m, in.get() + 2 * m, outb.get(), outb.get() + m / 2, outb.get() + m, e.get(), rd, m, o3, ctx->ws, st);
         else if (which == 1) launch_sc1_round(in.get(), in.get() + m, in.get() + 2 * m, nullptr, nullptr, nullptr, e.get(), nullptr, m, o3, ctx->ws, st);
         else if (which == 2) launch_sc2_round(in.get(), in.get() + m, outb.get(), outb.get() + m / 2, rd, m, o3, ctx->ws, st);
-        else launch_open_fold(in.get(), outb.get(), outb.get() + m / 2, rd, m / 2, st);
+        else launch_open_fold(in.get(), outb.get(), outb.get() + m / 2, pd.get(), m / 2, st);
         SB_CUDA(cudaEventRecord(e1, st));
         SB_CUDA(cudaEventSynchronize(e1));
         float ms = 0; SB_CUDA(cudaEventElapsedTime(&ms, e0, e1));

@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-from .api import COMM_ALLGATHER, CommStruct, Context
+from .api import COMM_ALLGATHER, COMM_BARRIER, CommStruct, Context
 
 
 class TorchComm:
@@ -31,7 +31,7 @@ class TorchComm:
         self.calls = 0
         self.bytes = 0
         self.cb = COMM_ALLGATHER(self._allgather)
-        self.struct = CommStruct(self.rank, self.world, self.cb, None)
+        self.struct = CommStruct(self.rank, self.world, self.cb, COMM_BARRIER(), None)   # no barrier hook: the collective itself orders the ranks
 
     def _allgather(self, user, send, recv, nbytes):
         try:

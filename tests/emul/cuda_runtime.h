@@ -63,6 +63,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& fn)
 
 static inline void __syncthreads() { emu::g_block->block_bar->arrive_and_wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { (*emu::g_block->warp_bar)[emu::t_threadIdx.x >> 5]->arrive_and_wait(); }
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline uint32_t __shfl_down_sync(unsigned, uint32_t v, int off) {
     const unsigned lane = emu::t_threadIdx.x & 31, warp = emu::t_threadIdx.x >> 5;
@@ -134,6 +135,7 @@ static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
 static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)malloc(8); return cudaSuccess; }
