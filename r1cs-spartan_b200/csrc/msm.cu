@@ -100,9 +100,12 @@ struct PlanPtrs {
     uint32_t* offsets; uint32_t* cursors; uint32_t* info;
     uint32_t* perm; uint32_t* invperm;          // bucket order of the accumulation (nullptr: natural order)
     uint32_t* plan[MSM_MAX_LEVELS];
+    uint32_t* hplan[MSM_MAX_HALVINGS];          // hplan[r-1][b] = exclusive scan (bucket order) of ceil(count_b / 2^r): list layout after round r
+    uint32_t R;                                 // pairwise affine rounds before the XYZZ accumulation (0: none)
 };
 // per-CTA aggregates the plan kernels hand to one another
 struct PlanWs {
+    uint32_t* cta_hsum;    // [R][nC]         outputs of pairwise round r of the CTA's buckets
     uint32_t* cta_sum;     // [nC]            entries of the CTA's buckets
     uint32_t* cta_max;     // [nC]            longest run among them
     uint32_t* cta_hist;    // [nC][s0 + 1]    buckets per first-level chunk length
@@ -156,25 +159,38 @@ __device__ inline uint32_t plan_block_exscan(uint32_t v, uint32_t* sh /* PLAN_T 
 //   D  per CTA of positions in that order: chunks per level
 //   F  plan[l][k] = exclusive scan over that order of ceil(count / (S0 S1^l))   (chunk plan of accumulation level l)
 // info: [0] entries, [1] longest run, [2] S0, [3] levels, [4] S1, [MSM_INFO_ITEMS + l] chunks of level l.
-__global__ void __launch_bounds__(PLAN_T) k_plan_a(const uint32_t* __restrict__ counts, uint32_t B, uint32_t s0, PlanWs ws) {
+// (with R pairwise affine rounds in front, the XYZZ accumulation sees runs of ceil(count / 2^R) points: chunk lengths,
+// accumulation order and level plans are all derived from those)
+__global__ void __launch_bounds__(PLAN_T) k_plan_a(const uint32_t* __restrict__ counts, uint32_t B, uint32_t s0, uint32_t R, PlanWs ws) {
     __shared__ uint32_t hist[1025];
     __shared__ uint32_t sh[3 * PLAN_T];
-    const uint32_t t = threadIdx.x;
+    const uint32_t t = threadIdx.x, nC = gridDim.x;
     for (uint32_t k = t; k <= s0; k += PLAN_T) hist[k] = 0;
     __syncthreads();
     uint32_t sum = 0, zero = 0, mx = 0;
+    uint32_t hs[MSM_MAX_HALVINGS];
+#pragma unroll
+    for (int r = 0; r < MSM_MAX_HALVINGS; r++) hs[r] = 0;
     const uint32_t b0 = blockIdx.x * PLAN_TILE + t * PLAN_V;
+    const uint32_t radd = (1u << R) - 1;
 #pragma unroll
     for (int v = 0; v < PLAN_V; v++) {
         const uint32_t b = b0 + v;
         if (b < B) {
             const uint32_t c = __ldg(&counts[b]);
             sum += c; mx = max(mx, c);
-            atomicAdd(&hist[plan_key(c, s0)], 1u);
+            atomicAdd(&hist[plan_key((c + radd) >> R, s0)], 1u);
+#pragma unroll
+            for (int r = 0; r < MSM_MAX_HALVINGS; r++) if ((uint32_t)r < R) hs[r] += (c + (2u << r) - 1) >> (r + 1);
         }
     }
     plan_block_sum3(sum, zero, mx, sh);
     if (t == 0) { ws.cta_sum[blockIdx.x] = sum; ws.cta_max[blockIdx.x] = mx; }
+    for (uint32_t r = 0; r < R; r++) {
+        uint32_t h = hs[r], z0 = 0, z1 = 0;
+        plan_block_sum3(h, z0, z1, sh);
+        if (t == 0) ws.cta_hsum[(size_t)r * nC + blockIdx.x] = h;
+    }
     for (uint32_t k = t; k <= s0; k += PLAN_T) ws.cta_hist[(size_t)blockIdx.x * (s0 + 1) + k] = hist[k];
 }
 
@@ -192,10 +208,12 @@ __global__ void __launch_bounds__(PLAN_T) k_plan_c(const uint32_t* __restrict__ 
         mx = max(mx, ws.cta_max[c]);
     }
     plan_block_sum3(before, total, mx, sh);
+    const uint32_t R = pp.R, radd = (1u << R) - 1;
     if (blk == 0 && t == 0) {
-        const uint32_t s1 = msm_pick_s1(mx, s0, s1_min, nlaunch);
+        const uint32_t mxr = (mx + radd) >> R;            // longest run the XYZZ accumulation sees
+        const uint32_t s1 = msm_pick_s1(mxr, s0, s1_min, nlaunch);
         pp.offsets[B] = total;
-        pp.info[0] = total; pp.info[1] = mx; pp.info[2] = s0; pp.info[3] = msm_levels(mx, s0, s1); pp.info[4] = s1;
+        pp.info[0] = total; pp.info[1] = mx; pp.info[2] = s0; pp.info[3] = msm_levels(mxr, s0, s1); pp.info[4] = s1;
     }
     const bool sorted = pp.perm != nullptr;
     if (sorted) {
@@ -226,10 +244,28 @@ __global__ void __launch_bounds__(PLAN_T) k_plan_c(const uint32_t* __restrict__ 
         if (b < B) {
             pp.offsets[b] = run; pp.cursors[b] = run; run += c[v];
             if (sorted) {
-                const uint32_t p = atomicAdd(&pos[plan_key(c[v], s0)], 1u);
+                const uint32_t p = atomicAdd(&pos[plan_key((c[v] + radd) >> R, s0)], 1u);
                 pp.perm[p] = b; pp.invperm[b] = p;
             }
         }
+    }
+    // layouts of the lists after every pairwise round
+    for (uint32_t r = 0; r < R; r++) {
+        uint32_t bef = 0, tot2 = 0, z = 0;
+        for (uint32_t cc = t; cc < nC; cc += PLAN_T) {
+            const uint32_t h = ws.cta_hsum[(size_t)r * nC + cc];
+            tot2 += h; if (cc < blk) bef += h;
+        }
+        plan_block_sum3(bef, tot2, z, sh);
+        uint32_t n[PLAN_V], hsum = 0;
+#pragma unroll
+        for (int v = 0; v < PLAN_V; v++) { n[v] = (c[v] + (2u << r) - 1) >> (r + 1); hsum += n[v]; }
+        uint32_t x = bef + plan_block_exscan(hsum, sh);
+#pragma unroll
+        for (int v = 0; v < PLAN_V; v++) {
+            if (b0 + v < B) { pp.hplan[r][b0 + v] = x; x += n[v]; }
+        }
+        if (blk == 0 && t == 0) { pp.hplan[r][B] = tot2; pp.info[MSM_INFO_HTOT + r] = tot2; }
     }
 }
 
@@ -244,7 +280,7 @@ __global__ void __launch_bounds__(PLAN_T) k_plan_levels(const uint32_t* __restri
 #pragma unroll
     for (int v = 0; v < PLAN_V; v++) {
         const uint32_t k = k0 + v;
-        c[v] = k < B ? __ldg(&counts[pp.perm ? pp.perm[k] : k]) : 0;
+        c[v] = k < B ? ((__ldg(&counts[pp.perm ? pp.perm[k] : k]) + ((1u << pp.R) - 1)) >> pp.R) : 0;
     }
     uint64_t div = s0;
     for (uint32_t l = 0; l < levels; l++, div *= s1) {
@@ -292,8 +328,11 @@ constexpr int ACC_THREADS = 64;
 // MIXED: level 0, mixed additions of table entries (sorted -> tab, sign in bit 31); otherwise level `level` >= 1, full
 // additions of the partial sums of level - 1 (in_pts, laid out by the plan of level - 1 = seg_off).  Levels the plan
 // does not use return at once (the host launches a fixed number of levels, see msm_group_run).
+// (after pairwise affine rounds, level 0 reads the affine list they left -- aff_in, laid out by the last round's plan --
+// instead of the table)
 template <class F, bool MIXED>
 __global__ void __launch_bounds__(ACC_THREADS) k_seg_accum(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
+                                                           const AffinePt<F>* __restrict__ aff_in,
                                                            const XyzzPt<F>* __restrict__ in_pts, const uint32_t* __restrict__ seg_off,
                                                            const uint32_t* __restrict__ chunk_start, uint32_t nseg, uint32_t level,
                                                            const uint32_t* __restrict__ info, const uint32_t* __restrict__ perm,
@@ -316,15 +355,112 @@ __global__ void __launch_bounds__(ACC_THREADS) k_seg_accum(const AffinePt<F>* __
     XyzzPt<F> acc = XyzzPt<F>::inf();
     for (uint32_t e = beg; e < end; e++) {
         if (MIXED) {
-            uint32_t ent = __ldg(&sorted[e]);
-            AffinePt<F> q = ldg_elem(&tab[ent & 0x7fffffffu]);
-            if (ent & 0x80000000u) q.y = F::neg(q.y);
+            AffinePt<F> q;
+            if (aff_in) q = ldg_elem(&aff_in[e]);
+            else {
+                uint32_t ent = __ldg(&sorted[e]);
+                q = ldg_elem(&tab[ent & 0x7fffffffu]);
+                if (ent & 0x80000000u) q.y = F::neg(q.y);
+            }
             acc = XyzzPt<F>::add_mixed(acc, q);
         } else {
             acc = XyzzPt<F>::add(acc, ldg_elem(&in_pts[e]));
         }
     }
     st_elem(&out[p], acc);
+}
+
+// ------------------------------------------------------------------ pairwise rounds in affine coordinates
+// One round halves every bucket run: output element j of bucket b is the sum of input elements 2j and 2j+1 of that
+// bucket (or a copy of element 2j when the run is odd).  An affine addition is one inversion plus 2M + 1S; each thread
+// owns K consecutive output elements and shares ONE inversion among them (Montgomery's trick: +3M per element), so an
+// addition costs 5M + 1S + (one inversion) / K instead of the 8M + 2S of a mixed XYZZ addition -- over Fq2, 4 176
+// against 6 912 integer products.  The inversion is the binary-GCD one (Fp::inv_fast, ~30 k instructions): with
+// the Fermat ladder (~170 k) round 1 measured this LOSING at every K; the rounds only pay with the cheap inversion.
+// The exceptional cases of the group law (an input at infinity, P = Q, P = -Q) are handled exactly; their
+// denominator is replaced by 1 so that the shared inversion stays well defined.
+constexpr int AFF_THREADS = 64;
+enum { PAIR_COPY_P = 0, PAIR_COPY_Q = 1, PAIR_ADD = 2, PAIR_DBL = 3, PAIR_INF = 4 };
+
+template <class F>
+__device__ __forceinline__ int pair_classify(const AffinePt<F>& P, const AffinePt<F>& Q, bool has2, F& d) {
+    d = F::one();
+    if (!has2 || Q.is_inf()) return PAIR_COPY_P;
+    if (P.is_inf()) return PAIR_COPY_Q;
+    if (P.x == Q.x) {
+        if (P.y == Q.y && !P.y.is_zero()) { d = F::dbl(P.y); return PAIR_DBL; }
+        return PAIR_INF;
+    }
+    d = F::sub(Q.x, P.x);
+    return PAIR_ADD;
+}
+
+template <class F, bool FIRST>
+__global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
+                                                              const AffinePt<F>* __restrict__ in_aff, const uint32_t* __restrict__ in_off,
+                                                              const uint32_t* __restrict__ out_off, uint32_t B, uint32_t nthreads, uint32_t K,
+                                                              F* __restrict__ prefix, AffinePt<F>* __restrict__ out_aff) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = out_off[B];
+    // the outputs are dealt to the threads in equal shares: thread t owns [t * per, (t + 1) * per), per = ceil(total / nthreads) <= K
+    const uint32_t per = (total + nthreads - 1) / nthreads;
+    const uint64_t p0l = (uint64_t)t * per;
+    if (t >= nthreads || per == 0 || p0l >= total) return;
+    const uint32_t p0 = (uint32_t)p0l, p1 = min(p0 + per, total);
+    (void)K;
+    auto load_in = [&](uint32_t idx) -> AffinePt<F> {
+        if (FIRST) {
+            uint32_t ent = __ldg(&sorted[idx]);
+            AffinePt<F> q = ldg_elem(&tab[ent & 0x7fffffffu]);
+            if (ent & 0x80000000u) q.y = F::neg(q.y);
+            return q;
+        }
+        return ldg_elem(&in_aff[idx]);
+    };
+    uint32_t lo = 0, hi = B;                    // bucket of p0: last b with out_off[b] <= p0
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&out_off[mid]) <= p0) lo = mid; else hi = mid;
+    }
+    // pass 1: prefix products of the denominators
+    uint32_t b = lo;
+    F acc = F::one();
+    for (uint32_t p = p0; p < p1; p++) {
+        while (__ldg(&out_off[b + 1]) <= p) b++;
+        const uint32_t j = p - __ldg(&out_off[b]);
+        const uint32_t ib = __ldg(&in_off[b]), n_in = __ldg(&in_off[b + 1]) - ib;
+        const bool has2 = 2 * j + 1 < n_in;
+        AffinePt<F> P = load_in(ib + 2 * j), Q = has2 ? load_in(ib + 2 * j + 1) : P;
+        F d;
+        pair_classify(P, Q, has2, d);
+        st_elem(&prefix[(size_t)(p - p0) * nthreads + t], acc);
+        acc = F::mul(acc, d);
+    }
+    F inv = F::inv_fast(acc);
+    // pass 2, backwards: 1/d_k = inv * prefix_k, then inv *= d_k
+    for (uint32_t p = p1; p-- > p0;) {
+        while (__ldg(&out_off[b]) > p) b--;
+        const uint32_t j = p - __ldg(&out_off[b]);
+        const uint32_t ib = __ldg(&in_off[b]), n_in = __ldg(&in_off[b + 1]) - ib;
+        const bool has2 = 2 * j + 1 < n_in;
+        AffinePt<F> P = load_in(ib + 2 * j), Q = has2 ? load_in(ib + 2 * j + 1) : P;
+        F d;
+        const int kind = pair_classify(P, Q, has2, d);
+        F dinv = F::mul(inv, ldg_elem(&prefix[(size_t)(p - p0) * nthreads + t]));
+        inv = F::mul(inv, d);
+        AffinePt<F> r;
+        if (kind == PAIR_COPY_P) r = P;
+        else if (kind == PAIR_COPY_Q) r = Q;
+        else if (kind == PAIR_INF) r = AffinePt<F>::inf();
+        else {
+            F lam;
+            if (kind == PAIR_ADD) lam = F::mul(F::sub(Q.y, P.y), dinv);
+            else { F xx = F::sqr(P.x); lam = F::mul(F::add(F::dbl(xx), xx), dinv); }
+            r.x = F::sub(F::sub(F::sqr(lam), P.x), Q.x);
+            r.y = F::sub(F::mul(lam, F::sub(P.x, r.x)), P.y);
+        }
+        st_elem(&out_aff[p], r);
+    }
 }
 
 template <class F>
@@ -474,6 +610,17 @@ static bool msm_sorted() { static const bool v = msm_env_u32("SB_MSM_SORTED", 1,
 static uint32_t msm_s1_min() { static const uint32_t v = msm_env_u32("SB_MSM_S1", 3, 2, 4096); return v; }
 // accumulation levels a pipeline launches; the device raises S1 when that many levels of the minimal S1 would not
 // cover the longest run (S0 * 3^4 = 3888 entries per bucket at the defaults, 10x the runs of uniform scalars)
+// Pairwise affine rounds (see k_affine_round): R rounds for G2 groups of at least 2^SB_MSM_AFFINE_LOG2 entries, each thread
+// sharing one inversion among at most SB_MSM_AFFINE_K additions.  Over Fq (G1) the inversion costs 16 additions instead of
+// 5 and the saving per addition is the same 40 %, so G1 groups only take the rounds when SB_MSM_AFFINE_G1=1.
+template <class F>
+static uint32_t msm_affine_rounds(uint64_t etot) {
+    static const uint32_t lg = msm_env_u32("SB_MSM_AFFINE_LOG2", 21, 0, 40), rounds = msm_env_u32("SB_MSM_AFFINE_ROUNDS", 0, 0, MSM_MAX_HALVINGS);
+    static const bool g1 = msm_env_u32("SB_MSM_AFFINE_G1", 0, 0, 1) != 0;
+    if (sizeof(F) != sizeof(Fq2) && !g1) return 0;
+    return etot >= ((uint64_t)1 << lg) ? rounds : 0;
+}
+static uint32_t msm_affine_kmax() { static const uint32_t v = msm_env_u32("SB_MSM_AFFINE_K", 64, 1, 1024); return v; }
 static uint32_t msm_nlaunch() { static const uint32_t v = msm_env_u32("SB_MSM_LEVELS", 5, 2, MSM_MAX_LEVELS); return v; }
 
 template <class F>
@@ -500,10 +647,20 @@ void msm_group_prepare(const std::vector<const AffinePt<F>*>& bases_dev, const s
     }
     SB_REQUIRE(etot < ((uint64_t)1 << 31) && mtot < ((uint64_t)1 << 31), "msm: too many (window, point) pairs for 31-bit table indices");
     out.mtot = (uint32_t)mtot; out.etot = (uint32_t)etot; out.btot = (uint32_t)btot; out.rtot = (uint32_t)rtot;
-    out.s0 = msm_s0(etot);
+    out.R = msm_affine_rounds<F>(etot);
+    out.s0 = msm_s0(etot >> out.R);
     {
+        // the XYZZ accumulation sees at most etot / 2^R + btot points
+        const uint64_t e0 = (etot >> out.R) + (out.R ? btot : 0);
         uint64_t div = out.s0;
-        for (int l = 0; l < MSM_MAX_LEVELS; l++, div *= msm_s1_min()) out.items_bound[l] = (uint32_t)(etot / div + btot);
+        for (int l = 0; l < MSM_MAX_LEVELS; l++, div *= msm_s1_min()) out.items_bound[l] = (uint32_t)(e0 / div + btot);
+        for (uint32_t r = 0; r < out.R; r++) {
+            const uint64_t bound = (etot >> (r + 1)) + btot;            // outputs of round r
+            const uint64_t resident = (uint64_t)SB_SMS * 4 * AFF_THREADS;  // threads one wave of the round kernel holds
+            uint64_t k = (bound + resident - 1) / resident;
+            k = std::min<uint64_t>(std::max<uint64_t>(k, std::min<uint32_t>(8, msm_affine_kmax())), msm_affine_kmax());
+            out.round_bound[r] = (uint32_t)bound; out.round_k[r] = (uint32_t)k; out.round_threads[r] = (uint32_t)((bound + k - 1) / k);
+        }
     }
     out.slots_dev.alloc(J, stream);
     SB_CUDA(cudaMemcpyAsync(out.slots_dev.get(), out.slots.data(), J * sizeof(MsmSlot), cudaMemcpyHostToDevice, stream));
@@ -538,6 +695,18 @@ void msm_group_prepare(const std::vector<const AffinePt<F>*>& bases_dev, const s
     sc.ptsA.alloc(std::max<uint32_t>(out.items_bound[0], 1), stream);
     sc.ptsB.alloc(std::max<uint32_t>(out.items_bound[1], 1), stream);
     sc.block_out.alloc(rtot, stream);
+    if (out.R) {
+        const size_t nC = (btot + PLAN_TILE - 1) / PLAN_TILE;
+        sc.cta_hsum.alloc(nC * out.R, stream);
+        size_t pre = 0;
+        for (uint32_t r = 0; r < out.R; r++) {
+            sc.hplan[r].alloc(btot + 1, stream);
+            pre = std::max<size_t>(pre, (size_t)out.round_threads[r] * out.round_k[r]);
+        }
+        sc.affA.alloc(out.round_bound[0], stream);
+        if (out.R > 1) sc.affB.alloc(out.round_bound[1], stream);
+        sc.prefix.alloc(pre, stream);
+    }
     SB_CUDA(cudaStreamSynchronize(stream));           // `slots` (host) was the source of an asynchronous copy
 }
 
@@ -551,26 +720,42 @@ void msm_group_run(const MsmGroup<F>& g, const MsmScalarPtrs& scalars, XyzzPt<F>
     pp.offsets = sc.offsets.get(); pp.cursors = sc.cursors.get(); pp.info = sc.info.get();
     if (msm_sorted()) { pp.perm = sc.perm.get(); pp.invperm = sc.invperm.get(); }
     for (uint32_t l = 0; l < nlaunch; l++) pp.plan[l] = sc.plan[l].get();
+    pp.R = g.R;
+    for (uint32_t r = 0; r < g.R; r++) pp.hplan[r] = sc.hplan[r].get();
     if (g_sb_prof_on) { g_sb_prof_tag = 0; while (((size_t)2 << g_sb_prof_tag) <= g.mtot) g_sb_prof_tag++; }
     SB_CUDA(cudaMemsetAsync(sc.counts.get(), 0, (size_t)B * sizeof(uint32_t), stream));
     SB_LAUNCH(k_msm_digits, grid_for(g.mtot, 256, 8), 256, 0, stream, scalars, g.slots_dev.get(), J, g.mtot, sc.codes.get(), sc.counts.get());
-    PlanWs ws{sc.cta_sum.get(), sc.cta_max.get(), sc.cta_hist.get(), sc.cta_lsum.get()};
+    PlanWs ws{sc.cta_hsum.get(), sc.cta_sum.get(), sc.cta_max.get(), sc.cta_hist.get(), sc.cta_lsum.get()};
     const int nC = (int)((B + PLAN_TILE - 1) / PLAN_TILE);
-    SB_LAUNCH(k_plan_a, nC, PLAN_T, 0, stream, sc.counts.get(), B, g.s0, ws);
+    SB_LAUNCH(k_plan_a, nC, PLAN_T, 0, stream, sc.counts.get(), B, g.s0, g.R, ws);
     SB_LAUNCH(k_plan_c, nC, PLAN_T, 0, stream, sc.counts.get(), B, g.s0, msm_s1_min(), nlaunch, ws, pp);
     SB_LAUNCH_NAMED("k_plan_levels<sum>", (k_plan_levels<false>), nC, PLAN_T, 0, stream, sc.counts.get(), B, ws, pp);
     SB_LAUNCH_NAMED("k_plan_levels<write>", (k_plan_levels<true>), nC, PLAN_T, 0, stream, sc.counts.get(), B, ws, pp);
     SB_LAUNCH(k_msm_scatter, grid_for(g.etot, 256, 8), 256, 0, stream, sc.codes.get(), (size_t)g.etot, sc.cursors.get(), sc.sorted.get());
+    // pairwise affine rounds: every bucket run is halved R times
+    const AffinePt<F>* aff = nullptr;
+    const uint32_t* seg0 = sc.offsets.get();
+    for (uint32_t r = 0; r < g.R; r++) {
+        AffinePt<F>* outp = (r % 2 == 0) ? sc.affA.get() : sc.affB.get();
+        const int grid = (int)((g.round_threads[r] + AFF_THREADS - 1) / AFF_THREADS);
+        if (r == 0)
+            SB_LAUNCH_NAMED(SB_KNAME(F, "k_affine_round"), (k_affine_round<F, true>), grid, AFF_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), aff, seg0,
+                            sc.hplan[r].get(), B, g.round_threads[r], g.round_k[r], sc.prefix.get(), outp);
+        else
+            SB_LAUNCH_NAMED(SB_KNAME(F, "k_affine_round"), (k_affine_round<F, false>), grid, AFF_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), aff, seg0,
+                            sc.hplan[r].get(), B, g.round_threads[r], g.round_k[r], sc.prefix.get(), outp);
+        aff = outp; seg0 = sc.hplan[r].get();
+    }
     for (uint32_t l = 0; l < nlaunch; l++) {
         XyzzPt<F>* outp = (l % 2 == 0) ? sc.ptsA.get() : sc.ptsB.get();
         const XyzzPt<F>* inp = (l % 2 == 0) ? sc.ptsB.get() : sc.ptsA.get();
         const int grid = (int)((std::max<uint32_t>(g.items_bound[l], 1) + ACC_THREADS - 1) / ACC_THREADS);
         if (l == 0)
-            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_mixed"), (k_seg_accum<F, true>), grid, ACC_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), inp,
-                            sc.offsets.get(), sc.plan[0].get(), B, l, sc.info.get(), pp.perm, outp);
+            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_mixed"), (k_seg_accum<F, true>), grid, ACC_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), aff, inp,
+                            seg0, sc.plan[0].get(), B, l, sc.info.get(), pp.perm, outp);
         else
-            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, false>), grid, ACC_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), inp,
-                            sc.plan[l - 1].get(), sc.plan[l].get(), B, l, sc.info.get(), (const uint32_t*)nullptr, outp);
+            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, false>), grid, ACC_THREADS, 0, stream, g.tab.get(), sc.sorted.get(),
+                            (const AffinePt<F>*)nullptr, inp, sc.plan[l - 1].get(), sc.plan[l].get(), B, l, sc.info.get(), (const uint32_t*)nullptr, outp);
     }
     const size_t smem = RED_THREADS * sizeof(XyzzPt<F>);
     SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce1"), (k_bucket_reduce1<F>), (int)g.rtot, RED_THREADS, smem, stream, sc.ptsA.get(), sc.ptsB.get(), pp,

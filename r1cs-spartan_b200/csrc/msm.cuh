@@ -35,8 +35,9 @@ WinLayout msm_layout(size_t m);
 
 constexpr int MSM_MAX_SLOTS = 32;
 constexpr int MSM_MAX_LEVELS = 8;        // accumulation levels a pipeline launches (levels the plan does not use exit at once)
-constexpr int MSM_INFO_WORDS = 32;       // see k_scan_plan: entries, longest run, S0, levels, S1, items[MSM_MAX_LEVELS] at 8
-constexpr int MSM_INFO_ITEMS = 8;
+constexpr int MSM_MAX_HALVINGS = 8;      // batched-affine pairwise rounds before the XYZZ accumulation
+constexpr int MSM_INFO_WORDS = 32;       // entries, longest run, S0, levels, S1; items[MSM_MAX_LEVELS] at 8; round totals[MSM_MAX_HALVINGS] at 16
+constexpr int MSM_INFO_ITEMS = 8, MSM_INFO_HTOT = 16;
 
 // One MSM of a group: m points, its own window layout, its own range of the shared table / bucket / reduction spaces.
 struct MsmSlot {
@@ -57,7 +58,10 @@ template <class F>
 struct MsmScratch {
     DevBuf<uint32_t> codes, sorted, counts, offsets, cursors, info, perm, invperm;
     DevBuf<uint32_t> plan[MSM_MAX_LEVELS];
-    DevBuf<uint32_t> cta_sum, cta_max, cta_hist, cta_lsum;     // per-CTA aggregates of the plan kernels
+    DevBuf<uint32_t> cta_sum, cta_max, cta_hist, cta_lsum, cta_hsum;     // per-CTA aggregates of the plan kernels
+    DevBuf<uint32_t> hplan[MSM_MAX_HALVINGS];
+    DevBuf<AffinePt<F>> affA, affB;        // outputs of the pairwise rounds (ping-pong)
+    DevBuf<F> prefix;                      // per-thread prefix products of the simultaneous inversion
     DevBuf<XyzzPt<F>> ptsA, ptsB, block_out;
 };
 
@@ -69,6 +73,8 @@ struct MsmGroup {
     uint32_t mtot = 0, etot = 0, btot = 0, rtot = 0;
     uint32_t s0 = 0;                 // chunk length of the first accumulation level (fixed when the group is prepared)
     uint32_t items_bound[MSM_MAX_LEVELS] = {};   // upper bounds on the chunk count of every level (grid sizes)
+    uint32_t R = 0;                  // pairwise affine rounds in front of the XYZZ accumulation (fixed when the group is prepared)
+    uint32_t round_bound[MSM_MAX_HALVINGS] = {}, round_k[MSM_MAX_HALVINGS] = {}, round_threads[MSM_MAX_HALVINGS] = {};
     mutable MsmScratch<F> scratch;
     size_t nslots() const { return slots.size(); }
 };
