@@ -382,19 +382,28 @@ __global__ void __launch_bounds__(ACC_THREADS) k_seg_accum(const AffinePt<F>* __
 constexpr int AFF_THREADS = 64;
 enum { PAIR_COPY_P = 0, PAIR_COPY_Q = 1, PAIR_ADD = 2, PAIR_DBL = 3, PAIR_INF = 4 };
 
-template <class F>
-__device__ __forceinline__ int pair_classify(const AffinePt<F>& P, const AffinePt<F>& Q, bool has2, F& d) {
+// denominator of the addition P + Q from the x coordinates alone; the y coordinates are only fetched in the rare cases
+// that need them (an x coordinate that is zero: the point may be the encoding of infinity; equal x coordinates:
+// doubling or cancellation).  load_y(k): y of input k (0 = P, 1 = Q).
+template <class F, class LoadY>
+__device__ __forceinline__ int pair_classify_x(const F& px, const F& qx, bool has2, LoadY load_y, F& d) {
     d = F::one();
-    if (!has2 || Q.is_inf()) return PAIR_COPY_P;
-    if (P.is_inf()) return PAIR_COPY_Q;
-    if (P.x == Q.x) {
-        if (P.y == Q.y && !P.y.is_zero()) { d = F::dbl(P.y); return PAIR_DBL; }
+    if (!has2) return PAIR_COPY_P;
+    const bool pz = px.is_zero(), qz = qx.is_zero();
+    if (qz && load_y(1).is_zero()) return PAIR_COPY_P;          // Q at infinity
+    if (pz && load_y(0).is_zero()) return PAIR_COPY_Q;          // P at infinity
+    if (px == qx) {
+        const F py = load_y(0);
+        if (py == load_y(1) && !py.is_zero()) { d = F::dbl(py); return PAIR_DBL; }
         return PAIR_INF;
     }
-    d = F::sub(Q.x, P.x);
+    d = F::sub(qx, px);
     return PAIR_ADD;
 }
 
+// The outputs of a round are dealt to the threads in equal contiguous shares (per = ceil(total / nthreads) <= K).  A
+// share may span several buckets: the loops run bucket by bucket, so that inside a bucket the input of output j is
+// simply elements 2j, 2j+1 of the bucket's run -- no lookup, no dependent index loads in the inner loop.
 template <class F, bool FIRST>
 __global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
                                                               const AffinePt<F>* __restrict__ in_aff, const uint32_t* __restrict__ in_off,
@@ -402,64 +411,85 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>*
                                                               F* __restrict__ prefix, AffinePt<F>* __restrict__ out_aff) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = out_off[B];
-    // the outputs are dealt to the threads in equal shares: thread t owns [t * per, (t + 1) * per), per = ceil(total / nthreads) <= K
     const uint32_t per = (total + nthreads - 1) / nthreads;
     const uint64_t p0l = (uint64_t)t * per;
     if (t >= nthreads || per == 0 || p0l >= total) return;
     const uint32_t p0 = (uint32_t)p0l, p1 = min(p0 + per, total);
     (void)K;
-    auto load_in = [&](uint32_t idx) -> AffinePt<F> {
+    // element `idx` of the input list: its address (first round: through the sorted entry, with the sign of the digit)
+    auto in_ptr = [&](uint32_t idx, bool& negate) -> const AffinePt<F>* {
         if (FIRST) {
-            uint32_t ent = __ldg(&sorted[idx]);
-            AffinePt<F> q = ldg_elem(&tab[ent & 0x7fffffffu]);
-            if (ent & 0x80000000u) q.y = F::neg(q.y);
-            return q;
+            const uint32_t ent = __ldg(&sorted[idx]);
+            negate = (ent & 0x80000000u) != 0;
+            return &tab[ent & 0x7fffffffu];
         }
-        return ldg_elem(&in_aff[idx]);
+        negate = false;
+        return &in_aff[idx];
+    };
+    auto load_full = [&](uint32_t idx) -> AffinePt<F> {
+        bool neg;
+        const AffinePt<F>* ptr = in_ptr(idx, neg);
+        AffinePt<F> q = ldg_elem(ptr);
+        if (neg) q.y = F::neg(q.y);
+        return q;
     };
     uint32_t lo = 0, hi = B;                    // bucket of p0: last b with out_off[b] <= p0
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
         if (__ldg(&out_off[mid]) <= p0) lo = mid; else hi = mid;
     }
-    // pass 1: prefix products of the denominators
-    uint32_t b = lo;
+    const uint32_t b_first = lo;
+    // pass 1: prefix products of the denominators (x coordinates only)
     F acc = F::one();
-    for (uint32_t p = p0; p < p1; p++) {
-        while (__ldg(&out_off[b + 1]) <= p) b++;
-        const uint32_t j = p - __ldg(&out_off[b]);
+    uint32_t b = b_first, p = p0;
+    while (p < p1) {
+        const uint32_t ob = __ldg(&out_off[b]), ob1 = __ldg(&out_off[b + 1]);
         const uint32_t ib = __ldg(&in_off[b]), n_in = __ldg(&in_off[b + 1]) - ib;
-        const bool has2 = 2 * j + 1 < n_in;
-        AffinePt<F> P = load_in(ib + 2 * j), Q = has2 ? load_in(ib + 2 * j + 1) : P;
-        F d;
-        pair_classify(P, Q, has2, d);
-        st_elem(&prefix[(size_t)(p - p0) * nthreads + t], acc);
-        acc = F::mul(acc, d);
+        const uint32_t jend = min(ob1, p1) - ob;
+        for (uint32_t j = p - ob; j < jend; j++, p++) {
+            const bool has2 = 2 * j + 1 < n_in;
+            bool n0, n1 = false;
+            const AffinePt<F>* pp0 = in_ptr(ib + 2 * j, n0);
+            const AffinePt<F>* pp1 = has2 ? in_ptr(ib + 2 * j + 1, n1) : pp0;
+            const F px = ldg_elem(&pp0->x), qx = has2 ? ldg_elem(&pp1->x) : px;
+            F d;
+            pair_classify_x(px, qx, has2, [&](int k) { F y = ldg_elem(k ? &pp1->y : &pp0->y); return (k ? n1 : n0) ? F::neg(y) : y; }, d);
+            st_elem(&prefix[(size_t)(p - p0) * nthreads + t], acc);
+            acc = F::mul(acc, d);
+        }
+        b++;
     }
     F inv = F::inv_fast(acc);
     // pass 2, backwards: 1/d_k = inv * prefix_k, then inv *= d_k
-    for (uint32_t p = p1; p-- > p0;) {
-        while (__ldg(&out_off[b]) > p) b--;
-        const uint32_t j = p - __ldg(&out_off[b]);
+    b--;
+    p = p1;
+    while (p > p0) {
+        const uint32_t ob = __ldg(&out_off[b]), ob1 = __ldg(&out_off[b + 1]);
         const uint32_t ib = __ldg(&in_off[b]), n_in = __ldg(&in_off[b + 1]) - ib;
-        const bool has2 = 2 * j + 1 < n_in;
-        AffinePt<F> P = load_in(ib + 2 * j), Q = has2 ? load_in(ib + 2 * j + 1) : P;
-        F d;
-        const int kind = pair_classify(P, Q, has2, d);
-        F dinv = F::mul(inv, ldg_elem(&prefix[(size_t)(p - p0) * nthreads + t]));
-        inv = F::mul(inv, d);
-        AffinePt<F> r;
-        if (kind == PAIR_COPY_P) r = P;
-        else if (kind == PAIR_COPY_Q) r = Q;
-        else if (kind == PAIR_INF) r = AffinePt<F>::inf();
-        else {
-            F lam;
-            if (kind == PAIR_ADD) lam = F::mul(F::sub(Q.y, P.y), dinv);
-            else { F xx = F::sqr(P.x); lam = F::mul(F::add(F::dbl(xx), xx), dinv); }
-            r.x = F::sub(F::sub(F::sqr(lam), P.x), Q.x);
-            r.y = F::sub(F::mul(lam, F::sub(P.x, r.x)), P.y);
+        const uint32_t jbeg = max(ob, p0) - ob;
+        for (uint32_t j = min(ob1, p1) - ob; j-- > jbeg;) {
+            p--;
+            const bool has2 = 2 * j + 1 < n_in;
+            const AffinePt<F> P = load_full(ib + 2 * j), Q = has2 ? load_full(ib + 2 * j + 1) : P;
+            F d;
+            const int kind = pair_classify_x(P.x, Q.x, has2, [&](int k) { return k ? Q.y : P.y; }, d);
+            const F dinv = F::mul(inv, ldg_elem(&prefix[(size_t)(p - p0) * nthreads + t]));
+            inv = F::mul(inv, d);
+            AffinePt<F> r;
+            if (kind == PAIR_COPY_P) r = P;
+            else if (kind == PAIR_COPY_Q) r = Q;
+            else if (kind == PAIR_INF) r = AffinePt<F>::inf();
+            else {
+                F lam;
+                if (kind == PAIR_ADD) lam = F::mul(F::sub(Q.y, P.y), dinv);
+                else { F xx = F::sqr(P.x); lam = F::mul(F::add(F::dbl(xx), xx), dinv); }
+                r.x = F::sub(F::sub(F::sqr(lam), P.x), Q.x);
+                r.y = F::sub(F::mul(lam, F::sub(P.x, r.x)), P.y);
+            }
+            st_elem(&out_aff[p], r);
         }
-        st_elem(&out_aff[p], r);
+        if (b == 0) break;
+        b--;
     }
 }
 
@@ -620,7 +650,7 @@ static uint32_t msm_affine_rounds(uint64_t etot) {
     if (sizeof(F) != sizeof(Fq2) && !g1) return 0;
     return etot >= ((uint64_t)1 << lg) ? rounds : 0;
 }
-static uint32_t msm_affine_kmax() { static const uint32_t v = msm_env_u32("SB_MSM_AFFINE_K", 64, 1, 1024); return v; }
+static uint32_t msm_affine_kmax() { static const uint32_t v = msm_env_u32("SB_MSM_AFFINE_K", 128, 1, 1024); return v; }
 static uint32_t msm_nlaunch() { static const uint32_t v = msm_env_u32("SB_MSM_LEVELS", 5, 2, MSM_MAX_LEVELS); return v; }
 
 template <class F>
@@ -710,19 +740,32 @@ void msm_group_prepare(const std::vector<const AffinePt<F>*>& bases_dev, const s
     SB_CUDA(cudaStreamSynchronize(stream));           // `slots` (host) was the source of an asynchronous copy
 }
 
-// digits + histogram -> plan -> scatter -> accumulation levels -> bucket reduction, all slots at once, no host round trip
+// digits + histogram -> plan -> scatter -> accumulation levels -> bucket reduction, all slots at once, no host round trip.
+// The pipeline is queued in three phases so that a caller can pipeline several groups (see msm_groups_run):
+//   front  digits, plan, scatter                                    (short, launch-bound)
+//   accum  pairwise affine rounds, first accumulation level         (throughput-bound: this is where the time goes)
+//   tail   later accumulation levels, bucket reduction              (latency-bound: ~2 ms of dependent point additions)
 template <class F>
-void msm_group_run(const MsmGroup<F>& g, const MsmScalarPtrs& scalars, XyzzPt<F>* out_dev, cudaStream_t stream, const char* tag) {
+static PlanPtrs msm_plan_ptrs(const MsmGroup<F>& g) {
     MsmScratch<F>& sc = g.scratch;
-    const uint32_t J = (uint32_t)g.nslots(), B = g.btot, nlaunch = msm_nlaunch();
-    (void)tag;
     PlanPtrs pp{};
     pp.offsets = sc.offsets.get(); pp.cursors = sc.cursors.get(); pp.info = sc.info.get();
     if (msm_sorted()) { pp.perm = sc.perm.get(); pp.invperm = sc.invperm.get(); }
-    for (uint32_t l = 0; l < nlaunch; l++) pp.plan[l] = sc.plan[l].get();
+    for (uint32_t l = 0; l < msm_nlaunch(); l++) pp.plan[l] = sc.plan[l].get();
     pp.R = g.R;
     for (uint32_t r = 0; r < g.R; r++) pp.hplan[r] = sc.hplan[r].get();
+    return pp;
+}
+template <class F>
+static void msm_prof_tag(const MsmGroup<F>& g) {
     if (g_sb_prof_on) { g_sb_prof_tag = 0; while (((size_t)2 << g_sb_prof_tag) <= g.mtot) g_sb_prof_tag++; }
+}
+template <class F>
+void msm_group_front(const MsmGroup<F>& g, const MsmScalarPtrs& scalars, cudaStream_t stream) {
+    MsmScratch<F>& sc = g.scratch;
+    const uint32_t J = (uint32_t)g.nslots(), B = g.btot, nlaunch = msm_nlaunch();
+    PlanPtrs pp = msm_plan_ptrs(g);
+    msm_prof_tag(g);
     SB_CUDA(cudaMemsetAsync(sc.counts.get(), 0, (size_t)B * sizeof(uint32_t), stream));
     SB_LAUNCH(k_msm_digits, grid_for(g.mtot, 256, 8), 256, 0, stream, scalars, g.slots_dev.get(), J, g.mtot, sc.codes.get(), sc.counts.get());
     PlanWs ws{sc.cta_hsum.get(), sc.cta_sum.get(), sc.cta_max.get(), sc.cta_hist.get(), sc.cta_lsum.get()};
@@ -732,6 +775,14 @@ void msm_group_run(const MsmGroup<F>& g, const MsmScalarPtrs& scalars, XyzzPt<F>
     SB_LAUNCH_NAMED("k_plan_levels<sum>", (k_plan_levels<false>), nC, PLAN_T, 0, stream, sc.counts.get(), B, ws, pp);
     SB_LAUNCH_NAMED("k_plan_levels<write>", (k_plan_levels<true>), nC, PLAN_T, 0, stream, sc.counts.get(), B, ws, pp);
     SB_LAUNCH(k_msm_scatter, grid_for(g.etot, 256, 8), 256, 0, stream, sc.codes.get(), (size_t)g.etot, sc.cursors.get(), sc.sorted.get());
+    g_sb_prof_tag = -1;
+}
+template <class F>
+void msm_group_accum(const MsmGroup<F>& g, cudaStream_t stream) {
+    MsmScratch<F>& sc = g.scratch;
+    const uint32_t B = g.btot;
+    PlanPtrs pp = msm_plan_ptrs(g);
+    msm_prof_tag(g);
     // pairwise affine rounds: every bucket run is halved R times
     const AffinePt<F>* aff = nullptr;
     const uint32_t* seg0 = sc.offsets.get();
@@ -746,22 +797,36 @@ void msm_group_run(const MsmGroup<F>& g, const MsmScalarPtrs& scalars, XyzzPt<F>
                             sc.hplan[r].get(), B, g.round_threads[r], g.round_k[r], sc.prefix.get(), outp);
         aff = outp; seg0 = sc.hplan[r].get();
     }
-    for (uint32_t l = 0; l < nlaunch; l++) {
+    const int grid = (int)((std::max<uint32_t>(g.items_bound[0], 1) + ACC_THREADS - 1) / ACC_THREADS);
+    SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_mixed"), (k_seg_accum<F, true>), grid, ACC_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), aff,
+                    (const XyzzPt<F>*)nullptr, seg0, sc.plan[0].get(), B, 0u, sc.info.get(), pp.perm, sc.ptsA.get());
+    g_sb_prof_tag = -1;
+}
+template <class F>
+void msm_group_tail(const MsmGroup<F>& g, XyzzPt<F>* out_dev, cudaStream_t stream) {
+    MsmScratch<F>& sc = g.scratch;
+    const uint32_t J = (uint32_t)g.nslots(), B = g.btot, nlaunch = msm_nlaunch();
+    PlanPtrs pp = msm_plan_ptrs(g);
+    msm_prof_tag(g);
+    for (uint32_t l = 1; l < nlaunch; l++) {
         XyzzPt<F>* outp = (l % 2 == 0) ? sc.ptsA.get() : sc.ptsB.get();
         const XyzzPt<F>* inp = (l % 2 == 0) ? sc.ptsB.get() : sc.ptsA.get();
         const int grid = (int)((std::max<uint32_t>(g.items_bound[l], 1) + ACC_THREADS - 1) / ACC_THREADS);
-        if (l == 0)
-            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_mixed"), (k_seg_accum<F, true>), grid, ACC_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), aff, inp,
-                            seg0, sc.plan[0].get(), B, l, sc.info.get(), pp.perm, outp);
-        else
-            SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, false>), grid, ACC_THREADS, 0, stream, g.tab.get(), sc.sorted.get(),
-                            (const AffinePt<F>*)nullptr, inp, sc.plan[l - 1].get(), sc.plan[l].get(), B, l, sc.info.get(), (const uint32_t*)nullptr, outp);
+        SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, false>), grid, ACC_THREADS, 0, stream, g.tab.get(), sc.sorted.get(),
+                        (const AffinePt<F>*)nullptr, inp, sc.plan[l - 1].get(), sc.plan[l].get(), B, l, sc.info.get(), (const uint32_t*)nullptr, outp);
     }
     const size_t smem = RED_THREADS * sizeof(XyzzPt<F>);
     SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce1"), (k_bucket_reduce1<F>), (int)g.rtot, RED_THREADS, smem, stream, sc.ptsA.get(), sc.ptsB.get(), pp,
                     g.slots_dev.get(), J, sc.block_out.get());
     SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce2"), (k_bucket_reduce2<F>), (int)J, RED_THREADS, smem, stream, sc.block_out.get(), g.slots_dev.get(), out_dev);
     g_sb_prof_tag = -1;
+}
+template <class F>
+void msm_group_run(const MsmGroup<F>& g, const MsmScalarPtrs& scalars, XyzzPt<F>* out_dev, cudaStream_t stream, const char* tag) {
+    (void)tag;
+    msm_group_front(g, scalars, stream);
+    msm_group_accum(g, stream);
+    msm_group_tail(g, out_dev, stream);
 }
 
 // ------------------------------------------------------------------ fixed-base multiplication (keygen)
@@ -821,6 +886,12 @@ void fixed_base_mul(const AffinePt<F>& g_host, const Fr* scalars_dev, size_t n, 
 
 template void msm_group_prepare<Fq>(const std::vector<const AffinePt<Fq>*>&, const std::vector<size_t>&, MsmGroup<Fq>&, cudaStream_t);
 template void msm_group_prepare<Fq2>(const std::vector<const AffinePt<Fq2>*>&, const std::vector<size_t>&, MsmGroup<Fq2>&, cudaStream_t);
+template void msm_group_front<Fq>(const MsmGroup<Fq>&, const MsmScalarPtrs&, cudaStream_t);
+template void msm_group_front<Fq2>(const MsmGroup<Fq2>&, const MsmScalarPtrs&, cudaStream_t);
+template void msm_group_accum<Fq>(const MsmGroup<Fq>&, cudaStream_t);
+template void msm_group_accum<Fq2>(const MsmGroup<Fq2>&, cudaStream_t);
+template void msm_group_tail<Fq>(const MsmGroup<Fq>&, XyzzPt<Fq>*, cudaStream_t);
+template void msm_group_tail<Fq2>(const MsmGroup<Fq2>&, XyzzPt<Fq2>*, cudaStream_t);
 template void msm_group_run<Fq>(const MsmGroup<Fq>&, const MsmScalarPtrs&, XyzzPt<Fq>*, cudaStream_t, const char*);
 template void msm_group_run<Fq2>(const MsmGroup<Fq2>&, const MsmScalarPtrs&, XyzzPt<Fq2>*, cudaStream_t, const char*);
 template void fixed_base_mul<Fq>(const AffinePt<Fq>&, const Fr*, size_t, AffinePt<Fq>*, cudaStream_t);

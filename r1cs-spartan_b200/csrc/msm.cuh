@@ -91,6 +91,12 @@ void msm_group_prepare(const std::vector<const AffinePt<F>*>& bases_dev, const s
 template <class F>
 void msm_group_run(const MsmGroup<F>& g, const MsmScalarPtrs& scalars, XyzzPt<F>* out_dev, cudaStream_t stream, const char* tag = nullptr);
 
+// The three phases of msm_group_run, for callers that pipeline several groups: a group's `accum` must follow its `front`
+// and its `tail` its `accum` (in stream order or through events); different groups are independent of one another.
+template <class F> void msm_group_front(const MsmGroup<F>& g, const MsmScalarPtrs& scalars, cudaStream_t stream);
+template <class F> void msm_group_accum(const MsmGroup<F>& g, cudaStream_t stream);
+template <class F> void msm_group_tail(const MsmGroup<F>& g, XyzzPt<F>* out_dev, cudaStream_t stream);
+
 // out[i] = scalars[i] * g for n scalars (device, Montgomery), affine results (device)
 template <class F>
 void fixed_base_mul(const AffinePt<F>& g_host, const Fr* scalars_dev, size_t n, AffinePt<F>* out_dev, cudaStream_t stream);

@@ -42,9 +42,10 @@ struct sb_ctx {
     // auxiliary streams: an opening may be split into several MSM groups (pipelines) that run concurrently, so that the
     // latency-bound end of one (later accumulation levels, bucket reduction) hides behind the throughput-bound
     // accumulation of the next; the sharded prover's tail opening is one more group
-    static constexpr int NAUX = 4;
-    cudaStream_t aux[NAUX] = {};
-    cudaEvent_t ev_main = nullptr, ev_aux[NAUX] = {};
+    static constexpr int NAUX = 6;
+    cudaStream_t aux[NAUX] = {};       // front + accumulation of group k
+    cudaStream_t tail[NAUX] = {};      // high priority: the latency-bound tail of group k (later levels, bucket reduction)
+    cudaEvent_t ev_main = nullptr, ev_acc[NAUX] = {}, ev_done[NAUX] = {};
     cudaStream_t copy_stream = nullptr; // witness upload that overlaps the commitment (sharded sb_prove)
     cudaEvent_t ev_copy = nullptr;
     bool serial_msm = false;           // profiling aid: keep every MSM group on the main stream
@@ -103,7 +104,9 @@ struct sb_pp {
     sb_ctx* ctx = nullptr;
     uint32_t nv = 0;            // variables handled by g1 / g2 below
     uint32_t nv_total = 0;      // variables of the whole polynomial
-    MsmGroup<Fq> g1;                              // one slot: powers_of_g[0] (slice)
+    // powers_of_g[0] (slice) in g1_parts contiguous parts of equal size, one single-slot group each: the commitment is the
+    // sum of the parts' MSMs, run as a software pipeline like the groups of an opening
+    std::vector<std::unique_ptr<MsmGroup<Fq>>> g1;
     // The opening ladder: slot i (= proof element i, open.rs:49) is the MSM over powers_of_h[i+1] (slice)
     // for i < nv - 1 and over {last base} for i = nv - 1.  The slots are spread over one or more groups, each one
     // pipeline (group k holds ladder slots [g2_first[k], g2_first[k+1])).
@@ -395,7 +398,19 @@ static std::vector<uint32_t> ladder_split(uint32_t nv) {
 static void pp_prepare(sb_ctx* c, sb_pp* pp, const G1Aff* g1_level0_dev, const std::vector<const G2Aff*>& g2_levels_dev /* index L, 1..nv-1 */,
                        const G2Aff& last_base) {
     const uint32_t nv = pp->nv;
-    if (g1_level0_dev) msm_group_prepare<Fq>({g1_level0_dev}, {(size_t)1 << nv}, pp->g1, c->stream);
+    if (g1_level0_dev) {
+        static const int parts_env = getenv("SB_MSM_G1_PARTS") ? atoi(getenv("SB_MSM_G1_PARTS")) : 2;
+        static const int min_nv = getenv("SB_MSM_SPLIT_MIN_NV") ? atoi(getenv("SB_MSM_SPLIT_MIN_NV")) : 12;
+        int lgp = 0;
+        while ((2 << lgp) <= std::min(std::max(parts_env, 1), (int)sb_ctx::NAUX) && (uint32_t)(lgp + 1) < nv) lgp++;
+        if ((int)nv < min_nv) lgp = 0;
+        const size_t parts = (size_t)1 << lgp, sz = ((size_t)1 << nv) >> lgp;
+        pp->g1.clear();
+        for (size_t k = 0; k < parts; k++) {
+            pp->g1.emplace_back(new MsmGroup<Fq>);
+            msm_group_prepare<Fq>({g1_level0_dev + k * sz}, {sz}, *pp->g1.back(), c->stream);
+        }
+    }
     DevBuf<G2Aff> hdev(1, c->stream);
     SB_CUDA(cudaMemcpyAsync(hdev.get(), &last_base, sizeof(G2Aff), cudaMemcpyHostToDevice, c->stream));
     pp->g2_first = ladder_split(nv);
@@ -533,19 +548,61 @@ static sb_pp* pp_keygen(sb_ctx* c, uint32_t nv, const void* g, const void* h, co
     return pp.release();
 }
 
+// ====================================================================== MSM groups as a software pipeline
+// Several independent MSM pipelines (the groups of an opening ladder, the parts of a commitment).  Each is front ->
+// accumulation -> tail.  The accumulations are throughput-bound and are chained one after another (each gets the whole
+// machine); the fronts run ahead on their group's stream; every tail -- ~2 ms of dependent point additions on a few
+// hundred CTAs whatever the size -- runs on a HIGH-PRIORITY stream beside the next group's accumulation, so that only the
+// last group's tail is exposed.  Everything is ordered by events; the host does not wait.  `ev_main` must have been
+// recorded on the main stream at the point the groups may start from; the main stream is joined to every tail.
+// alone: a single group runs on the main stream itself when main_too (nothing to overlap with).
+template <class F>
+static void msm_groups_run(sb_ctx* c, const std::vector<const MsmGroup<F>*>& gs, const std::vector<MsmScalarPtrs>& sps,
+                           const std::vector<XyzzPt<F>*>& outs, int first_aux, bool main_too) {
+    cudaStream_t st = c->stream;
+    const size_t ng = gs.size();
+    if (c->serial_msm || (ng == 1 && main_too)) {
+        for (size_t k = 0; k < ng; k++) msm_group_run<F>(*gs[k], sps[k], outs[k], st);
+        return;
+    }
+    int prev = -1;
+    for (size_t k = 0; k < ng; k++) {
+        const int a = (first_aux + (int)k) % sb_ctx::NAUX;
+        cudaStream_t s = c->aux[a], t = c->tail[a];
+        SB_CUDA(cudaStreamWaitEvent(s, c->ev_main, 0));
+        msm_group_front<F>(*gs[k], sps[k], s);
+        if (prev >= 0) SB_CUDA(cudaStreamWaitEvent(s, c->ev_acc[prev], 0));
+        msm_group_accum<F>(*gs[k], s);
+        SB_CUDA(cudaEventRecord(c->ev_acc[a], s));
+        SB_CUDA(cudaStreamWaitEvent(t, c->ev_acc[a], 0));
+        msm_group_tail<F>(*gs[k], outs[k], t);
+        SB_CUDA(cudaEventRecord(c->ev_done[a], t));
+        SB_CUDA(cudaStreamWaitEvent(st, c->ev_done[a], 0));
+        prev = a;
+    }
+}
+
 // ====================================================================== commitment ops on device tables
 // commit.rs:17-29.  Sharded: every rank sums its slice, the G partial sums are exchanged and added on the host.
 static G1Aff commit_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full) {
-    DevBuf<G1Xyzz> out(1, c->stream);
-    const size_t nl = (size_t)1 << pp->nv;
-    MsmScalarPtrs sp{};
-    sp.p[0] = z_dev_full + (size_t)c->rank * nl;
-    msm_group_run<Fq>(pp->g1, sp, out.get(), c->stream);
-    G1Xyzz mine; fetch_xyzz(c, out.get(), 1, &mine);
-    if (!c->sharded()) return xyzz_to_affine_host(mine);
+    const size_t nl = (size_t)1 << pp->nv, parts = pp->g1.size(), sz = nl / parts;
+    DevBuf<G1Xyzz> out(parts, c->stream);
+    std::vector<const MsmGroup<Fq>*> gs; std::vector<MsmScalarPtrs> sps(parts); std::vector<G1Xyzz*> outs;
+    for (size_t k = 0; k < parts; k++) {
+        gs.push_back(pp->g1[k].get());
+        sps[k].p[0] = z_dev_full + (size_t)c->rank * nl + k * sz;
+        outs.push_back(out.get() + k);
+    }
+    SB_CUDA(cudaEventRecord(c->ev_main, c->stream));
+    msm_groups_run<Fq>(c, gs, sps, outs, 0, true);
+    std::vector<G1Xyzz> mine(parts);
+    fetch_xyzz(c, out.get(), parts, mine.data());
+    G1Xyzz acc = mine[0];
+    for (size_t k = 1; k < parts; k++) acc = G1Xyzz::add(acc, mine[k]);
+    if (!c->sharded()) return xyzz_to_affine_host(acc);
     std::vector<G1Xyzz> all(c->world);
-    c->allgather(&mine, all.data(), sizeof(G1Xyzz));
-    G1Xyzz acc = all[0];
+    c->allgather(&acc, all.data(), sizeof(G1Xyzz));
+    acc = all[0];
     for (int r = 1; r < c->world; r++) acc = G1Xyzz::add(acc, all[r]);
     return xyzz_to_affine_host(acc);
 }
@@ -569,29 +626,17 @@ static void open_folds(sb_ctx* c, uint32_t nv, const Fr* table_dev, int point_sl
     SB_CUDA(cudaMemcpyAsync(c->d_mail.get() + out_slot, cur, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
 }
 // Stage 2 -- the nv MSMs of one parameter set: every group of the ladder is one pipeline, queued without any host
-// synchronisation.  Group 0 runs on the main stream, the others on auxiliary streams (first_aux, first_aux + 1, ..)
-// that wait for the folds and are joined to the main stream again.
+// synchronisation (see msm_groups_run).
 static void open_queue_msms(sb_ctx* c, const sb_pp* pp, const Fr* q, G2Xyzz* res_dev, int first_aux, bool main_too) {
-    cudaStream_t st = c->stream;
     const size_t ng = pp->g2.size();
-    SB_CUDA(cudaEventRecord(c->ev_main, st));      // the folds are queued: every group may start from here
+    std::vector<const MsmGroup<Fq2>*> gs; std::vector<MsmScalarPtrs> sps(ng); std::vector<G2Xyzz*> outs;
     for (size_t k = 0; k < ng; k++) {
-        MsmScalarPtrs sp{};
         const uint32_t i0 = pp->g2_first[k];
-        for (uint32_t i = i0; i < pp->g2_first[k + 1]; i++) sp.p[i - i0] = q + ((size_t)1 << (pp->nv - i - 1));
-        cudaStream_t s = st;
-        int a = -1;
-        if (!c->serial_msm && !(k == 0 && main_too)) {
-            a = (first_aux + (int)k - (main_too ? 1 : 0)) % sb_ctx::NAUX;
-            s = c->aux[a];
-            SB_CUDA(cudaStreamWaitEvent(s, c->ev_main, 0));
-        }
-        msm_group_run<Fq2>(*pp->g2[k], sp, res_dev + i0, s);
-        if (a >= 0) {
-            SB_CUDA(cudaEventRecord(c->ev_aux[a], s));
-            SB_CUDA(cudaStreamWaitEvent(st, c->ev_aux[a], 0));
-        }
+        for (uint32_t i = i0; i < pp->g2_first[k + 1]; i++) sps[k].p[i - i0] = q + ((size_t)1 << (pp->nv - i - 1));
+        gs.push_back(pp->g2[k].get()); outs.push_back(res_dev + i0);
     }
+    SB_CUDA(cudaEventRecord(c->ev_main, c->stream));      // the folds are queued: every group may start from here
+    msm_groups_run<Fq2>(c, gs, sps, outs, first_aux, main_too);
 }
 
 // Full opening of the nv_total-variable polynomial z at `point`.  Sharded: each rank folds its slice over the
@@ -929,9 +974,13 @@ sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
         c->d_mail.alloc(sb_ctx::MAIL, c->stream);
         c->h_mail.alloc(sb_ctx::MAIL);
         c->round_out.alloc(4); c->round_flag.alloc(16);
+        int prio_least = 0, prio_greatest = 0;
+        SB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
         for (int i = 0; i < sb_ctx::NAUX; i++) {
-            SB_CUDA(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
-            SB_CUDA(cudaEventCreateWithFlags(&c->ev_aux[i], cudaEventDisableTiming));
+            SB_CUDA(cudaStreamCreateWithPriority(&c->aux[i], cudaStreamNonBlocking, prio_least));
+            SB_CUDA(cudaStreamCreateWithPriority(&c->tail[i], cudaStreamNonBlocking, prio_greatest));
+            SB_CUDA(cudaEventCreateWithFlags(&c->ev_acc[i], cudaEventDisableTiming));
+            SB_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
         }
         SB_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
         SB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -960,7 +1009,9 @@ void sb_ctx_destroy(sb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < sb_ctx::NAUX; i++) {
         if (c->aux[i]) { cudaStreamSynchronize(c->aux[i]); cudaStreamDestroy(c->aux[i]); }
-        if (c->ev_aux[i]) cudaEventDestroy(c->ev_aux[i]);
+        if (c->tail[i]) { cudaStreamSynchronize(c->tail[i]); cudaStreamDestroy(c->tail[i]); }
+        if (c->ev_acc[i]) cudaEventDestroy(c->ev_acc[i]);
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
     }
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
