@@ -158,6 +158,9 @@ typedef struct {
     double phase_ms[16];                   /* device+host time per phase, see sb_phase_name */
 } sb_trace;
 const char* sb_phase_name(int i);          /* NULL past the last phase */
+/* the reference's own timer span for phase i ("Prove 1" ... "Prove Sumcheck 2", src/lib.rs:71-135); sb_prove wraps each
+ * phase in an NVTX range of that name */
+const char* sb_phase_span(int i);
 /* Serialized Proof (src/data_structures/proof.rs:11-20, CanonicalSerialize, compressed points).
  * *len: in = capacity of `proof`, out = bytes written (or needed, with SB_EINVAL, if too small). */
 sb_status sb_prove(sb_ctx* ctx, const sb_index* idx, const sb_pp* pp, const void* v, size_t nv_len, const void* w, size_t nw_len,

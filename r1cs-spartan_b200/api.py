@@ -28,7 +28,7 @@ EXPORTS = [
     "sb_pp_destroy", "sb_commit", "sb_open", "sb_msm", "sb_eq_table", "sb_sum_over_y", "sb_eval_on_x",
     "sb_prover_init", "sb_prover_destroy", "sb_prover_first_round", "sb_prover_second_round", "sb_prover_third_round",
     "sb_prover_first_sumcheck_round", "sb_prover_fourth_round", "sb_prover_fifth_round",
-    "sb_prover_second_sumcheck_round", "sb_prover_sixth_round", "sb_prover_export_abc", "sb_phase_name", "sb_prove",
+    "sb_prover_second_sumcheck_round", "sb_prover_sixth_round", "sb_prover_export_abc", "sb_phase_name", "sb_phase_span", "sb_prove",
     "sb_proof_size", "sb_field_binop", "sb_mul_bench", "sb_kernel_bench",
     "sb_witness_upload", "sb_witness_destroy", "sb_prove_resident", "sb_copy_counters", "sb_prof_enable", "sb_prof_report",
     "sb_set_serial_msm", "sb_prof_timeline", "sb_comm_shm_open", "sb_comm_shm_close", "sb_comm_local_open",

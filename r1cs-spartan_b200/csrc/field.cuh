@@ -198,27 +198,44 @@ struct alignas(16) Fp {
         u[0] = 1;
         // invariants: a = u * x, b = v * x (mod p), as plain integers (x is whatever residue the caller holds)
         for (int round = 0; round < (2 * 32 * N - 1 + K - 1) / K; round++) {
-            // 64-bit approximations: the low 31 bits and the top 33 bits of the n-bit window, n = max(len a, len b, 64)
-            int top = N - 1;
-            while (top > 1 && (a[top] | b[top]) == 0) top--;
-            uint64_t abar = ((uint64_t)a[top] << 32) | a[top - 1], bbar = ((uint64_t)b[top] << 32) | b[top - 1];
-            if (top > 1) {                                               // (top == 1: both values are below 2^64, the approximation is exact)
-                uint32_t hi = a[top] | b[top];
+            // 64-bit approximations: the low 31 bits and the top 33 bits of the n-bit window, n = max(len a, len b, 64).
+            // The three limbs at the top of the longer value are picked with a fixed, fully unrolled scan (no dynamic
+            // indexing: the limb arrays stay in registers) and every step below is branch-free (the lanes of a warp
+            // invert different values: data-dependent branches would serialise them).
+            uint32_t ah = a[N - 1], am = a[N - 2], al = a[N - 3], bh = b[N - 1], bm = b[N - 2], bl = b[N - 3];
+#pragma unroll
+            for (int i = N - 2; i >= 2; i--) {
+                const bool empty = (ah | bh) == 0;                       // nothing found above limb i yet: slide the window down
+                ah = empty ? a[i] : ah; am = empty ? a[i - 1] : am; al = empty ? a[i - 2] : al;
+                bh = empty ? b[i] : bh; bm = empty ? b[i - 1] : bm; bl = empty ? b[i - 2] : bl;
+            }
+            uint64_t abar, bbar;
+            {
+                const uint32_t hi = ah | bh;
+                const bool exact = hi == 0;                             // both values below 2^64: (am, al) = limbs (1, 0) are the values themselves
                 int lz = 0;
-                while (!(hi & 0x80000000u)) { hi <<= 1; lz++; }
-                if (lz) {
-                    abar = (abar << lz) | ((uint64_t)a[top - 2] >> (32 - lz));
-                    bbar = (bbar << lz) | ((uint64_t)b[top - 2] >> (32 - lz));
-                }
-                abar = ((abar >> 31) << 31) | (a[0] & 0x7fffffffu);
-                bbar = ((bbar >> 31) << 31) | (b[0] & 0x7fffffffu);
+#if defined(__CUDA_ARCH__)
+                lz = exact ? 0 : __clz((int)hi);
+#else
+                if (!exact) lz = __builtin_clz(hi);
+#endif
+                // top 64 bits of the window (ah, am, al) << lz, then keep its upper 33 bits
+                uint64_t wa = ((uint64_t)ah << 32) | am, wb = ((uint64_t)bh << 32) | bm;
+                wa = lz ? (wa << lz) | ((uint64_t)al >> (32 - lz)) : wa;
+                wb = lz ? (wb << lz) | ((uint64_t)bl >> (32 - lz)) : wb;
+                const uint64_t xa = ((wa >> 31) << 31) | (a[0] & 0x7fffffffu), xb = ((wb >> 31) << 31) | (b[0] & 0x7fffffffu);
+                const uint64_t ea = ((uint64_t)am << 32) | al, eb = ((uint64_t)bm << 32) | bl;
+                abar = exact ? ea : xa; bbar = exact ? eb : xb;
             }
             int64_t f0 = 1, g0 = 0, f1 = 0, g1 = 1;
+#pragma unroll 1
             for (int j = 0; j < K; j++) {
-                const bool odd = abar & 1;
-                const bool sw = odd && abar < bbar;
-                if (sw) { uint64_t t = abar; abar = bbar; bbar = t; int64_t s = f0; f0 = f1; f1 = s; s = g0; g0 = g1; g1 = s; }
-                if (odd) { abar -= bbar; f0 -= f1; g0 -= g1; }
+                const uint64_t odd = (uint64_t)0 - (abar & 1);                          // all ones when a is odd
+                const uint64_t sw = odd & ((uint64_t)0 - (uint64_t)(abar < bbar));       // ... and smaller than b: swap first
+                uint64_t x = (abar ^ bbar) & sw; abar ^= x; bbar ^= x;
+                x = (uint64_t)(f0 ^ f1) & sw; f0 ^= (int64_t)x; f1 ^= (int64_t)x;
+                x = (uint64_t)(g0 ^ g1) & sw; g0 ^= (int64_t)x; g1 ^= (int64_t)x;
+                abar -= bbar & odd; f0 -= f1 & (int64_t)odd; g0 -= g1 & (int64_t)odd;
                 abar >>= 1; f1 <<= 1; g1 <<= 1;
             }
             // (a, b) <- ((a f0 + b g0) / 2^31, (a f1 + b g1) / 2^31), exact; a negative result is negated together with its row

@@ -348,6 +348,14 @@ __global__ void __launch_bounds__(256) k_open_fold(const Fr* __restrict__ in, Fr
         st_elem(&r_out[b], Fr::add(x0, Fr::mul(p, q)));
     }
 }
+// q[b] = in[2b+1] - in[2b]: the first quotient of an opening (open.rs:42 at i = 0), which does not depend on the point
+__global__ void __launch_bounds__(256) k_pair_diff(const Fr* __restrict__ in, Fr* __restrict__ q_out, size_t half) {
+    for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < half; b += (size_t)gridDim.x * blockDim.x)
+        st_elem(&q_out[b], Fr::sub(ldg_elem(&in[2 * b + 1]), ldg_elem(&in[2 * b])));
+}
+void launch_pair_diff(const Fr* in, Fr* q_out, size_t half, cudaStream_t stream) {
+    SB_LAUNCH(k_pair_diff, grid_for(half, 256, 8), 256, 0, stream, in, q_out, half);
+}
 void launch_open_fold(const Fr* in, Fr* r_out, Fr* q_out, const Fr* p_dev, size_t half, cudaStream_t stream) {
     SB_LAUNCH(k_open_fold, grid_for(half, 256, 8), 256, 0, stream, in, r_out, q_out, p_dev, half);
 }

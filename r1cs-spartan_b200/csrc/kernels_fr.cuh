@@ -57,6 +57,8 @@ void launch_sc2_round(const Fr* M, const Fr* Z, Fr* Mo, Fr* Zo, const Fr* r_host
 void launch_final_fold3(const Fr* A, const Fr* B, const Fr* C, int ntab, const Fr* r_host, const RoundOut& o, cudaStream_t stream);
 // open.rs:42-45: q[b] = in[2b+1] - in[2b]; r_out[b] = in[2b] + p (in[2b+1] - in[2b])
 void launch_open_fold(const Fr* in, Fr* r_out, Fr* q_out, const Fr* p_dev, size_t half, cudaStream_t stream);
+// q[b] = in[2b+1] - in[2b] alone (the quotient of the first opening round is independent of the point)
+void launch_pair_diff(const Fr* in, Fr* q_out, size_t half, cudaStream_t stream);
 // elementwise self-test helpers: out = a (op) b with the PTX path; op 0 add, 1 sub, 2 mul, 3 mul_portable
 void launch_fr_binop(int op, const Fr* a, const Fr* b, Fr* out, size_t n, cudaStream_t stream);
 void launch_fq_binop(int op, const Fq* a, const Fq* b, Fq* out, size_t n, cudaStream_t stream);

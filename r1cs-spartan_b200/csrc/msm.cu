@@ -401,9 +401,12 @@ __device__ __forceinline__ int pair_classify_x(const F& px, const F& qx, bool ha
     return PAIR_ADD;
 }
 
-// The outputs of a round are dealt to the threads in equal contiguous shares (per = ceil(total / nthreads) <= K).  A
-// share may span several buckets: the loops run bucket by bucket, so that inside a bucket the input of output j is
-// simply elements 2j, 2j+1 of the bucket's run -- no lookup, no dependent index loads in the inner loop.
+// The outputs of a round are dealt out warp by warp: a warp owns 32 * per consecutive outputs (per = ceil(total /
+// nthreads) <= K) and lane l takes outputs base + l, base + l + 32, ...: in every iteration the 32 lanes work on 32
+// CONSECUTIVE outputs -- the same bucket or two neighbouring ones, so the bucket tracking is (almost) uniform across the
+// warp, the entry indices and the results are read and written as contiguous runs, and every lane runs the same number
+// of iterations (a first version with per-thread contiguous shares and bucket-by-bucket loops had 17.9 of 32 lanes
+// active: ncu, profiles/r02_ncu_affine_round_v1.txt).
 template <class F, bool FIRST>
 __global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
                                                               const AffinePt<F>* __restrict__ in_aff, const uint32_t* __restrict__ in_off,
@@ -412,10 +415,14 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>*
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = out_off[B];
     const uint32_t per = (total + nthreads - 1) / nthreads;
-    const uint64_t p0l = (uint64_t)t * per;
-    if (t >= nthreads || per == 0 || p0l >= total) return;
-    const uint32_t p0 = (uint32_t)p0l, p1 = min(p0 + per, total);
     (void)K;
+    if (t >= nthreads || per == 0) return;
+    const uint64_t first64 = (uint64_t)(t & ~31u) * per + (t & 31u);      // this lane's first output
+    if (first64 >= total) return;
+    const uint32_t first = (uint32_t)first64;
+    // iterations of this lane: outputs first + 32 i < min(warp's end, total)
+    const uint64_t wend = min((uint64_t)((t & ~31u) + 32) * per, (uint64_t)total);
+    const uint32_t iters = (uint32_t)((wend - first + 31) / 32);
     // element `idx` of the input list: its address (first round: through the sorted entry, with the sign of the digit)
     auto in_ptr = [&](uint32_t idx, bool& negate) -> const AffinePt<F>* {
         if (FIRST) {
@@ -426,70 +433,60 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>*
         negate = false;
         return &in_aff[idx];
     };
-    auto load_full = [&](uint32_t idx) -> AffinePt<F> {
-        bool neg;
-        const AffinePt<F>* ptr = in_ptr(idx, neg);
-        AffinePt<F> q = ldg_elem(ptr);
-        if (neg) q.y = F::neg(q.y);
-        return q;
-    };
-    uint32_t lo = 0, hi = B;                    // bucket of p0: last b with out_off[b] <= p0
+    uint32_t lo = 0, hi = B;                    // bucket of the first output: last b with out_off[b] <= first
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(&out_off[mid]) <= p0) lo = mid; else hi = mid;
+        if (__ldg(&out_off[mid]) <= first) lo = mid; else hi = mid;
     }
-    const uint32_t b_first = lo;
     // pass 1: prefix products of the denominators (x coordinates only)
     F acc = F::one();
-    uint32_t b = b_first, p = p0;
-    while (p < p1) {
-        const uint32_t ob = __ldg(&out_off[b]), ob1 = __ldg(&out_off[b + 1]);
+    uint32_t b = lo;
+    for (uint32_t i = 0; i < iters; i++) {
+        const uint32_t p = first + 32 * i;
+        while (__ldg(&out_off[b + 1]) <= p) b++;
+        const uint32_t j = p - __ldg(&out_off[b]);
         const uint32_t ib = __ldg(&in_off[b]), n_in = __ldg(&in_off[b + 1]) - ib;
-        const uint32_t jend = min(ob1, p1) - ob;
-        for (uint32_t j = p - ob; j < jend; j++, p++) {
-            const bool has2 = 2 * j + 1 < n_in;
-            bool n0, n1 = false;
-            const AffinePt<F>* pp0 = in_ptr(ib + 2 * j, n0);
-            const AffinePt<F>* pp1 = has2 ? in_ptr(ib + 2 * j + 1, n1) : pp0;
-            const F px = ldg_elem(&pp0->x), qx = has2 ? ldg_elem(&pp1->x) : px;
-            F d;
-            pair_classify_x(px, qx, has2, [&](int k) { F y = ldg_elem(k ? &pp1->y : &pp0->y); return (k ? n1 : n0) ? F::neg(y) : y; }, d);
-            st_elem(&prefix[(size_t)(p - p0) * nthreads + t], acc);
-            acc = F::mul(acc, d);
-        }
-        b++;
+        const bool has2 = 2 * j + 1 < n_in;
+        bool n0, n1 = false;
+        const AffinePt<F>* pp0 = in_ptr(ib + 2 * j, n0);
+        const AffinePt<F>* pp1 = has2 ? in_ptr(ib + 2 * j + 1, n1) : pp0;
+        const F px = ldg_elem(&pp0->x), qx = has2 ? ldg_elem(&pp1->x) : px;
+        F d;
+        pair_classify_x(px, qx, has2, [&](int k) { F y = ldg_elem(k ? &pp1->y : &pp0->y); return (k ? n1 : n0) ? F::neg(y) : y; }, d);
+        st_elem(&prefix[(size_t)i * nthreads + t], acc);
+        acc = F::mul(acc, d);
     }
     F inv = F::inv_fast(acc);
     // pass 2, backwards: 1/d_k = inv * prefix_k, then inv *= d_k
-    b--;
-    p = p1;
-    while (p > p0) {
-        const uint32_t ob = __ldg(&out_off[b]), ob1 = __ldg(&out_off[b + 1]);
+    for (uint32_t i = iters; i-- > 0;) {
+        const uint32_t p = first + 32 * i;
+        while (__ldg(&out_off[b]) > p) b--;
+        const uint32_t j = p - __ldg(&out_off[b]);
         const uint32_t ib = __ldg(&in_off[b]), n_in = __ldg(&in_off[b + 1]) - ib;
-        const uint32_t jbeg = max(ob, p0) - ob;
-        for (uint32_t j = min(ob1, p1) - ob; j-- > jbeg;) {
-            p--;
-            const bool has2 = 2 * j + 1 < n_in;
-            const AffinePt<F> P = load_full(ib + 2 * j), Q = has2 ? load_full(ib + 2 * j + 1) : P;
-            F d;
-            const int kind = pair_classify_x(P.x, Q.x, has2, [&](int k) { return k ? Q.y : P.y; }, d);
-            const F dinv = F::mul(inv, ldg_elem(&prefix[(size_t)(p - p0) * nthreads + t]));
-            inv = F::mul(inv, d);
-            AffinePt<F> r;
-            if (kind == PAIR_COPY_P) r = P;
-            else if (kind == PAIR_COPY_Q) r = Q;
-            else if (kind == PAIR_INF) r = AffinePt<F>::inf();
-            else {
-                F lam;
-                if (kind == PAIR_ADD) lam = F::mul(F::sub(Q.y, P.y), dinv);
-                else { F xx = F::sqr(P.x); lam = F::mul(F::add(F::dbl(xx), xx), dinv); }
-                r.x = F::sub(F::sub(F::sqr(lam), P.x), Q.x);
-                r.y = F::sub(F::mul(lam, F::sub(P.x, r.x)), P.y);
-            }
-            st_elem(&out_aff[p], r);
+        const bool has2 = 2 * j + 1 < n_in;
+        bool n0, n1 = false;
+        const AffinePt<F>* pp0 = in_ptr(ib + 2 * j, n0);
+        const AffinePt<F>* pp1 = has2 ? in_ptr(ib + 2 * j + 1, n1) : pp0;
+        AffinePt<F> P = ldg_elem(pp0), Q = has2 ? ldg_elem(pp1) : P;
+        if (n0) P.y = F::neg(P.y);
+        if (has2 && n1) Q.y = F::neg(Q.y);
+        if (!has2) Q = P;
+        F d;
+        const int kind = pair_classify_x(P.x, Q.x, has2, [&](int k) { return k ? Q.y : P.y; }, d);
+        const F dinv = F::mul(inv, ldg_elem(&prefix[(size_t)i * nthreads + t]));
+        inv = F::mul(inv, d);
+        AffinePt<F> r;
+        if (kind == PAIR_COPY_P) r = P;
+        else if (kind == PAIR_COPY_Q) r = Q;
+        else if (kind == PAIR_INF) r = AffinePt<F>::inf();
+        else {
+            F lam;
+            if (kind == PAIR_ADD) lam = F::mul(F::sub(Q.y, P.y), dinv);
+            else { F xx = F::sqr(P.x); lam = F::mul(F::add(F::dbl(xx), xx), dinv); }
+            r.x = F::sub(F::sub(F::sqr(lam), P.x), Q.x);
+            r.y = F::sub(F::mul(lam, F::sub(P.x, r.x)), P.y);
         }
-        if (b == 0) break;
-        b--;
+        st_elem(&out_aff[p], r);
     }
 }
 
@@ -689,7 +686,7 @@ void msm_group_prepare(const std::vector<const AffinePt<F>*>& bases_dev, const s
             const uint64_t resident = (uint64_t)SB_SMS * 4 * AFF_THREADS;  // threads one wave of the round kernel holds
             uint64_t k = (bound + resident - 1) / resident;
             k = std::min<uint64_t>(std::max<uint64_t>(k, std::min<uint32_t>(8, msm_affine_kmax())), msm_affine_kmax());
-            out.round_bound[r] = (uint32_t)bound; out.round_k[r] = (uint32_t)k; out.round_threads[r] = (uint32_t)((bound + k - 1) / k);
+            out.round_bound[r] = (uint32_t)bound; out.round_k[r] = (uint32_t)k; out.round_threads[r] = (uint32_t)(((bound + k - 1) / k + 31) / 32 * 32);   // whole warps (see k_affine_round)
         }
     }
     out.slots_dev.alloc(J, stream);

@@ -17,6 +17,14 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#if !defined(SB_EMUL)
+#include <nvtx3/nvToolsExt.h>       // header-only; the ranges cost nothing unless a profiler is attached
+#define SB_SPAN_PUSH(name) nvtxRangePushA(name)
+#define SB_SPAN_POP() nvtxRangePop()
+#else
+#define SB_SPAN_PUSH(name) ((void)0)
+#define SB_SPAN_POP() ((void)0)
+#endif
 
 using sbhost::Bytes;
 
@@ -46,6 +54,8 @@ struct sb_ctx {
     cudaStream_t aux[NAUX] = {};       // front + accumulation of group k
     cudaStream_t tail[NAUX] = {};      // high priority: the latency-bound tail of group k (later levels, bucket reduction)
     cudaEvent_t ev_main = nullptr, ev_acc[NAUX] = {}, ev_done[NAUX] = {};
+    int next_aux = 0;                  // groups take the auxiliary streams in rotation
+    int chain_prev = -1;               // stream index of the last queued accumulation: the next one is chained behind it
     cudaStream_t copy_stream = nullptr; // witness upload that overlaps the commitment (sharded sb_prove)
     cudaEvent_t ev_copy = nullptr;
     bool serial_msm = false;           // profiling aid: keep every MSM group on the main stream
@@ -147,6 +157,16 @@ struct sb_prover {
     DevBuf<Fr> x3;            // r_k * eq(r_x, .), 3n (replicated)
     DevBuf<Fr> mtab;          // local slice of M(y), nl
     DevBuf<Fr> open_r0, open_r1, open_q;
+    // the first element of an opening proof, MSM(powers_of_h[1], z_odd - z_even), does not depend on the
+    // opening point, so the two openings of a proof share it: computed once (queued next to the commitment), used twice
+    struct Pi0 {
+        bool queued = false, ready = false;
+        DevBuf<Fr> q0;
+        DevBuf<G2Xyzz> out;
+        cudaEvent_t done = nullptr;
+        G2Xyzz host;
+        ~Pi0() { if (done) { if (queued && !ready) cudaEventSynchronize(done); cudaEventDestroy(done); } }   // never free under a running pipeline
+    } pi0;
     // tail instance over the top glog variables (sharded only): gathered tables, pyramid, fold buffers
     DevBuf<Fr> tail_tabs, tail_pyr, tail_ping, tail_pong;
     bool in_tail = false;
@@ -399,7 +419,7 @@ static void pp_prepare(sb_ctx* c, sb_pp* pp, const G1Aff* g1_level0_dev, const s
                        const G2Aff& last_base) {
     const uint32_t nv = pp->nv;
     if (g1_level0_dev) {
-        static const int parts_env = getenv("SB_MSM_G1_PARTS") ? atoi(getenv("SB_MSM_G1_PARTS")) : 2;
+        static const int parts_env = getenv("SB_MSM_G1_PARTS") ? atoi(getenv("SB_MSM_G1_PARTS")) : 1;   // (2 and 4 measured slower)
         static const int min_nv = getenv("SB_MSM_SPLIT_MIN_NV") ? atoi(getenv("SB_MSM_SPLIT_MIN_NV")) : 12;
         int lgp = 0;
         while ((2 << lgp) <= std::min(std::max(parts_env, 1), (int)sb_ctx::NAUX) && (uint32_t)(lgp + 1) < nv) lgp++;
@@ -548,43 +568,56 @@ static sb_pp* pp_keygen(sb_ctx* c, uint32_t nv, const void* g, const void* h, co
     return pp.release();
 }
 
-// ====================================================================== MSM groups as a software pipeline
-// Several independent MSM pipelines (the groups of an opening ladder, the parts of a commitment).  Each is front ->
-// accumulation -> tail.  The accumulations are throughput-bound and are chained one after another (each gets the whole
-// machine); the fronts run ahead on their group's stream; every tail -- ~2 ms of dependent point additions on a few
-// hundred CTAs whatever the size -- runs on a HIGH-PRIORITY stream beside the next group's accumulation, so that only the
-// last group's tail is exposed.  Everything is ordered by events; the host does not wait.  `ev_main` must have been
-// recorded on the main stream at the point the groups may start from; the main stream is joined to every tail.
-// alone: a single group runs on the main stream itself when main_too (nothing to overlap with).
+// ====================================================================== several MSM groups at once
+// Several independent MSM pipelines (the groups of an opening ladder, the shared first proof element, the parts of a
+// commitment) are queued on one auxiliary stream each and run concurrently; the host does not wait.  `ev_main` must
+// have been recorded on the main stream at the point the groups may start from; the main stream is joined to every group
+// unless `done_instead_of_join` asks for an event instead (the caller joins later).  A single group runs on the main
+// stream itself when main_too.
+// Two scheduling experiments, both measured SLOWER on B200 at 2^20 and 2^17 and therefore off (round 2, gpurun sweep 4):
+//   SB_MSM_CHAIN=1      chain the throughput-bound accumulations one after another by events (each gets the whole machine)
+//   SB_MSM_TAIL_PRIO=1  run every group's latency-bound tail on a high-priority stream beside the next accumulation
+// (the machine drains at every chain link, and the tails' 2-warp CTAs take SM slots from the accumulations: 62.6 against
+// 58.7 ms at 2^20).
 template <class F>
 static void msm_groups_run(sb_ctx* c, const std::vector<const MsmGroup<F>*>& gs, const std::vector<MsmScalarPtrs>& sps,
-                           const std::vector<XyzzPt<F>*>& outs, int first_aux, bool main_too) {
+                           const std::vector<XyzzPt<F>*>& outs, bool main_too, cudaEvent_t done_instead_of_join = nullptr) {
     cudaStream_t st = c->stream;
     const size_t ng = gs.size();
     if (c->serial_msm || (ng == 1 && main_too)) {
         for (size_t k = 0; k < ng; k++) msm_group_run<F>(*gs[k], sps[k], outs[k], st);
+        if (done_instead_of_join) SB_CUDA(cudaEventRecord(done_instead_of_join, st));
         return;
     }
-    int prev = -1;
+    static const bool chain = getenv("SB_MSM_CHAIN") && atoi(getenv("SB_MSM_CHAIN")) != 0;
+    static const bool tail_prio = getenv("SB_MSM_TAIL_PRIO") && atoi(getenv("SB_MSM_TAIL_PRIO")) != 0;
     for (size_t k = 0; k < ng; k++) {
-        const int a = (first_aux + (int)k) % sb_ctx::NAUX;
-        cudaStream_t s = c->aux[a], t = c->tail[a];
+        const int a = c->next_aux;
+        c->next_aux = (c->next_aux + 1) % sb_ctx::NAUX;
+        cudaStream_t s = c->aux[a], t = tail_prio ? c->tail[a] : s;
         SB_CUDA(cudaStreamWaitEvent(s, c->ev_main, 0));
         msm_group_front<F>(*gs[k], sps[k], s);
-        if (prev >= 0) SB_CUDA(cudaStreamWaitEvent(s, c->ev_acc[prev], 0));
+        if (chain && c->chain_prev >= 0) SB_CUDA(cudaStreamWaitEvent(s, c->ev_acc[c->chain_prev], 0));
         msm_group_accum<F>(*gs[k], s);
-        SB_CUDA(cudaEventRecord(c->ev_acc[a], s));
-        SB_CUDA(cudaStreamWaitEvent(t, c->ev_acc[a], 0));
+        if (chain || tail_prio) {
+            SB_CUDA(cudaEventRecord(c->ev_acc[a], s));
+            c->chain_prev = a;
+            if (tail_prio) SB_CUDA(cudaStreamWaitEvent(t, c->ev_acc[a], 0));
+        }
         msm_group_tail<F>(*gs[k], outs[k], t);
-        SB_CUDA(cudaEventRecord(c->ev_done[a], t));
-        SB_CUDA(cudaStreamWaitEvent(st, c->ev_done[a], 0));
-        prev = a;
+        if (done_instead_of_join && k + 1 == ng) SB_CUDA(cudaEventRecord(done_instead_of_join, t));
+        else {
+            SB_CUDA(cudaEventRecord(c->ev_done[a], t));
+            SB_CUDA(cudaStreamWaitEvent(st, c->ev_done[a], 0));
+        }
     }
 }
 
 // ====================================================================== commitment ops on device tables
 // commit.rs:17-29.  Sharded: every rank sums its slice, the G partial sums are exchanged and added on the host.
-static G1Aff commit_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full) {
+static bool pi0_prepare(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full, sb_prover::Pi0& pi0);
+static void pi0_launch(sb_ctx* c, const sb_pp* pp, sb_prover::Pi0& pi0);
+static G1Aff commit_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full, sb_prover::Pi0* pi0 = nullptr) {
     const size_t nl = (size_t)1 << pp->nv, parts = pp->g1.size(), sz = nl / parts;
     DevBuf<G1Xyzz> out(parts, c->stream);
     std::vector<const MsmGroup<Fq>*> gs; std::vector<MsmScalarPtrs> sps(parts); std::vector<G1Xyzz*> outs;
@@ -593,8 +626,10 @@ static G1Aff commit_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full) {
         sps[k].p[0] = z_dev_full + (size_t)c->rank * nl + k * sz;
         outs.push_back(out.get() + k);
     }
+    const bool with_pi0 = pi0 && pi0_prepare(c, pp, z_dev_full, *pi0);
     SB_CUDA(cudaEventRecord(c->ev_main, c->stream));
-    msm_groups_run<Fq>(c, gs, sps, outs, 0, true);
+    msm_groups_run<Fq>(c, gs, sps, outs, true);
+    if (with_pi0) pi0_launch(c, pp, *pi0);
     std::vector<G1Xyzz> mine(parts);
     fetch_xyzz(c, out.get(), parts, mine.data());
     G1Xyzz acc = mine[0];
@@ -627,16 +662,39 @@ static void open_folds(sb_ctx* c, uint32_t nv, const Fr* table_dev, int point_sl
 }
 // Stage 2 -- the nv MSMs of one parameter set: every group of the ladder is one pipeline, queued without any host
 // synchronisation (see msm_groups_run).
-static void open_queue_msms(sb_ctx* c, const sb_pp* pp, const Fr* q, G2Xyzz* res_dev, int first_aux, bool main_too) {
+static void open_queue_msms(sb_ctx* c, const sb_pp* pp, const Fr* q, G2Xyzz* res_dev, bool main_too, bool skip_first_group) {
     const size_t ng = pp->g2.size();
-    std::vector<const MsmGroup<Fq2>*> gs; std::vector<MsmScalarPtrs> sps(ng); std::vector<G2Xyzz*> outs;
-    for (size_t k = 0; k < ng; k++) {
+    std::vector<const MsmGroup<Fq2>*> gs; std::vector<MsmScalarPtrs> sps; std::vector<G2Xyzz*> outs;
+    for (size_t k = skip_first_group ? 1 : 0; k < ng; k++) {
         const uint32_t i0 = pp->g2_first[k];
-        for (uint32_t i = i0; i < pp->g2_first[k + 1]; i++) sps[k].p[i - i0] = q + ((size_t)1 << (pp->nv - i - 1));
-        gs.push_back(pp->g2[k].get()); outs.push_back(res_dev + i0);
+        MsmScalarPtrs sp{};
+        for (uint32_t i = i0; i < pp->g2_first[k + 1]; i++) sp.p[i - i0] = q + ((size_t)1 << (pp->nv - i - 1));
+        gs.push_back(pp->g2[k].get()); sps.push_back(sp); outs.push_back(res_dev + i0);
     }
     SB_CUDA(cudaEventRecord(c->ev_main, c->stream));      // the folds are queued: every group may start from here
-    msm_groups_run<Fq2>(c, gs, sps, outs, first_aux, main_too);
+    if (!gs.empty()) msm_groups_run<Fq2>(c, gs, sps, outs, main_too);
+}
+// the ladder keeps its first slot in a group of its own (ladder_split with at least two groups): the shared first proof
+// element can then be computed apart from the rest
+static bool pi0_layout(const sb_pp* pp) { return pp->g2.size() >= 2 && pp->g2_first[1] == 1; }
+// MSM(powers_of_h[1] slice, z_odd - z_even), queued beside whatever else is running; nothing waits for it until an opening
+// needs it (open_dev).  Two steps, because the quotient is computed on the main stream and must be queued there BEFORE the
+// event the groups start from is recorded (and before the main stream is joined to anything):
+//   pi0_prepare: buffers + the quotient on the main stream;  pi0_launch: the pipeline, after `ev_main` has been recorded.
+static bool pi0_prepare(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full, sb_prover::Pi0& pi0) {
+    if (pi0.queued || pi0.ready || !pi0_layout(pp)) return false;
+    const size_t nl = (size_t)1 << pp->nv;
+    cudaStream_t st = c->stream;
+    if (pi0.q0.n < nl / 2) pi0.q0.alloc(nl / 2, st);
+    if (pi0.out.n < 1) pi0.out.alloc(1, st);
+    if (!pi0.done) SB_CUDA(cudaEventCreateWithFlags(&pi0.done, cudaEventDisableTiming));
+    launch_pair_diff(z_dev_full + (size_t)c->rank * nl, pi0.q0.get(), nl / 2, st);
+    return true;
+}
+static void pi0_launch(sb_ctx* c, const sb_pp* pp, sb_prover::Pi0& pi0) {
+    MsmScalarPtrs sp{}; sp.p[0] = pi0.q0.get();
+    msm_groups_run<Fq2>(c, {pp->g2[0].get()}, {sp}, {pi0.out.get()}, false, pi0.done);
+    pi0.queued = true;
 }
 
 // Full opening of the nv_total-variable polynomial z at `point`.  Sharded: each rank folds its slice over the
@@ -645,7 +703,7 @@ static void open_queue_msms(sb_ctx* c, const sb_pp* pp, const Fr* q, G2Xyzz* res
 // rank's slice of the parameters) and of the tail levels are queued together; finally the per-level partial sums
 // of the local levels are exchanged and added on the host.
 static void open_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full, const Fr* point_host, Fr* eval_out, G2Aff* proofs_out,
-                     DevBuf<Fr>& r0, DevBuf<Fr>& r1, DevBuf<Fr>& q) {
+                     DevBuf<Fr>& r0, DevBuf<Fr>& r1, DevBuf<Fr>& q, sb_prover::Pi0* pi0 = nullptr) {
     const uint32_t loc = pp->nv, total = pp->nv_total, g = total - loc;
     const size_t nl = (size_t)1 << loc;
     const int G = c->world;
@@ -657,7 +715,8 @@ static void open_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full, const Fr*
     open_folds(c, loc, z_dev_full + (size_t)c->rank * nl, sb_ctx::SLOT_VEC2, r0, r1, q, sb_ctx::SLOT_OUT);
     // sharded: the local pipelines go to auxiliary streams at once, so that the main stream is free for the exchange of
     // the folded values and the (tiny) tail opening, which then overlap them
-    open_queue_msms(c, pp, q.get(), res.get(), 0, !c->sharded());
+    const bool shared0 = pi0 && (pi0->queued || pi0->ready);      // the first proof element comes from the cache (D6)
+    open_queue_msms(c, pp, q.get(), res.get(), !c->sharded(), shared0);
     if (c->sharded()) {
         Fr folded; d2h_fr(c, sb_ctx::SLOT_OUT, &folded, 1);
         std::vector<Fr> tail_tab(G);
@@ -667,11 +726,18 @@ static void open_dev(sb_ctx* c, const sb_pp* pp, const Fr* z_dev_full, const Fr*
         g_sb_h2d_bytes += G * sizeof(Fr);
         open_folds(c, g, tt.get(), sb_ctx::SLOT_VEC2 + loc, t0, t1, tq, sb_ctx::SLOT_OUT);
         ctx_sync(c);                                // tail_tab (host) is read by the async copy above
-        open_queue_msms(c, pp->tail.get(), tq.get(), res.get() + loc, (int)pp->g2.size(), true);
+        open_queue_msms(c, pp->tail.get(), tq.get(), res.get() + loc, true, false);
     }
     std::vector<G2Xyzz> pts(total);
+    if (shared0 && !pi0->ready) {
+        SB_CUDA(cudaStreamWaitEvent(st, pi0->done, 0));
+        SB_CUDA(cudaMemcpyAsync(&pi0->host, pi0->out.get(), sizeof(G2Xyzz), cudaMemcpyDeviceToHost, st));
+        g_sb_d2h_bytes += sizeof(G2Xyzz);
+    }
     fetch_xyzz(c, res.get(), total, pts.data());
     d2h_fr(c, sb_ctx::SLOT_OUT, eval_out, 1);
+    if (shared0) { pi0->ready = true; pts[0] = pi0->host; }
+    else if (pi0 && pi0_layout(pp)) { pi0->host = pts[0]; pi0->ready = true; }      // this rank's share, before the exchange
     if (c->sharded()) {
         std::vector<G2Xyzz> all((size_t)loc * G);
         c->allgather(pts.data(), all.data(), loc * sizeof(G2Xyzz));
@@ -928,10 +994,19 @@ static void prover_sc2_round(sb_prover* p, const Fr* v_msg, Fr* out3_host) {
 
 static const char* kPhaseNames[] = {"transcript_init", "prove1_commit", "prove2_open", "prove3_eq_spmv", "sumcheck1", "prove4",
                                     "prove5_eval_on_x", "sumcheck2", "prove6_open", "serialize", "total", nullptr};
+// the reference's own timer spans (start_timer!/end_timer! in src/lib.rs:71-135); the same names label the NVTX ranges
+// of sb_prove, so that a profiler timeline lines up with the reference's print-trace output
+static const char* kPhaseSpans[] = {"feed matrices + v (lib.rs:61-65)", "Prove 1", "Prove 2", "Prove 3", "Prove Sumcheck 1", "Prove 4",
+                                    "Prove 5", "Prove Sumcheck 2", "Prove 6", "serialize Proof", "Prove", nullptr};
+struct Span {            // RAII NVTX range
+    explicit Span(int phase) { SB_SPAN_PUSH(kPhaseSpans[phase]); }
+    ~Span() { SB_SPAN_POP(); }
+};
 
 extern "C" {
 
 const char* sb_phase_name(int i) { return (i >= 0 && i < 11) ? kPhaseNames[i] : nullptr; }
+const char* sb_phase_span(int i) { return (i >= 0 && i < 11) ? kPhaseSpans[i] : nullptr; }
 uint64_t sb_launch_count(void) { return g_sb_launches; }
 size_t sb_proof_size(uint32_t l) {
     size_t open = 32 + 96 + 8 + (size_t)l * 96;
@@ -1188,7 +1263,7 @@ sb_status sb_prover_first_round(sb_prover* p, const sb_pp* pp, void* out_commit)
     SB_REQUIRE(p && pp && out_commit, "null argument");
     SB_REQUIRE(p->stage == ST_INIT, "round called out of order");
     SB_REQUIRE(pp->nv_total == p->log_n, "public parameter size does not match the instance");
-    G1Aff r = commit_dev(p->ctx, pp, p->z);
+    G1Aff r = commit_dev(p->ctx, pp, p->z, &p->pi0);
     memcpy(out_commit, &r, sizeof r);
     p->stage = ST_R1;
     SB_API_END
@@ -1201,7 +1276,7 @@ sb_status sb_prover_second_round(sb_prover* p, const sb_pp* pp, const void* r_v,
     std::vector<Fr> point(p->log_n, Fr::zero());          // r_v extended with zeros (prover.rs:152)
     if (p->log_v) memcpy(point.data(), r_v, p->log_v * sizeof(Fr));
     Fr ev; std::vector<G2Aff> pr(p->log_n);
-    open_dev(p->ctx, pp, p->z, point.data(), &ev, pr.data(), p->open_r0, p->open_r1, p->open_q);
+    open_dev(p->ctx, pp, p->z, point.data(), &ev, pr.data(), p->open_r0, p->open_r1, p->open_q, &p->pi0);
     memcpy(out_z_rv_0, &ev, sizeof ev);
     memcpy(out_proofs, pr.data(), pr.size() * sizeof(G2Aff));
     p->stage = ST_R2;
@@ -1260,7 +1335,7 @@ sb_status sb_prover_sixth_round(sb_prover* p, const sb_pp* pp, const void* last,
     SB_REQUIRE(pp->nv_total == p->log_n, "public parameter size does not match the instance");
     p->r_y.push_back(*static_cast<const Fr*>(last));
     Fr ev; std::vector<G2Aff> pr(p->log_n);
-    open_dev(p->ctx, pp, p->z, p->r_y.data(), &ev, pr.data(), p->open_r0, p->open_r1, p->open_q);
+    open_dev(p->ctx, pp, p->z, p->r_y.data(), &ev, pr.data(), p->open_r0, p->open_r1, p->open_q, &p->pi0);
     memcpy(out_z_ry, &ev, sizeof ev);
     memcpy(out_proofs, pr.data(), pr.size() * sizeof(G2Aff));
     p->stage = ST_DONE;
@@ -1292,30 +1367,37 @@ static void prove_body(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const v
     if (!proof || *len < need) { *len = need; throw SbError(SB_EINVAL, "proof buffer too small"); }
     double t_all = now_ms(), t0 = t_all;
     double ph[16] = {0};
+    Span span_all(10);
+    std::unique_ptr<Span> span(new Span(0));
+    auto next_span = [&](int phase) { span.reset(); span.reset(new Span(phase)); };
     std::unique_ptr<sb_prover> p(resident ? prover_init_resident(ctx, ix, resident) : prover_init(ctx, ix, v, nv_len, w, nw_len, true));
     if (resident) { v = resident->v_host.data(); nv_len = resident->v_host.size(); }
     const Fr* vh = static_cast<const Fr*>(v);
     sbhost::Transcript fs = ix->fs_after_matrices;              // lib.rs:61-64, absorbed once at index time
     { Bytes b; sbhost::put_fr_vec(b, vh, nv_len); fs.feed(b); } // lib.rs:65
     ph[0] = now_ms() - t0; t0 = now_ms();
-    // Prove 1
-    G1Aff com = commit_dev(ctx, pp, p->z);
+    next_span(1);
+    // Prove 1 (the shared first element of both opening proofs is queued right behind the commitment's MSMs: it only
+    // needs z, and the device works on it while the host hashes and the first opening's other levels are planned)
+    G1Aff com = commit_dev(ctx, pp, p->z, &p->pi0);
     Bytes pm1; sbhost::put_u64(pm1, ell); sbhost::put_g1(pm1, com);
     fs.feed(pm1);
     std::vector<Fr> r_v(p->log_v);
     for (auto& x : r_v) x = fs.challenge();                      // verifier.rs:172-178
     ph[1] = now_ms() - t0; t0 = now_ms();
+    next_span(2);
     // Prove 2
     std::vector<Fr> point(ell, Fr::zero());
     std::copy(r_v.begin(), r_v.end(), point.begin());
     Fr z_rv_0; std::vector<G2Aff> pr1(ell);
-    open_dev(ctx, pp, p->z, point.data(), &z_rv_0, pr1.data(), p->open_r0, p->open_r1, p->open_q);
+    open_dev(ctx, pp, p->z, point.data(), &z_rv_0, pr1.data(), p->open_r0, p->open_r1, p->open_q, &p->pi0);
     Bytes pm2; sbhost::put_fr(pm2, z_rv_0); sbhost::put_g2(pm2, pp->h_host); sbhost::put_u64(pm2, ell);
     for (auto& q : pr1) sbhost::put_g2(pm2, q);
     fs.feed(pm2);
     std::vector<Fr> tor(ell);
     for (auto& x : tor) x = fs.challenge();                      // verifier.rs:211-217
     ph[2] = now_ms() - t0; t0 = now_ms();
+    next_span(3);
     // Prove 3
     prover_third_round(p.get(), tor.data());
     if (tr && (tr->az || tr->bz || tr->cz)) {
@@ -1328,6 +1410,7 @@ static void prove_body(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const v
     Bytes pm3; sbhost::put_u64(pm3, ell + 2); sbhost::put_u64(pm3, ell);   // IndexInfo{max_multiplicands, num_variables}
     fs.feed(pm3);
     ph[3] = now_ms() - t0; t0 = now_ms();
+    next_span(4);
     // Sumcheck 1 (lib.rs:88-103)
     Bytes sc1; sbhost::put_u64(sc1, ell);
     std::vector<Fr> evals(ell + 3);
@@ -1340,6 +1423,7 @@ static void prove_body(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const v
         vm = fs.challenge(); have = true;
     }
     ph[4] = now_ms() - t0; t0 = now_ms();
+    next_span(5);
     // Prove 4
     Fr vabc[3];
     prover_fourth_round(p.get(), &vm, vabc);
@@ -1348,12 +1432,14 @@ static void prove_body(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const v
     Fr r_abc[3];
     for (int k = 0; k < 3; k++) r_abc[k] = fs.challenge();       // verifier.rs:354-360
     ph[5] = now_ms() - t0; t0 = now_ms();
+    next_span(6);
     // Prove 5
     prover_fifth_round(p.get(), r_abc);
     Bytes pm5; sbhost::put_u64(pm5, 2); sbhost::put_u64(pm5, ell);
     fs.feed(pm5);
     ctx_sync(ctx);
     ph[6] = now_ms() - t0; t0 = now_ms();
+    next_span(7);
     // Sumcheck 2 (lib.rs:116-131)
     Bytes sc2; sbhost::put_u64(sc2, ell);
     have = false;
@@ -1366,13 +1452,15 @@ static void prove_body(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const v
         vm = fs.challenge(); have = true;
     }
     ph[7] = now_ms() - t0; t0 = now_ms();
+    next_span(8);
     // Prove 6
     p->r_y.push_back(vm);
     Fr z_ry; std::vector<G2Aff> pr2(ell);
-    open_dev(ctx, pp, p->z, p->r_y.data(), &z_ry, pr2.data(), p->open_r0, p->open_r1, p->open_q);
+    open_dev(ctx, pp, p->z, p->r_y.data(), &z_ry, pr2.data(), p->open_r0, p->open_r1, p->open_q, &p->pi0);
     ph[8] = now_ms() - t0; t0 = now_ms();
     Bytes pm6; sbhost::put_fr(pm6, z_ry); sbhost::put_g2(pm6, pp->h_host); sbhost::put_u64(pm6, ell);
     for (auto& q : pr2) sbhost::put_g2(pm6, q);
+    next_span(9);
     // Proof field order: data_structures/proof.rs:11-20
     Bytes out; out.reserve(need);
     auto app = [&](const Bytes& b) { out.insert(out.end(), b.begin(), b.end()); };
