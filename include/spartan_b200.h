@@ -74,10 +74,18 @@ void sb_comm_shm_close(sb_comm* comm);
 /* ---- context ---------------------------------------------------------------------------------- */
 sb_status sb_ctx_create(int device, sb_ctx** out);
 sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out);
+/* ONE context over several GPUs of this process (ndev a power of two): the hypercube-sharded prover with one host thread per
+ * GPU inside the library and an in-process exchange, so that MLArgumentForR1CS::prove (src/lib.rs:58) stays one call from
+ * one process.  Handles made from it (index, parameters, witness, prover state) hold one part per GPU; index / keygen /
+ * load / commit / open / prove / the prover rounds work as on a single-GPU context and give the same bytes.  The
+ * single-matrix helpers (sb_msm, sb_eq_table, sb_sum_over_y, sb_eval_on_x, sb_pp_export) need a single-GPU context. */
+sb_status sb_ctx_create_multi(const int* devices, int ndev, sb_ctx** out);
 void sb_ctx_destroy(sb_ctx* ctx);
 const char* sb_last_error(const sb_ctx* ctx);   /* ctx may be NULL: last error of a failed sb_ctx_create */
 /* number of CUDA kernels this library has launched in this process (bench.py: gpu_launches) */
 uint64_t sb_launch_count(void);
+/* CUDA devices visible to this process (0 when there is none: every sb_ctx_create* then fails with SB_ECUDA) */
+int sb_device_count(void);
 
 /* ---- indexer: MLArgumentForR1CS::index, src/lib.rs:45-51 -> src/ahp/indexer.rs:41-64 ------------ */
 /* Same checks as the reference: n = 2^log_n rows per matrix (indexer.rs:49, r1cs_reader.rs:38-52),

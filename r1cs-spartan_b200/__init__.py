@@ -11,6 +11,6 @@ The directory name follows the project naming; Python code imports it as `r1cs_s
 """
 from .api import (  # noqa: F401
     Context, CudaError, InvalidArgument, IndexPK, MLArgumentForR1CS, MLPolyCommit, MLProofForR1CS, PublicParameter,
-    ProveTrace, Witness, default_context, eq_extension, load_library, multi_scalar_mul, LIB_PATH, EXPORTS,
+    ProveTrace, Witness, default_context, device_count, eq_extension, load_library, multi_scalar_mul, LIB_PATH, EXPORTS,
 )
 from .workload import SyntheticR1CS  # noqa: F401

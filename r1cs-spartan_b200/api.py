@@ -23,7 +23,7 @@ _lib = None
 SB_OK, SB_EINVAL, SB_ECUDA, SB_ENOMEM, SB_ECOMM, SB_EINTERNAL = range(6)
 
 EXPORTS = [
-    "sb_ctx_create", "sb_ctx_create_sharded", "sb_ctx_destroy", "sb_last_error", "sb_launch_count",
+    "sb_ctx_create", "sb_ctx_create_sharded", "sb_ctx_create_multi", "sb_ctx_destroy", "sb_last_error", "sb_launch_count", "sb_device_count",
     "sb_index_create", "sb_index_destroy", "sb_pp_load", "sb_pp_keygen", "sb_pp_export", "sb_pp_export_g_mask",
     "sb_pp_destroy", "sb_commit", "sb_open", "sb_msm", "sb_eq_table", "sb_sum_over_y", "sb_eval_on_x",
     "sb_prover_init", "sb_prover_destroy", "sb_prover_first_round", "sb_prover_second_round", "sb_prover_third_round",
@@ -100,11 +100,15 @@ def _fr(a, count=None):
 
 
 class Context:
-    def __init__(self, device=0, comm=None):
+    def __init__(self, device=0, comm=None, devices=None):
+        """device: one GPU.  devices=[...]: ONE context over several GPUs of this process (sb_ctx_create_multi)."""
         L = load_library()
         self.h = C.c_void_p()
         self._comm = None
-        if comm is None:
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            st = L.sb_ctx_create_multi(arr, C.c_int(len(devices)), C.byref(self.h))
+        elif comm is None:
             st = L.sb_ctx_create(C.c_int(device), C.byref(self.h))
         else:
             self._comm = comm             # keeps the callback alive
@@ -189,6 +193,10 @@ class Context:
 
 
 _default_ctx = None
+
+
+def device_count():
+    return int(load_library().sb_device_count())
 
 
 def default_context():

@@ -38,8 +38,9 @@ constexpr int SB_SMS = 148;
 
 // Counter of kernels this library launched (bench.py reports it as gpu_launches), host<->device byte
 // counters, and the optional per-kernel CUDA-event profiler (sb_prof_enable / sb_prof_report).
-extern unsigned long long g_sb_launches;
-extern unsigned long long g_sb_h2d_bytes, g_sb_d2h_bytes;
+#include <atomic>
+extern std::atomic<unsigned long long> g_sb_launches;           // (atomic: a multi-GPU context drives one host thread per GPU)
+extern std::atomic<unsigned long long> g_sb_h2d_bytes, g_sb_d2h_bytes;
 extern bool g_sb_prof_on;
 extern int g_sb_prof_tag;
 void sb_prof_begin(const char* name, cudaStream_t stream);

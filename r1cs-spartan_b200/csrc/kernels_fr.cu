@@ -7,8 +7,8 @@
 #include <string>
 #include <vector>
 
-unsigned long long g_sb_launches = 0;
-unsigned long long g_sb_h2d_bytes = 0, g_sb_d2h_bytes = 0;
+std::atomic<unsigned long long> g_sb_launches{0};
+std::atomic<unsigned long long> g_sb_h2d_bytes{0}, g_sb_d2h_bytes{0};
 bool g_sb_prof_on = false;
 int g_sb_prof_tag = -1;            // free-form tag attached to the records (the MSM code sets log2 of the job size)
 

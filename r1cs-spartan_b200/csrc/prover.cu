@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -37,6 +39,14 @@ struct sb_ctx {
     sb_comm comm{};
     int rank = 0, world = 1, glog = 0;
     bool sharded() const { return world > 1; }
+    // A MULTI context (sb_ctx_create_multi) owns no device itself: it is `shards.size()` sharded contexts, one per GPU of this
+    // process, each driven by its own worker thread, exchanging through an in-process mailbox.  Handles made from it hold
+    // one part per shard; every library call fans out to the workers and returns when all of them are done.
+    struct Worker;
+    std::vector<sb_ctx*> shards;
+    std::vector<std::unique_ptr<Worker>> workers;
+    std::vector<sb_comm> shard_comms;
+    bool is_multi() const { return !shards.empty(); }
     // per-round reduction workspace + mailbox
     DevBuf<Fr> block_partials;
     DevBuf<unsigned int> ticket;
@@ -96,6 +106,7 @@ struct SegPlan {
 
 // Sharded contexts hold the plans of their own slice only: rows / columns [rank * nl, (rank + 1) * nl).
 struct sb_index {
+    std::vector<sb_index*> parts;    // multi context: one index per shard (this object then holds nothing else but ctx / log_n / n)
     sb_ctx* ctx = nullptr;
     uint32_t log_n = 0, loc = 0;     // total variables, variables of the local slice (log_n - glog)
     size_t n = 0, nl = 0;
@@ -111,6 +122,7 @@ struct sb_index {
 // h^{eq(t[L..], x)} factors over the top bits), and `tail` is the parameter set over the top glog variables
 // that every rank keeps for the last glog levels of an opening.
 struct sb_pp {
+    std::vector<sb_pp*> parts;       // multi context: one parameter slice per shard
     sb_ctx* ctx = nullptr;
     uint32_t nv = 0;            // variables handled by g1 / g2 below
     uint32_t nv_total = 0;      // variables of the whole polynomial
@@ -133,6 +145,7 @@ struct sb_pp {
 
 // z = v || w resident in HBM (bench.py: the "inputs already resident" arm)
 struct sb_witness {
+    std::vector<sb_witness*> parts;  // multi context
     sb_ctx* ctx = nullptr;
     size_t n = 0;
     DevBuf<Fr> z;
@@ -142,6 +155,7 @@ struct sb_witness {
 enum ProverStage { ST_INIT, ST_R1, ST_R2, ST_R3, ST_SC1, ST_R4, ST_R5, ST_SC2, ST_DONE };
 
 struct sb_prover {
+    std::vector<sb_prover*> parts;   // multi context
     sb_ctx* ctx = nullptr;
     const sb_index* idx = nullptr;
     uint32_t log_n = 0, log_v = 0, loc = 0;
@@ -1003,11 +1017,66 @@ struct Span {            // RAII NVTX range
     ~Span() { SB_SPAN_POP(); }
 };
 
+// ====================================================================== multi-GPU context (one process, one thread per GPU)
+// SURVEY 8(b) / lib.rs:58: MLArgumentForR1CS::prove is ONE call from ONE process.  sb_ctx_create_multi makes that call
+// span several GPUs: the context holds one hypercube-sharded context per device (the same code path a one-process-per-GPU
+// host uses), one worker thread each, and an in-process exchange mailbox (sb_comm_local_open).  Every handle made from a
+// multi context holds one part per shard; a library call fans out to the workers through the public entry point of the
+// shard contexts and returns when all of them have returned.
+struct sb_ctx::Worker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<sb_status()> job;
+    bool has_job = false, done = false, quit = false;
+    sb_status result = SB_OK;
+    void loop() {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv.wait(lk, [&] { return has_job || quit; });
+            if (quit) return;
+            std::function<sb_status()> j = std::move(job);
+            has_job = false;
+            lk.unlock();
+            sb_status r;
+            try { r = j(); } catch (...) { r = SB_EINTERNAL; }
+            lk.lock();
+            result = r; done = true;
+            cv.notify_all();
+        }
+    }
+};
+// run fn(rank, shard context) on every worker at once; the first failing status wins and its message becomes the multi context's
+template <class Fn>
+static sb_status multi_call(sb_ctx* m, Fn fn) {
+    const size_t G = m->shards.size();
+    for (size_t r = 0; r < G; r++) {
+        sb_ctx::Worker& w = *m->workers[r];
+        std::lock_guard<std::mutex> g(w.m);
+        sb_ctx* sc = m->shards[r];
+        const int rank = (int)r;
+        w.job = [fn, rank, sc]() -> sb_status { return fn(rank, sc); };
+        w.has_job = true; w.done = false;
+        w.cv.notify_all();
+    }
+    sb_status st = SB_OK;
+    for (size_t r = 0; r < G; r++) {
+        sb_ctx::Worker& w = *m->workers[r];
+        std::unique_lock<std::mutex> lk(w.m);
+        w.cv.wait(lk, [&] { return w.done; });
+        if (w.result != SB_OK && st == SB_OK) { st = w.result; m->last_error = "rank " + std::to_string(r) + ": " + m->shards[r]->last_error; }
+    }
+    return st;
+}
+template <class T>
+static std::vector<T*> multi_parts(const std::vector<T*>& v) { return v; }
+
 extern "C" {
 
 const char* sb_phase_name(int i) { return (i >= 0 && i < 11) ? kPhaseNames[i] : nullptr; }
 const char* sb_phase_span(int i) { return (i >= 0 && i < 11) ? kPhaseSpans[i] : nullptr; }
 uint64_t sb_launch_count(void) { return g_sb_launches; }
+int sb_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
 size_t sb_proof_size(uint32_t l) {
     size_t open = 32 + 96 + 8 + (size_t)l * 96;
     return (8 + 48) + open + 16 + 8 + (size_t)l * (8 + 32 * ((size_t)l + 3)) + 96 + 16 + 8 + (size_t)l * (8 + 96) + open;
@@ -1075,8 +1144,43 @@ sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
 }
 sb_status sb_ctx_create(int device, sb_ctx** out) { return sb_ctx_create_sharded(device, nullptr, out); }
 
+sb_status sb_ctx_create_multi(const int* devices, int ndev, sb_ctx** out) {
+    if (!out || !devices || ndev < 1 || ndev > 64 || (ndev & (ndev - 1))) { g_create_error = "sb_ctx_create_multi needs a power-of-two number of devices"; return SB_EINVAL; }
+    if (ndev == 1) return sb_ctx_create(devices[0], out);
+    std::unique_ptr<sb_ctx> m(new sb_ctx);
+    m->device = devices[0];
+    m->shard_comms.resize(ndev);
+    sb_status st = sb_comm_local_open(ndev, m->shard_comms.data());
+    if (st != SB_OK) { g_create_error = "cannot create the in-process exchange"; return st; }
+    for (int r = 0; r < ndev && st == SB_OK; r++) {
+        sb_ctx* sc = nullptr;
+        st = sb_ctx_create_sharded(devices[r], &m->shard_comms[r], &sc);
+        if (st == SB_OK) m->shards.push_back(sc);
+    }
+    if (st != SB_OK) {
+        for (sb_ctx* sc : m->shards) sb_ctx_destroy(sc);
+        m->shards.clear();
+        for (int r = ndev; r-- > 0;) sb_comm_shm_close(&m->shard_comms[r]);
+        return st;
+    }
+    for (int r = 0; r < ndev; r++) {
+        m->workers.emplace_back(new sb_ctx::Worker);
+        sb_ctx::Worker* w = m->workers.back().get();
+        w->th = std::thread([w] { w->loop(); });
+    }
+    *out = m.release();
+    return SB_OK;
+}
+
 void sb_ctx_destroy(sb_ctx* c) {
     if (!c) return;
+    if (c->is_multi()) {
+        for (auto& w : c->workers) { { std::lock_guard<std::mutex> g(w->m); w->quit = true; } w->cv.notify_all(); w->th.join(); }
+        for (sb_ctx* sc : c->shards) sb_ctx_destroy(sc);
+        for (size_t r = c->shard_comms.size(); r-- > 0;) sb_comm_shm_close(&c->shard_comms[r]);
+        delete c;
+        return;
+    }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->block_partials.release(); c->ticket.release(); c->d_mail.release(); c->h_mail.release();
@@ -1097,6 +1201,16 @@ void sb_ctx_destroy(sb_ctx* c) {
 const char* sb_last_error(const sb_ctx* c) { return c ? c->last_error.c_str() : g_create_error.c_str(); }
 
 sb_status sb_index_create(sb_ctx* ctx, uint32_t log_n, const sb_csr* a, const sb_csr* b, const sb_csr* c, sb_index** out) {
+    if (ctx && ctx->is_multi()) {
+        if (!out) return SB_EINVAL;
+        std::unique_ptr<sb_index> ix(new sb_index);
+        ix->ctx = ctx; ix->log_n = log_n; ix->n = (size_t)1 << (log_n & 63); ix->parts.assign(ctx->shards.size(), nullptr);
+        sb_index** parts = ix->parts.data();
+        sb_status st = multi_call(ctx, [=](int r, sb_ctx* sc) { return sb_index_create(sc, log_n, a, b, c, &parts[r]); });
+        if (st != SB_OK) { for (sb_index* p : ix->parts) sb_index_destroy(p); return st; }
+        *out = ix.release();
+        return SB_OK;
+    }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && out, "null argument");
     const sb_csr* m[3] = {a, b, c};
@@ -1105,23 +1219,45 @@ sb_status sb_index_create(sb_ctx* ctx, uint32_t log_n, const sb_csr* a, const sb
 }
 void sb_index_destroy(sb_index* ix) {
     if (!ix) return;
+    if (!ix->parts.empty()) { for (sb_index* p : ix->parts) sb_index_destroy(p); delete ix; return; }
     cudaSetDevice(ix->ctx->device);
     delete ix;
 }
 
 sb_status sb_pp_load(sb_ctx* ctx, uint32_t nv, const void* g0, const void* const* hs, const void* h, sb_pp** out) {
+    if (ctx && ctx->is_multi()) {
+        if (!out) return SB_EINVAL;
+        std::unique_ptr<sb_pp> pp(new sb_pp);
+        pp->ctx = ctx; pp->nv_total = nv; pp->parts.assign(ctx->shards.size(), nullptr);
+        sb_pp** parts = pp->parts.data();
+        sb_status st = multi_call(ctx, [=](int r, sb_ctx* sc) { return sb_pp_load(sc, nv, g0, hs, h, &parts[r]); });
+        if (st != SB_OK) { for (sb_pp* p : pp->parts) sb_pp_destroy(p); return st; }
+        *out = pp.release();
+        return SB_OK;
+    }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && out, "null argument");
     *out = pp_load(ctx, nv, g0, hs, h);
     SB_API_END
 }
 sb_status sb_pp_keygen(sb_ctx* ctx, uint32_t nv, const void* g, const void* h, const void* t, int keep_all, sb_pp** out) {
+    if (ctx && ctx->is_multi()) {
+        if (!out) return SB_EINVAL;
+        std::unique_ptr<sb_pp> pp(new sb_pp);
+        pp->ctx = ctx; pp->nv_total = nv; pp->parts.assign(ctx->shards.size(), nullptr);
+        sb_pp** parts = pp->parts.data();
+        sb_status st = multi_call(ctx, [=](int r, sb_ctx* sc) { return sb_pp_keygen(sc, nv, g, h, t, keep_all, &parts[r]); });
+        if (st != SB_OK) { for (sb_pp* p : pp->parts) sb_pp_destroy(p); return st; }
+        *out = pp.release();
+        return SB_OK;
+    }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && out, "null argument");
     *out = pp_keygen(ctx, nv, g, h, t, keep_all != 0);
     SB_API_END
 }
 sb_status sb_pp_export(sb_ctx* ctx, const sb_pp* pp, int group, uint32_t level, void* outp) {
+    if (ctx && ctx->is_multi()) { ctx->last_error = "this entry point is only available on a single-GPU context"; return SB_EINVAL; }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && pp && outp && level < pp->nv && (group == 1 || group == 2), "bad export request");
     SB_REQUIRE(!ctx->sharded(), "export is only available on a single-GPU context");
@@ -1137,6 +1273,7 @@ sb_status sb_pp_export(sb_ctx* ctx, const sb_pp* pp, int group, uint32_t level, 
     SB_API_END
 }
 sb_status sb_pp_export_g_mask(sb_ctx* ctx, const sb_pp* pp, void* outp) {
+    if (ctx && ctx->is_multi()) return (pp && !pp->parts.empty()) ? sb_pp_export_g_mask(ctx->shards[0], pp->parts[0], outp) : SB_EINVAL;
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && pp && outp && pp->g_mask.size() == pp->nv_total, "g_mask_random only exists after sb_pp_keygen");
     memcpy(outp, pp->g_mask.data(), pp->nv_total * sizeof(G1Aff));
@@ -1144,11 +1281,20 @@ sb_status sb_pp_export_g_mask(sb_ctx* ctx, const sb_pp* pp, void* outp) {
 }
 void sb_pp_destroy(sb_pp* pp) {
     if (!pp) return;
+    if (!pp->parts.empty()) { for (sb_pp* p : pp->parts) sb_pp_destroy(p); delete pp; return; }
     cudaSetDevice(pp->ctx->device);
     delete pp;
 }
 
 sb_status sb_commit(sb_ctx* ctx, const sb_pp* pp, const void* z, void* out_g1) {
+    if (ctx && ctx->is_multi()) {
+        if (!pp || pp->parts.size() != ctx->shards.size() || !out_g1) return SB_EINVAL;
+        std::vector<G1Aff> outs(ctx->shards.size());
+        G1Aff* o = outs.data();
+        sb_status st = multi_call(ctx, [=](int r, sb_ctx* sc) { return sb_commit(sc, pp->parts[r], z, &o[r]); });
+        if (st == SB_OK) memcpy(out_g1, &outs[0], sizeof(G1Aff));
+        return st;
+    }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && pp && z && out_g1, "null argument");
     size_t n = (size_t)1 << pp->nv_total;
@@ -1159,6 +1305,15 @@ sb_status sb_commit(sb_ctx* ctx, const sb_pp* pp, const void* z, void* out_g1) {
     SB_API_END
 }
 sb_status sb_open(sb_ctx* ctx, const sb_pp* pp, const void* z, const void* point, void* out_eval, void* out_proofs) {
+    if (ctx && ctx->is_multi()) {
+        if (!pp || pp->parts.size() != ctx->shards.size() || !out_eval || !out_proofs) return SB_EINVAL;
+        const size_t G = ctx->shards.size(), nv = pp->nv_total;
+        std::vector<Fr> evs(G); std::vector<G2Aff> prs(G * nv);
+        Fr* e = evs.data(); G2Aff* q = prs.data();
+        sb_status st = multi_call(ctx, [=](int r, sb_ctx* sc) { return sb_open(sc, pp->parts[r], z, point, &e[r], q + (size_t)r * nv); });
+        if (st == SB_OK) { memcpy(out_eval, &evs[0], sizeof(Fr)); memcpy(out_proofs, prs.data(), nv * sizeof(G2Aff)); }
+        return st;
+    }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && pp && z && point && out_eval && out_proofs, "null argument");
     size_t n = (size_t)1 << pp->nv_total;
@@ -1171,6 +1326,7 @@ sb_status sb_open(sb_ctx* ctx, const sb_pp* pp, const void* z, const void* point
     SB_API_END
 }
 sb_status sb_msm(sb_ctx* ctx, int group, const void* bases, const void* scalars, size_t n, void* out_affine) {
+    if (ctx && ctx->is_multi()) { ctx->last_error = "this entry point is only available on a single-GPU context"; return SB_EINVAL; }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && bases && scalars && out_affine && n >= 1 && (group == 1 || group == 2), "bad msm request");
     SB_REQUIRE(!ctx->sharded(), "sb_msm is only available on a single-GPU context");
@@ -1198,6 +1354,7 @@ sb_status sb_msm(sb_ctx* ctx, int group, const void* bases, const void* scalars,
 }
 
 sb_status sb_eq_table(sb_ctx* ctx, const void* t, uint32_t dim, void* outp) {
+    if (ctx && ctx->is_multi()) { ctx->last_error = "this entry point is only available on a single-GPU context"; return SB_EINVAL; }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && t && outp && dim >= 1 && dim <= 28, "bad eq request");
     size_t n = (size_t)1 << dim;
@@ -1211,6 +1368,7 @@ sb_status sb_eq_table(sb_ctx* ctx, const void* t, uint32_t dim, void* outp) {
     SB_API_END
 }
 sb_status sb_sum_over_y(sb_ctx* ctx, const sb_index* ix, const void* z, void* az, void* bz, void* cz) {
+    if (ctx && ctx->is_multi()) { ctx->last_error = "this entry point is only available on a single-GPU context"; return SB_EINVAL; }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && ix && z, "null argument");
     SB_REQUIRE(!ctx->sharded(), "sb_sum_over_y is only available on a single-GPU context");
@@ -1226,6 +1384,7 @@ sb_status sb_sum_over_y(sb_ctx* ctx, const sb_index* ix, const void* z, void* az
     SB_API_END
 }
 sb_status sb_eval_on_x(sb_ctx* ctx, const sb_index* ix, const void* r_x, const void* r_abc, int which, void* outp) {
+    if (ctx && ctx->is_multi()) { ctx->last_error = "this entry point is only available on a single-GPU context"; return SB_EINVAL; }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && ix && r_x && outp, "null argument");
     SB_REQUIRE(r_abc || (which >= 0 && which < 3), "which must be 0, 1 or 2");
@@ -1248,6 +1407,16 @@ sb_status sb_eval_on_x(sb_ctx* ctx, const sb_index* ix, const void* r_x, const v
 }
 
 sb_status sb_prover_init(sb_ctx* ctx, const sb_index* ix, const void* v, size_t nv_len, const void* w, size_t nw_len, sb_prover** out) {
+    if (ctx && ctx->is_multi()) {
+        if (!out || !ix || ix->parts.size() != ctx->shards.size()) return SB_EINVAL;
+        std::unique_ptr<sb_prover> p(new sb_prover);
+        p->ctx = ctx; p->idx = ix; p->log_n = ix->log_n; p->parts.assign(ctx->shards.size(), nullptr);
+        sb_prover** parts = p->parts.data();
+        sb_status st = multi_call(ctx, [=](int r, sb_ctx* sc) { return sb_prover_init(sc, ix->parts[r], v, nv_len, w, nw_len, &parts[r]); });
+        if (st != SB_OK) { for (sb_prover* q : p->parts) sb_prover_destroy(q); return st; }
+        *out = p.release();
+        return SB_OK;
+    }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && ix && out, "null argument");
     *out = prover_init(ctx, ix, v, nv_len, w, nw_len);
@@ -1255,10 +1424,18 @@ sb_status sb_prover_init(sb_ctx* ctx, const sb_index* ix, const void* v, size_t 
 }
 void sb_prover_destroy(sb_prover* p) {
     if (!p) return;
+    if (!p->parts.empty()) { for (sb_prover* q : p->parts) sb_prover_destroy(q); p->ctx = nullptr; delete p; return; }
     cudaSetDevice(p->ctx->device);
     delete p;
 }
 sb_status sb_prover_first_round(sb_prover* p, const sb_pp* pp, void* out_commit) {
+    if (p && !p->parts.empty()) {
+        if (!pp || pp->parts.size() != p->parts.size() || !out_commit) return SB_EINVAL;
+        std::vector<G1Aff> o(p->parts.size()); G1Aff* op = o.data();
+        sb_status st = multi_call(p->ctx, [=](int r, sb_ctx*) { return sb_prover_first_round(p->parts[r], pp->parts[r], &op[r]); });
+        if (st == SB_OK) memcpy(out_commit, &o[0], sizeof(G1Aff));
+        return st;
+    }
     SB_API_BEGIN(p ? p->ctx : nullptr)
     SB_REQUIRE(p && pp && out_commit, "null argument");
     SB_REQUIRE(p->stage == ST_INIT, "round called out of order");
@@ -1269,6 +1446,14 @@ sb_status sb_prover_first_round(sb_prover* p, const sb_pp* pp, void* out_commit)
     SB_API_END
 }
 sb_status sb_prover_second_round(sb_prover* p, const sb_pp* pp, const void* r_v, void* out_z_rv_0, void* out_proofs) {
+    if (p && !p->parts.empty()) {
+        if (!pp || pp->parts.size() != p->parts.size() || !out_z_rv_0 || !out_proofs) return SB_EINVAL;
+        const size_t G = p->parts.size(), nv = p->log_n;
+        std::vector<Fr> e(G); std::vector<G2Aff> q(G * nv); Fr* ep = e.data(); G2Aff* qp = q.data();
+        sb_status st = multi_call(p->ctx, [=](int r, sb_ctx*) { return sb_prover_second_round(p->parts[r], pp->parts[r], r_v, &ep[r], qp + (size_t)r * nv); });
+        if (st == SB_OK) { memcpy(out_z_rv_0, &e[0], sizeof(Fr)); memcpy(out_proofs, q.data(), nv * sizeof(G2Aff)); }
+        return st;
+    }
     SB_API_BEGIN(p ? p->ctx : nullptr)
     SB_REQUIRE(p && pp && out_z_rv_0 && out_proofs && (r_v || p->log_v == 0), "null argument");
     SB_REQUIRE(p->stage == ST_R1, "round called out of order");
@@ -1283,6 +1468,7 @@ sb_status sb_prover_second_round(sb_prover* p, const sb_pp* pp, const void* r_v,
     SB_API_END
 }
 sb_status sb_prover_third_round(sb_prover* p, const void* tor) {
+    if (p && !p->parts.empty()) return multi_call(p->ctx, [=](int r, sb_ctx*) { return sb_prover_third_round(p->parts[r], tor); });
     SB_API_BEGIN(p ? p->ctx : nullptr)
     SB_REQUIRE(p && tor, "null argument");
     SB_REQUIRE(p->stage == ST_R2, "round called out of order");
@@ -1291,6 +1477,14 @@ sb_status sb_prover_third_round(sb_prover* p, const void* tor) {
     SB_API_END
 }
 sb_status sb_prover_first_sumcheck_round(sb_prover* p, const void* v_msg, void* out_evals) {
+    if (p && !p->parts.empty()) {
+        if (!out_evals) return SB_EINVAL;
+        const size_t G = p->parts.size(), k = p->log_n + 3;
+        std::vector<Fr> e(G * k); Fr* ep = e.data();
+        sb_status st = multi_call(p->ctx, [=](int r, sb_ctx*) { return sb_prover_first_sumcheck_round(p->parts[r], v_msg, ep + (size_t)r * k); });
+        if (st == SB_OK) memcpy(out_evals, e.data(), k * sizeof(Fr));
+        return st;
+    }
     SB_API_BEGIN(p ? p->ctx : nullptr)
     SB_REQUIRE(p && out_evals, "null argument");
     SB_REQUIRE(p->stage == ST_R3 || p->stage == ST_SC1, "round called out of order");
@@ -1301,6 +1495,13 @@ sb_status sb_prover_first_sumcheck_round(sb_prover* p, const void* v_msg, void* 
     SB_API_END
 }
 sb_status sb_prover_fourth_round(sb_prover* p, const void* last, void* out_vabc) {
+    if (p && !p->parts.empty()) {
+        if (!out_vabc) return SB_EINVAL;
+        std::vector<Fr> e(p->parts.size() * 3); Fr* ep = e.data();
+        sb_status st = multi_call(p->ctx, [=](int r, sb_ctx*) { return sb_prover_fourth_round(p->parts[r], last, ep + 3 * (size_t)r); });
+        if (st == SB_OK) memcpy(out_vabc, e.data(), 3 * sizeof(Fr));
+        return st;
+    }
     SB_API_BEGIN(p ? p->ctx : nullptr)
     SB_REQUIRE(p && last && out_vabc, "null argument");
     SB_REQUIRE(p->stage == ST_SC1, "round called out of order");
@@ -1311,6 +1512,7 @@ sb_status sb_prover_fourth_round(sb_prover* p, const void* last, void* out_vabc)
     SB_API_END
 }
 sb_status sb_prover_fifth_round(sb_prover* p, const void* r_abc) {
+    if (p && !p->parts.empty()) return multi_call(p->ctx, [=](int r, sb_ctx*) { return sb_prover_fifth_round(p->parts[r], r_abc); });
     SB_API_BEGIN(p ? p->ctx : nullptr)
     SB_REQUIRE(p && r_abc, "null argument");
     SB_REQUIRE(p->stage == ST_R4, "round called out of order");
@@ -1319,6 +1521,13 @@ sb_status sb_prover_fifth_round(sb_prover* p, const void* r_abc) {
     SB_API_END
 }
 sb_status sb_prover_second_sumcheck_round(sb_prover* p, const void* v_msg, void* out_evals) {
+    if (p && !p->parts.empty()) {
+        if (!out_evals) return SB_EINVAL;
+        std::vector<Fr> e(p->parts.size() * 3); Fr* ep = e.data();
+        sb_status st = multi_call(p->ctx, [=](int r, sb_ctx*) { return sb_prover_second_sumcheck_round(p->parts[r], v_msg, ep + 3 * (size_t)r); });
+        if (st == SB_OK) memcpy(out_evals, e.data(), 3 * sizeof(Fr));
+        return st;
+    }
     SB_API_BEGIN(p ? p->ctx : nullptr)
     SB_REQUIRE(p && out_evals, "null argument");
     SB_REQUIRE(p->stage == ST_R5 || p->stage == ST_SC2, "round called out of order");
@@ -1329,6 +1538,14 @@ sb_status sb_prover_second_sumcheck_round(sb_prover* p, const void* v_msg, void*
     SB_API_END
 }
 sb_status sb_prover_sixth_round(sb_prover* p, const sb_pp* pp, const void* last, void* out_z_ry, void* out_proofs) {
+    if (p && !p->parts.empty()) {
+        if (!pp || pp->parts.size() != p->parts.size() || !out_z_ry || !out_proofs) return SB_EINVAL;
+        const size_t G = p->parts.size(), nv = p->log_n;
+        std::vector<Fr> e(G); std::vector<G2Aff> q(G * nv); Fr* ep = e.data(); G2Aff* qp = q.data();
+        sb_status st = multi_call(p->ctx, [=](int r, sb_ctx*) { return sb_prover_sixth_round(p->parts[r], pp->parts[r], last, &ep[r], qp + (size_t)r * nv); });
+        if (st == SB_OK) { memcpy(out_z_ry, &e[0], sizeof(Fr)); memcpy(out_proofs, q.data(), nv * sizeof(G2Aff)); }
+        return st;
+    }
     SB_API_BEGIN(p ? p->ctx : nullptr)
     SB_REQUIRE(p && pp && last && out_z_ry && out_proofs, "null argument");
     SB_REQUIRE(p->stage == ST_SC2 && p->round == p->log_n, "round called out of order");
@@ -1342,6 +1559,8 @@ sb_status sb_prover_sixth_round(sb_prover* p, const sb_pp* pp, const void* last,
     SB_API_END
 }
 sb_status sb_prover_export_abc(sb_prover* p, void* az, void* bz, void* cz) {
+    if (p && !p->parts.empty())     // every shard writes its own slice of the full-size outputs
+        return multi_call(p->ctx, [=](int r, sb_ctx*) { return sb_prover_export_abc(p->parts[r], az, bz, cz); });
     SB_API_BEGIN(p ? p->ctx : nullptr)
     SB_REQUIRE(p && p->abc.p, "Az/Bz/Cz exist only after the third round");
     void* dst[3] = {az, bz, cz};
@@ -1485,14 +1704,55 @@ static void prove_body(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const v
     }
 }
 
+// sb_prove / sb_prove_resident on a multi context: every shard proves (they exchange their partial round polynomials and
+// partial group elements among themselves), all obtain the same bytes, rank 0's are returned.  The trace goes to rank 0;
+// the other ranks only get the Az/Bz/Cz pointers (each shard writes its own slice of those).
+static sb_status multi_prove(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const void* v, size_t nv_len, const void* w, size_t nw_len,
+                             const sb_witness* wt, uint8_t* proof, size_t* len, sb_trace* tr) {
+    const size_t G = ctx->shards.size();
+    if (!ix || !pp || !len || ix->parts.size() != G || pp->parts.size() != G || (wt && wt->parts.size() != G)) { ctx->last_error = "handle does not belong to this multi context"; return SB_EINVAL; }
+    const size_t need = sb_proof_size(ix->log_n);
+    if (!proof || *len < need) { *len = need; ctx->last_error = "proof buffer too small"; return SB_EINVAL; }
+    std::vector<std::vector<uint8_t>> bufs(G, std::vector<uint8_t>(need));
+    std::vector<size_t> lens(G, need);
+    std::vector<sb_trace> traces(G);
+    for (size_t r = 0; r < G; r++) {
+        memset(&traces[r], 0, sizeof(sb_trace));
+        if (tr) { if (r == 0) traces[r] = *tr; else { traces[r].az = tr->az; traces[r].bz = tr->bz; traces[r].cz = tr->cz; } }
+    }
+    std::vector<uint8_t>* bp = bufs.data(); size_t* lp = lens.data(); sb_trace* tp = traces.data();
+    const bool want_trace = tr != nullptr;
+    sb_status st = multi_call(ctx, [=](int r, sb_ctx* sc) {
+        return wt ? sb_prove_resident(sc, ix->parts[r], pp->parts[r], wt->parts[r], bp[r].data(), &lp[r], want_trace ? &tp[r] : nullptr)
+                  : sb_prove(sc, ix->parts[r], pp->parts[r], v, nv_len, w, nw_len, bp[r].data(), &lp[r], want_trace ? &tp[r] : nullptr);
+    });
+    if (st != SB_OK) return st;
+    for (size_t r = 1; r < G; r++)
+        if (lens[r] != lens[0] || memcmp(bufs[r].data(), bufs[0].data(), lens[0]) != 0) { ctx->last_error = "the shards disagree on the proof"; return SB_EINTERNAL; }
+    memcpy(proof, bufs[0].data(), lens[0]); *len = lens[0];
+    if (tr) memcpy(tr->phase_ms, traces[0].phase_ms, sizeof tr->phase_ms);
+    return SB_OK;
+}
+
 extern "C" {
 sb_status sb_prove(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const void* v, size_t nv_len, const void* w, size_t nw_len,
                    uint8_t* proof, size_t* len, sb_trace* tr) {
+    if (ctx && ctx->is_multi()) return multi_prove(ctx, ix, pp, v, nv_len, w, nw_len, nullptr, proof, len, tr);
     SB_API_BEGIN(ctx)
     prove_body(ctx, ix, pp, v, nv_len, w, nw_len, nullptr, proof, len, tr);
     SB_API_END
 }
 sb_status sb_witness_upload(sb_ctx* ctx, const sb_index* ix, const void* v, size_t nv_len, const void* w, size_t nw_len, sb_witness** out) {
+    if (ctx && ctx->is_multi()) {
+        if (!out || !ix || ix->parts.size() != ctx->shards.size()) return SB_EINVAL;
+        std::unique_ptr<sb_witness> wt(new sb_witness);
+        wt->ctx = ctx; wt->n = ix->n; wt->parts.assign(ctx->shards.size(), nullptr);
+        sb_witness** parts = wt->parts.data();
+        sb_status st = multi_call(ctx, [=](int r, sb_ctx* sc) { return sb_witness_upload(sc, ix->parts[r], v, nv_len, w, nw_len, &parts[r]); });
+        if (st != SB_OK) { for (sb_witness* p : wt->parts) sb_witness_destroy(p); return st; }
+        *out = wt.release();
+        return SB_OK;
+    }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && ix && v && out && (w || nw_len == 0), "null argument");
     SB_REQUIRE(nv_len >= 1 && (nv_len & (nv_len - 1)) == 0, "public input should be power of two");
@@ -1509,10 +1769,12 @@ sb_status sb_witness_upload(sb_ctx* ctx, const sb_index* ix, const void* v, size
 }
 void sb_witness_destroy(sb_witness* w) {
     if (!w) return;
+    if (!w->parts.empty()) { for (sb_witness* p : w->parts) sb_witness_destroy(p); delete w; return; }
     cudaSetDevice(w->ctx->device);
     delete w;
 }
 sb_status sb_prove_resident(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const sb_witness* wt, uint8_t* proof, size_t* len, sb_trace* tr) {
+    if (ctx && ctx->is_multi()) return wt ? multi_prove(ctx, ix, pp, nullptr, 0, nullptr, 0, wt, proof, len, tr) : SB_EINVAL;
     SB_API_BEGIN(ctx)
     SB_REQUIRE(wt, "null witness");
     prove_body(ctx, ix, pp, nullptr, 0, nullptr, 0, wt, proof, len, tr);
@@ -1528,7 +1790,11 @@ size_t sb_prof_timeline(char* buf, size_t cap) {
     if (buf && cap) { size_t k = s.size() < cap - 1 ? s.size() : cap - 1; memcpy(buf, s.data(), k); buf[k] = 0; }
     return s.size() + 1;
 }
-void sb_set_serial_msm(sb_ctx* ctx, int on) { if (ctx) ctx->serial_msm = on != 0; }
+void sb_set_serial_msm(sb_ctx* ctx, int on) {
+    if (!ctx) return;
+    ctx->serial_msm = on != 0;
+    for (sb_ctx* sc : ctx->shards) sc->serial_msm = on != 0;
+}
 size_t sb_prof_report(char* buf, size_t cap) {
     std::string s = sb_prof_collect();
     if (buf && cap) { size_t k = s.size() < cap - 1 ? s.size() : cap - 1; memcpy(buf, s.data(), k); buf[k] = 0; }
@@ -1540,6 +1806,7 @@ extern "C" {
 
 // ---------------------------------------------------------------- self-test / measurement hooks
 sb_status sb_field_binop(sb_ctx* ctx, int field, int op, const void* a, const void* b, void* outp, size_t n) {
+    if (ctx && ctx->is_multi()) { ctx->last_error = "this entry point is only available on a single-GPU context"; return SB_EINVAL; }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && a && b && outp && n && (field == 0 || field == 1) && op >= 0 && op <= 3, "bad binop request");
     cudaStream_t st = ctx->stream;
@@ -1555,6 +1822,7 @@ sb_status sb_field_binop(sb_ctx* ctx, int field, int op, const void* a, const vo
 }
 
 sb_status sb_mul_bench(sb_ctx* ctx, int field, size_t n_threads, int iters, double* out_ms) {
+    if (ctx && ctx->is_multi()) { ctx->last_error = "this entry point is only available on a single-GPU context"; return SB_EINVAL; }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && out_ms && n_threads && iters > 0 && (field == 0 || field == 1), "bad bench request");
     cudaStream_t st = ctx->stream;
@@ -1582,6 +1850,7 @@ __global__ void k_flush_l2(uint4* buf, size_t n16) {
 }
 
 sb_status sb_kernel_bench(sb_ctx* ctx, int which, uint32_t log_m, int reps, int flush_l2, double* out_ms_avg) {
+    if (ctx && ctx->is_multi()) { ctx->last_error = "this entry point is only available on a single-GPU context"; return SB_EINVAL; }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && out_ms_avg && which >= 0 && which <= 3 && log_m >= 4 && log_m <= 28 && reps >= 1, "bad kernel bench request");
     cudaStream_t st = ctx->stream;

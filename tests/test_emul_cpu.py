@@ -74,3 +74,13 @@ def test_sharded_prover_under_emulation(emul_env, world, oracle):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+def test_multi_context_one_process_under_emulation(emul_env):
+    # sb_ctx_create_multi: one context over 2 / 4 (emulated) devices of ONE process, worker thread per device, in-process
+    # exchange; proof bytes and traced intermediates equal the oracle's, error mapping preserved
+    e = dict(emul_env, SB_EMUL_DEVICES="8")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_multi.py"), "-m", "gpu", "-x", "-q", "-k",
+                        "multi_context_one_process_2gpu or multi_context_one_process_4gpu"], env=e, cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])
+    assert "2 passed" in r.stdout, r.stdout[-500:]
