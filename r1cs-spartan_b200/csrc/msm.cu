@@ -637,17 +637,19 @@ static bool msm_sorted() { static const bool v = msm_env_u32("SB_MSM_SORTED", 1,
 static uint32_t msm_s1_min() { static const uint32_t v = msm_env_u32("SB_MSM_S1", 3, 2, 4096); return v; }
 // accumulation levels a pipeline launches; the device raises S1 when that many levels of the minimal S1 would not
 // cover the longest run (S0 * 3^4 = 3888 entries per bucket at the defaults, 10x the runs of uniform scalars)
-// Pairwise affine rounds (see k_affine_round): R rounds for G2 groups of at least 2^SB_MSM_AFFINE_LOG2 entries, each thread
-// sharing one inversion among at most SB_MSM_AFFINE_K additions.  Over Fq (G1) the inversion costs 16 additions instead of
-// 5 and the saving per addition is the same 40 %, so G1 groups only take the rounds when SB_MSM_AFFINE_G1=1.
+// Pairwise affine rounds (see k_affine_round): R rounds for groups of at least 2^SB_MSM_AFFINE_LOG2 entries, each thread
+// sharing one inversion among at most SB_MSM_AFFINE_K additions.  Measured on B200 at 2^20 constraints (round 2, gpurun sweep 5):
+// R = 0: 49.3 ms per proof; R = 4, K = 128: 47.0; R = 4, K = 256: 41.8; R = 5: 42.2; R = 4, K = 256 and the G1 commitment
+// too: 41.4 -- the defaults.  Below 2^21 entries per group (2^17 constraints) the rounds lose a few percent (too few threads
+// left in the later rounds) and stay off.  SB_MSM_AFFINE_ROUNDS=0 disables them; SB_MSM_AFFINE_G1=0 keeps G1 on XYZZ.
 template <class F>
 static uint32_t msm_affine_rounds(uint64_t etot) {
-    static const uint32_t lg = msm_env_u32("SB_MSM_AFFINE_LOG2", 21, 0, 40), rounds = msm_env_u32("SB_MSM_AFFINE_ROUNDS", 0, 0, MSM_MAX_HALVINGS);
-    static const bool g1 = msm_env_u32("SB_MSM_AFFINE_G1", 0, 0, 1) != 0;
+    static const uint32_t lg = msm_env_u32("SB_MSM_AFFINE_LOG2", 21, 0, 40), rounds = msm_env_u32("SB_MSM_AFFINE_ROUNDS", 4, 0, MSM_MAX_HALVINGS);
+    static const bool g1 = msm_env_u32("SB_MSM_AFFINE_G1", 1, 0, 1) != 0;
     if (sizeof(F) != sizeof(Fq2) && !g1) return 0;
     return etot >= ((uint64_t)1 << lg) ? rounds : 0;
 }
-static uint32_t msm_affine_kmax() { static const uint32_t v = msm_env_u32("SB_MSM_AFFINE_K", 128, 1, 1024); return v; }
+static uint32_t msm_affine_kmax() { static const uint32_t v = msm_env_u32("SB_MSM_AFFINE_K", 256, 1, 1024); return v; }
 static uint32_t msm_nlaunch() { static const uint32_t v = msm_env_u32("SB_MSM_LEVELS", 5, 2, MSM_MAX_LEVELS); return v; }
 
 template <class F>

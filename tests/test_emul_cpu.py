@@ -53,6 +53,7 @@ def test_product_kernels_match_oracle_under_emulation(emul_env):
     {"SB_MSM_S0": "2", "SB_MSM_S1": "2", "SB_MSM_LEVELS": "2"},                       # two launched levels: the device must raise S1
     {"SB_MSM_S0": "3", "SB_MSM_S1": "2", "SB_MSM_LEVELS": "8", "SB_MSM_SORTED": "0", "SB_MSM_RED_L": "8"},
     {"SB_MSM_SPLIT": "3", "SB_MSM_SPLIT_MIN_NV": "2", "SB_MSM_S0": "5"},                # opening ladders split into three pipelines
+    {"SB_MSM_AFFINE_LOG2": "3", "SB_MSM_AFFINE_ROUNDS": "3", "SB_MSM_AFFINE_K": "3", "SB_MSM_S0": "4"},   # pairwise affine rounds in front of the accumulation (G1 and G2)
 ])
 def test_msm_pipeline_knobs_under_emulation(emul_env, knobs):
     _pytest_gpu_subset(emul_env, "msm_matches or structured or adversarial or commit_and_open or padded or prove_bytes_and_trace_match_oracle[6", knobs)

@@ -493,12 +493,14 @@ def test_full_size_prove_is_bit_exact_and_accepted(sb, oracle, gpu_ctx, log_n):
 
 
 def test_msm_knobs_forced_on_small_inputs():
-    # The batched-affine pairwise rounds are off by default and the deep accumulation levels only appear with
-    # long bucket runs; force both on the small parity cases (tiny chunk sizes = many levels), in a fresh
-    # process because the knobs are read once.
+    # The batched-affine pairwise rounds only switch on for groups of >= 2^21 (window, point) pairs and the deep
+    # accumulation levels only appear with long bucket runs; force both on the small parity cases (tiny chunk
+    # sizes = many levels; 1..6 rounds, shares of 1..256 additions per inversion), in a fresh process because the
+    # knobs are read once.
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for extra in ({"SB_MSM_AFFINE_LOG2": "5"}, {"SB_MSM_AFFINE_LOG2": "3", "SB_MSM_S0": "3", "SB_MSM_S1": "2"},
+    for extra in ({"SB_MSM_AFFINE_LOG2": "5"}, {"SB_MSM_AFFINE_LOG2": "3", "SB_MSM_S0": "3", "SB_MSM_S1": "2", "SB_MSM_AFFINE_ROUNDS": "2", "SB_MSM_AFFINE_K": "3"},
+                  {"SB_MSM_AFFINE_LOG2": "0", "SB_MSM_AFFINE_ROUNDS": "6", "SB_MSM_AFFINE_K": "1"}, {"SB_MSM_AFFINE_ROUNDS": "0"},
                   {"SB_MSM_S0": "2", "SB_MSM_S1": "2", "SB_MSM_RED_L": "8", "SB_MSM_ORDER": "0", "SB_MSM_SORTED": "0"}):
         env = dict(os.environ, **extra)
         r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
