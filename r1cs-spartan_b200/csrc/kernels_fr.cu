@@ -304,16 +304,36 @@ k_sc_round(const Fr* __restrict__ A, const Fr* __restrict__ B, const Fr* __restr
     reduce_finish<3>(acc, out3, block_partials, ticket, flag, seq);
 }
 
+// CTA size of a round over h work items.  The tables are powers of two and the machine is not: with 148 SMs x 2 CTAs x 256
+// threads, 2^18 items are 3.46 per thread -- the last of four passes runs 46 % full and the kernel cannot exceed 86 % of
+// its own inner-loop rate (round 1 measured 0.58 / 0.50 of the Fr-product ceiling at 2^20 against 0.73-0.77 at 2^22).
+// 224-thread CTAs make 2^k items 0.988 x an integer number of passes for every k >= 16; the choice below takes the
+// CTA size (a multiple of a warp) whose last pass is fullest.  SB_SC_BLOCK forces a size.
+static int sc_block_for(size_t h, int cps) {
+    static const int forced = getenv("SB_SC_BLOCK") ? atoi(getenv("SB_SC_BLOCK")) : 0;
+    if (forced >= 32 && forced <= 256 && forced % 32 == 0) return forced;
+    int best = 256;
+    double best_eff = 0;
+    for (int blk = 256; blk >= 160; blk -= 32) {
+        const double x = (double)h / ((double)SB_SMS * cps * blk);
+        if (x <= 1.0) return best_eff > 0 ? best : 256;
+        const double eff = x / (double)(size_t)(x + 0.999999);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = blk; }
+    }
+    return best;
+}
 template <int KIND>
 static void launch_sc_round(const Fr* A, const Fr* B, const Fr* C, Fr* Ao, Fr* Bo, Fr* Co, const Fr* E, const Fr* r_host,
                             size_t m_in, const RoundOut& o, const RoundWs& ws, cudaStream_t stream) {
     const bool fold = r_host != nullptr;
     const Fr r = fold ? *r_host : Fr::zero();
     size_t h = fold ? m_in / 4 : m_in / 2;
-    int grid = grid_for(h, 256, ws.max_grid / SB_SMS > 1 ? ws.max_grid / SB_SMS : 1);   // 2 resident CTAs per SM by default
+    const int cps = ws.max_grid / SB_SMS > 1 ? ws.max_grid / SB_SMS : 1;                  // 2 resident CTAs per SM by default
+    const int block = sc_block_for(h, cps);
+    int grid = grid_for(h, block, cps);
     if (grid > ws.max_grid) grid = ws.max_grid;
-    if (fold) SB_LAUNCH_NAMED(KIND == 1 ? "k_sc_round<sc1,fold>" : "k_sc_round<sc2,fold>", (k_sc_round<KIND, true>), grid, 256, 0, stream, A, B, C, Ao, Bo, Co, E, r, h, o.out, ws.block_partials, ws.ticket, o.flag, o.seq);
-    else SB_LAUNCH_NAMED(KIND == 1 ? "k_sc_round<sc1,first>" : "k_sc_round<sc2,first>", (k_sc_round<KIND, false>), grid, 256, 0, stream, A, B, C, Ao, Bo, Co, E, r, h, o.out, ws.block_partials, ws.ticket, o.flag, o.seq);
+    if (fold) SB_LAUNCH_NAMED(KIND == 1 ? "k_sc_round<sc1,fold>" : "k_sc_round<sc2,fold>", (k_sc_round<KIND, true>), grid, block, 0, stream, A, B, C, Ao, Bo, Co, E, r, h, o.out, ws.block_partials, ws.ticket, o.flag, o.seq);
+    else SB_LAUNCH_NAMED(KIND == 1 ? "k_sc_round<sc1,first>" : "k_sc_round<sc2,first>", (k_sc_round<KIND, false>), grid, block, 0, stream, A, B, C, Ao, Bo, Co, E, r, h, o.out, ws.block_partials, ws.ticket, o.flag, o.seq);
 }
 void launch_sc1_round(const Fr* A, const Fr* B, const Fr* C, Fr* Ao, Fr* Bo, Fr* Co, const Fr* E, const Fr* r_host,
                       size_t m_in, const RoundOut& o, const RoundWs& ws, cudaStream_t stream) {

@@ -500,22 +500,124 @@ __device__ XyzzPt<F> mul_small(const XyzzPt<F>& p, uint32_t k) {
     return k ? acc : XyzzPt<F>::inf();
 }
 
-// ------------------------------------------------------------------ bucket reduction: sum_b (b + 1) B_b per slot
-constexpr int RED_THREADS = 64;
-// tree-sum RED_THREADS points held one per thread; result valid in thread 0
+// ------------------------------------------------------------------ quad-cooperative point arithmetic (latency-bound stages)
+// The bucket reduction is a chain of DEPENDENT point operations whatever the MSM size.  On one thread a G2 addition is 14
+// Fq2 products one after another (~18 k instructions, 25-30 us on a lone warp), and round 1 measured the two reduction
+// kernels at 1.2 + 0.65 ms per pipeline -- the latency floor of every commitment and opening, and what held the 8-GPU
+// efficiency at 0.42.  Here FOUR adjacent lanes (a "quad") share every operation: each stage of the XYZZ formulas has up
+// to four independent products, each lane takes one, and the results travel by warp shuffles -- 4 product latencies per
+// addition instead of 14, 3 per doubling instead of 9.  All four lanes hold the same inputs and obtain the same result.
+// Every lane of a warp must call these together (the shuffles are warp-wide); the exceptional cases of the group law
+// are resolved by selection AFTER the common path, so the calls never diverge.
 template <class F>
-__device__ XyzzPt<F> block_tree_sum(XyzzPt<F> v, XyzzPt<F>* sh) {
-    sh[threadIdx.x] = v;
+SB_D F quad_pick(int r, const F& a0, const F& a1, const F& a2, const F& a3) {
+    F o;
+    const uint32_t* p0 = reinterpret_cast<const uint32_t*>(&a0); const uint32_t* p1 = reinterpret_cast<const uint32_t*>(&a1);
+    const uint32_t* p2 = reinterpret_cast<const uint32_t*>(&a2); const uint32_t* p3 = reinterpret_cast<const uint32_t*>(&a3);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(F) / 4); i++) d[i] = r == 0 ? p0[i] : r == 1 ? p1[i] : r == 2 ? p2[i] : p3[i];
+    return o;
+}
+// add-2008-s, one product per lane and stage
+template <class F>
+__device__ __noinline__ XyzzPt<F> quad_add(const XyzzPt<F>& p, const XyzzPt<F>& q) {
+    const int lane = threadIdx.x & 31, r = lane & 3, base = lane & ~3;
+    const F m1 = F::mul(quad_pick(r, p.X, q.X, p.Y, q.Y), quad_pick(r, q.ZZ, p.ZZ, q.ZZZ, p.ZZZ));
+    const F U1 = shfl_elem(m1, base), U2 = shfl_elem(m1, base + 1), S1 = shfl_elem(m1, base + 2), S2 = shfl_elem(m1, base + 3);
+    const F Pp = F::sub(U2, U1), R = F::sub(S2, S1);
+    const F m2 = F::mul(quad_pick(r, Pp, p.ZZ, R, p.ZZZ), quad_pick(r, Pp, q.ZZ, R, q.ZZZ));      // PP, ZZ1 ZZ2, R^2, ZZZ1 ZZZ2
+    const F PP = shfl_elem(m2, base), RR = shfl_elem(m2, base + 2);
+    const F m3 = F::mul(quad_pick(r, Pp, m2, U1, m2), PP);                                         // PPP, ZZ3, Q, (unused)
+    const F PPP = shfl_elem(m3, base), Q = shfl_elem(m3, base + 2);
+    XyzzPt<F> o;
+    o.X = F::sub(F::sub(RR, PPP), F::dbl(Q));
+    const F m4 = F::mul(quad_pick(r, S1, S1, R, m2), quad_pick(r, PPP, PPP, F::sub(Q, o.X), PPP)); // S1 PPP, (unused), R (Q - X3), ZZZ3
+    o.Y = F::sub(shfl_elem(m4, base + 2), shfl_elem(m4, base));
+    o.ZZ = shfl_elem(m3, base + 1);
+    o.ZZZ = shfl_elem(m4, base + 3);
+    if (p.is_inf()) return q;
+    if (q.is_inf()) return p;
+    if (Pp.is_zero()) return R.is_zero() ? XyzzPt<F>::dbl(p) : XyzzPt<F>::inf();     // (no shuffles inside: may diverge)
+    return o;
+}
+// dbl-2008-s-1
+template <class F>
+__device__ __noinline__ XyzzPt<F> quad_dbl(const XyzzPt<F>& p) {
+    const int lane = threadIdx.x & 31, r = lane & 3, base = lane & ~3;
+    const F U = F::dbl(p.Y);
+    const F m1 = F::mul(quad_pick(r, U, p.X, U, U), quad_pick(r, U, p.X, U, U));                   // V = U^2, XX
+    const F V = shfl_elem(m1, base), XX = shfl_elem(m1, base + 1);
+    const F M = F::add(F::dbl(XX), XX);
+    const F m2 = F::mul(quad_pick(r, U, p.X, M, p.ZZ), quad_pick(r, V, V, M, V));                  // W, S, M^2, ZZ3
+    const F W = shfl_elem(m2, base), S = shfl_elem(m2, base + 1), MM = shfl_elem(m2, base + 2);
+    XyzzPt<F> o;
+    o.X = F::sub(MM, F::dbl(S));
+    const F m3 = F::mul(quad_pick(r, M, W, W, W), quad_pick(r, F::sub(S, o.X), p.Y, p.ZZZ, p.Y));  // M (S - X3), W Y, ZZZ3, (unused)
+    o.Y = F::sub(shfl_elem(m3, base), shfl_elem(m3, base + 1));
+    o.ZZ = shfl_elem(m2, base + 3);
+    o.ZZZ = shfl_elem(m3, base + 2);
+    if (p.is_inf()) return p;
+    return o;
+}
+// k * p for a small k that is the same in every lane of the warp
+template <class F>
+__device__ XyzzPt<F> quad_mul_small(const XyzzPt<F>& p, uint32_t k) {
+    if (k == 0) return XyzzPt<F>::inf();
+    XyzzPt<F> acc = p;
+    for (int bit = 30 - __clz(k); bit >= 0; bit--) {
+        acc = quad_dbl(acc);
+        if ((k >> bit) & 1) acc = quad_add(acc, p);
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------ bucket reduction: sum_b (b + 1) B_b per slot
+// Two stages of quads.  Stage 1: a CTA of RED_QUADS quads owns G = RED_QUADS * L consecutive buckets of one slot, quad t the
+// buckets [t L, (t + 1) L) of them.  With i = t L + j the local index of a bucket,
+//     sum_i (i + 1) B_i = sum_t [ sum_j (j + 1) B_{tL+j} ] + L * sum_t t * run_t,     run_t = sum_j B_{tL+j},
+// the inner sums are running sums (2 L additions per quad), and sum_t t * run_t = sum_{t >= 1} (run_t + run_{t+1} + ...) is a
+// suffix scan over the quads (log2 RED_QUADS steps in shared memory) followed by one tree.  The CTA writes A_c (the local sum
+// above) and R_c = the sum of its buckets.  Stage 2 (one CTA per slot) does the same to the CTAs: total = sum_c A_c + G sum_c c R_c.
+// Depth: 2 L + 2 log2(RED_QUADS) + 3 quad operations in stage 1 and about 30 in stage 2, ~7 us each, whatever the MSM size
+// (round 1: 2 L + ~22 doublings/additions of mul_small + 6 tree levels on single threads, ~30 us each).
+constexpr int RED_QUADS = 64, RED_THREADS = 4 * RED_QUADS;
+// suffix scan over the quads of a CTA: returns sum_{t' >= quad} v_{t'}; sh holds RED_QUADS points
+template <class F>
+__device__ XyzzPt<F> quad_block_suffix_scan(XyzzPt<F> v, XyzzPt<F>* sh) {
+    const uint32_t qd = threadIdx.x >> 2, r = threadIdx.x & 3;
+    if (r == 0) st_elem(&sh[qd], v);
     __syncthreads();
-    for (int stride = RED_THREADS / 2; stride > 0; stride >>= 1) {
-        if ((int)threadIdx.x < stride) sh[threadIdx.x] = XyzzPt<F>::add(sh[threadIdx.x], sh[threadIdx.x + stride]);
+    for (uint32_t off = 1; off < (uint32_t)RED_QUADS; off <<= 1) {
+        XyzzPt<F> o = XyzzPt<F>::inf();
+        if (qd + off < (uint32_t)RED_QUADS) o = sh[qd + off];
+        __syncthreads();
+        v = quad_add(v, o);
+        if (r == 0) st_elem(&sh[qd], v);
         __syncthreads();
     }
-    return sh[0];
+    return v;
 }
-// stage 1: thread t of a slot owns its buckets [t L, (t+1) L): sum_b (b+1) B_b = running sums + (t L) * (sum of its B_b).
+// tree sum over the quads of a CTA; the result is valid in quad 0
+template <class F>
+__device__ XyzzPt<F> quad_block_tree_sum(XyzzPt<F> v, XyzzPt<F>* sh) {
+    const uint32_t qd = threadIdx.x >> 2, r = threadIdx.x & 3;
+    __syncthreads();
+    if (r == 0) st_elem(&sh[qd], v);
+    __syncthreads();
+    for (uint32_t stride = RED_QUADS / 2; stride > 0; stride >>= 1) {
+        if ((qd & ~7u) < stride) {                  // whole warps (8 quads) drop out once they hold no active quad; idle quads of a live warp add infinity
+            XyzzPt<F> o = XyzzPt<F>::inf();
+            if (qd < stride) o = sh[qd + stride];
+            v = quad_add(v, o);
+            if (qd < stride && r == 0) st_elem(&sh[qd], v);
+        }
+        __syncthreads();
+    }
+    return v;
+}
 // CTA -> slot by the slots' rbase; the final points of the accumulation are found through the device-side plan
-// (levels = info[3]: the last level's output buffer and chunk plan).
+// (levels = info[3]: the last level's output buffer and chunk plan).  block_out[2 c] = A_c, block_out[2 c + 1] = R_c.
 template <class F>
 __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce1(const XyzzPt<F>* __restrict__ ptsA, const XyzzPt<F>* __restrict__ ptsB, PlanPtrs pp,
                                                                 const MsmSlot* __restrict__ slots, uint32_t nslots, XyzzPt<F>* __restrict__ block_out) {
@@ -528,35 +630,49 @@ __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce1(const XyzzPt<F>*
     const uint32_t levels = __ldg(&pp.info[3]);
     const XyzzPt<F>* pts = ((levels - 1) & 1) ? ptsB : ptsA;
     const uint32_t* off = pp.plan[levels - 1];
-    const uint32_t t = (blockIdx.x - __ldg(&sl->rbase)) * blockDim.x + threadIdx.x;
-    const uint64_t lo = (uint64_t)t * L;
-    XyzzPt<F> total = XyzzPt<F>::inf();
-    if (lo < B) {
-        const uint32_t hi = (uint32_t)min((uint64_t)B, lo + L);
-        XyzzPt<F> run = XyzzPt<F>::inf(), sum = XyzzPt<F>::inf();
-        for (uint32_t b = hi; b-- > (uint32_t)lo;) {
-            const uint32_t k = pp.invperm ? __ldg(&pp.invperm[bbase + b]) : bbase + b;      // bucket -> position in the accumulation order
+    const uint32_t qd = threadIdx.x >> 2;
+    const uint64_t lo = ((uint64_t)(blockIdx.x - __ldg(&sl->rbase)) * RED_QUADS + qd) * L;
+    XyzzPt<F> run = XyzzPt<F>::inf(), sum = XyzzPt<F>::inf();
+    for (uint32_t jj = L; jj-- > 0;) {
+        const uint64_t b = lo + jj;
+        XyzzPt<F> v = XyzzPt<F>::inf();
+        if (b < B) {
+            const uint32_t k = pp.invperm ? __ldg(&pp.invperm[bbase + (uint32_t)b]) : bbase + (uint32_t)b;      // bucket -> position in the accumulation order
             const uint32_t o = __ldg(&off[k]);
-            if (__ldg(&off[k + 1]) > o) run = XyzzPt<F>::add(run, ldg_elem(&pts[o]));
-            sum = XyzzPt<F>::add(sum, run);
+            if (__ldg(&off[k + 1]) > o) v = ldg_elem(&pts[o]);
         }
-        total = XyzzPt<F>::add(sum, mul_small(run, (uint32_t)lo));
+        run = quad_add(run, v);
+        sum = quad_add(sum, run);
     }
-    XyzzPt<F> r = block_tree_sum(total, sh);
-    if (threadIdx.x == 0) st_elem(&block_out[blockIdx.x], r);
+    const XyzzPt<F> suf = quad_block_suffix_scan(run, sh);            // quad 0: R_c
+    const XyzzPt<F> v = quad_add(sum, quad_mul_small(qd ? suf : XyzzPt<F>::inf(), L));
+    const XyzzPt<F> a = quad_block_tree_sum(v, sh);
+    if (threadIdx.x == 0) { st_elem(&block_out[2 * (size_t)blockIdx.x], a); st_elem(&block_out[2 * (size_t)blockIdx.x + 1], suf); }
 }
-// stage 2: one CTA per slot sums the slot's stage-1 results
+// stage 2: one CTA per slot; quad q takes the stage-1 CTAs [q cpt, (q + 1) cpt) of the slot
 template <class F>
 __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce2(const XyzzPt<F>* __restrict__ block_out, const MsmSlot* __restrict__ slots,
                                                                 XyzzPt<F>* __restrict__ out) {
     SB_DYN_SMEM(smem_raw);
     XyzzPt<F>* sh = reinterpret_cast<XyzzPt<F>*>(smem_raw);
     const MsmSlot* sl = slots + blockIdx.x;
-    const uint32_t r0 = __ldg(&sl->rbase), nblocks = __ldg(&sl->rblocks);
-    XyzzPt<F> acc = XyzzPt<F>::inf();
-    for (uint32_t i = threadIdx.x; i < nblocks; i += blockDim.x) acc = XyzzPt<F>::add(acc, ldg_elem(&block_out[r0 + i]));
-    XyzzPt<F> r = block_tree_sum(acc, sh);
-    if (threadIdx.x == 0) st_elem(&out[blockIdx.x], r);
+    const uint32_t r0 = __ldg(&sl->rbase), nblocks = __ldg(&sl->rblocks), L = __ldg(&sl->red_l);
+    const uint32_t cpt = (nblocks + RED_QUADS - 1) / RED_QUADS, qd = threadIdx.x >> 2;
+    XyzzPt<F> accA = XyzzPt<F>::inf(), run = XyzzPt<F>::inf(), sum = XyzzPt<F>::inf();       // sum_c A_c, sum_j R_{q cpt + j}, sum_j j R_{q cpt + j}
+    for (uint32_t jj = cpt; jj-- > 0;) {
+        const uint32_t c = qd * cpt + jj;
+        XyzzPt<F> a = XyzzPt<F>::inf(), rr = XyzzPt<F>::inf();
+        if (c < nblocks) { a = ldg_elem(&block_out[2 * (size_t)(r0 + c)]); rr = ldg_elem(&block_out[2 * (size_t)(r0 + c) + 1]); }
+        accA = quad_add(accA, a);
+        run = quad_add(run, rr);
+        if (jj >= 1) sum = quad_add(sum, run);
+    }
+    const XyzzPt<F> suf = quad_block_suffix_scan(run, sh);
+    // sum_c c R_c = sum_q [ sum_j j R + cpt * q * run_q ]; the total weighs it by G = RED_QUADS * L buckets per stage-1 CTA
+    XyzzPt<F> v = quad_add(sum, quad_mul_small(qd ? suf : XyzzPt<F>::inf(), cpt));
+    v = quad_add(accA, quad_mul_small(v, RED_QUADS * L));
+    const XyzzPt<F> total = quad_block_tree_sum(v, sh);
+    if (threadIdx.x == 0) st_elem(&out[blockIdx.x], total);
 }
 
 // ------------------------------------------------------------------ base expansion / affine conversion
@@ -664,13 +780,11 @@ void msm_group_prepare(const std::vector<const AffinePt<F>*>& bases_dev, const s
         SB_REQUIRE(ms[j] >= 1 && ms[j] < ((size_t)1 << 31), "msm: slot size out of range");
         s.m = (uint32_t)ms[j]; s.lay = msm_layout(ms[j]);
         s.nb = 1u << (s.lay.c - 1);
-        // buckets per thread in the first reduction stage: each thread pays 2 L additions for its running sums and
-        // ~1.5 log2(B) for the multiplication by its offset; small L = short chain, large L = less total work
-        // (measured in round 1: L = 2 wins below 2^18 points, L = 4 above)
-        const uint32_t red_l = red_env ? red_env : (ms[j] >= ((size_t)1 << 18) ? 4u : 2u);
-        s.red_l = s.nb >= red_l * RED_THREADS ? red_l : 1;
-        const uint32_t nthreads = (s.nb + s.red_l - 1) / s.red_l;
-        s.rblocks = (nthreads + RED_THREADS - 1) / RED_THREADS;
+        // buckets per quad in the first reduction stage (see k_bucket_reduce1): 2 L chained additions per quad
+        const uint32_t red_l = red_env ? red_env : 4u;
+        s.red_l = s.nb >= red_l * RED_QUADS ? red_l : 1;
+        const uint32_t nquads = (s.nb + s.red_l - 1) / s.red_l;
+        s.rblocks = (nquads + RED_QUADS - 1) / RED_QUADS;
         s.mbase = (uint32_t)mtot; s.ebase = (uint32_t)etot; s.bbase = (uint32_t)btot; s.rbase = (uint32_t)rtot;
         mtot += s.m; etot += (uint64_t)s.lay.W * s.m; btot += s.nb; rtot += s.rblocks;
     }
@@ -723,7 +837,7 @@ void msm_group_prepare(const std::vector<const AffinePt<F>*>& bases_dev, const s
     for (uint32_t l = 0; l < msm_nlaunch(); l++) sc.plan[l].alloc(btot + 1, stream);
     sc.ptsA.alloc(std::max<uint32_t>(out.items_bound[0], 1), stream);
     sc.ptsB.alloc(std::max<uint32_t>(out.items_bound[1], 1), stream);
-    sc.block_out.alloc(rtot, stream);
+    sc.block_out.alloc(2 * (size_t)rtot, stream);
     if (out.R) {
         const size_t nC = (btot + PLAN_TILE - 1) / PLAN_TILE;
         sc.cta_hsum.alloc(nC * out.R, stream);
@@ -814,7 +928,7 @@ void msm_group_tail(const MsmGroup<F>& g, XyzzPt<F>* out_dev, cudaStream_t strea
         SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, false>), grid, ACC_THREADS, 0, stream, g.tab.get(), sc.sorted.get(),
                         (const AffinePt<F>*)nullptr, inp, sc.plan[l - 1].get(), sc.plan[l].get(), B, l, sc.info.get(), (const uint32_t*)nullptr, outp);
     }
-    const size_t smem = RED_THREADS * sizeof(XyzzPt<F>);
+    const size_t smem = RED_QUADS * sizeof(XyzzPt<F>);
     SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce1"), (k_bucket_reduce1<F>), (int)g.rtot, RED_THREADS, smem, stream, sc.ptsA.get(), sc.ptsB.get(), pp,
                     g.slots_dev.get(), J, sc.block_out.get());
     SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce2"), (k_bucket_reduce2<F>), (int)J, RED_THREADS, smem, stream, sc.block_out.get(), g.slots_dev.get(), out_dev);
