@@ -93,6 +93,9 @@ int sb_device_count(void);
  * matrices into the Fiat-Shamir transcript once (src/lib.rs:62-64) and keeps the hash state. */
 sb_status sb_index_create(sb_ctx* ctx, uint32_t log_n, const sb_csr* a, const sb_csr* b, const sb_csr* c, sb_index** out);
 void sb_index_destroy(sb_index* idx);
+/* wall time of sb_index_create, in two parts: validation + device-side plan construction (upload included), and what the
+ * transcript hash of the matrices (a serial BLAKE2s chain on a host thread, running beside the former) added after it */
+void sb_index_timing(const sb_index* idx, double* plan_ms, double* hash_wait_ms);
 
 /* ---- public parameters ------------------------------------------------------------------------ */
 /* Load a reference PublicParameter (src/commitment/data_structures.rs:10-17):

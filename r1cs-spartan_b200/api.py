@@ -24,7 +24,7 @@ SB_OK, SB_EINVAL, SB_ECUDA, SB_ENOMEM, SB_ECOMM, SB_EINTERNAL = range(6)
 
 EXPORTS = [
     "sb_ctx_create", "sb_ctx_create_sharded", "sb_ctx_create_multi", "sb_ctx_destroy", "sb_last_error", "sb_launch_count", "sb_device_count",
-    "sb_index_create", "sb_index_destroy", "sb_pp_load", "sb_pp_keygen", "sb_pp_export", "sb_pp_export_g_mask",
+    "sb_index_create", "sb_index_destroy", "sb_index_timing", "sb_pp_load", "sb_pp_keygen", "sb_pp_export", "sb_pp_export_g_mask",
     "sb_pp_destroy", "sb_commit", "sb_open", "sb_msm", "sb_eq_table", "sb_sum_over_y", "sb_eval_on_x",
     "sb_prover_init", "sb_prover_destroy", "sb_prover_first_round", "sb_prover_second_round", "sb_prover_third_round",
     "sb_prover_first_sumcheck_round", "sb_prover_fourth_round", "sb_prover_fifth_round",
@@ -80,6 +80,7 @@ def load_library():
         L.sb_proof_size.argtypes = [C.c_uint32]
         L.sb_prof_report.restype = C.c_size_t
         L.sb_copy_counters.restype = None
+        L.sb_index_timing.restype = None
         _lib = L
     return _lib
 
@@ -236,6 +237,12 @@ class IndexPK:
             pass
 
     # MatrixExtension.sum_over_y x3
+    def timing(self):
+        """(plan_ms, hash_wait_ms) of the index call: device-side plans incl. upload, and the transcript hash's extra wait"""
+        a, b = C.c_double(), C.c_double()
+        load_library().sb_index_timing(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
     def sum_over_y(self, z):
         z = _fr(z, self.n)
         out = [np.empty((self.n, 4), dtype=np.uint64) for _ in range(3)]

@@ -308,10 +308,11 @@ k_sc_round(const Fr* __restrict__ A, const Fr* __restrict__ B, const Fr* __restr
 // threads, 2^18 items are 3.46 per thread -- the last of four passes runs 46 % full and the kernel cannot exceed 86 % of
 // its own inner-loop rate (round 1 measured 0.58 / 0.50 of the Fr-product ceiling at 2^20 against 0.73-0.77 at 2^22).
 // 224-thread CTAs make 2^k items 0.988 x an integer number of passes for every k >= 16; the choice below takes the
-// CTA size (a multiple of a warp) whose last pass is fullest.  SB_SC_BLOCK forces a size.
+// CTA size (a multiple of a warp) whose last pass is fullest.  SB_SC_BLOCK forces a size.  OFF by default: see below.
 static int sc_block_for(size_t h, int cps) {
     static const int forced = getenv("SB_SC_BLOCK") ? atoi(getenv("SB_SC_BLOCK")) : 0;
     if (forced >= 32 && forced <= 256 && forced % 32 == 0) return forced;
+    if (forced != 1) return 256;     // measured (round 2, sweep 7): the fuller last pass does not pay for 14 instead of 16 warps per SM (0.552 against 0.589 of the ceiling at 2^20); SB_SC_BLOCK=1 turns the choice below on
     int best = 256;
     double best_eff = 0;
     for (int blk = 256; blk >= 160; blk -= 32) {

@@ -410,12 +410,11 @@ __device__ __forceinline__ int pair_classify_x(const F& px, const F& qx, bool ha
 template <class F, bool FIRST>
 __global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
                                                               const AffinePt<F>* __restrict__ in_aff, const uint32_t* __restrict__ in_off,
-                                                              const uint32_t* __restrict__ out_off, uint32_t B, uint32_t nthreads, uint32_t K,
+                                                              const uint32_t* __restrict__ out_off, uint32_t B, uint32_t nthreads, uint32_t prefetch,
                                                               F* __restrict__ prefix, AffinePt<F>* __restrict__ out_aff) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = out_off[B];
     const uint32_t per = (total + nthreads - 1) / nthreads;
-    (void)K;
     if (t >= nthreads || per == 0) return;
     const uint64_t first64 = (uint64_t)(t & ~31u) * per + (t & 31u);      // this lane's first output
     if (first64 >= total) return;
@@ -438,38 +437,55 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>*
         uint32_t mid = (lo + hi) >> 1;
         if (__ldg(&out_off[mid]) <= first) lo = mid; else hi = mid;
     }
-    // pass 1: prefix products of the denominators (x coordinates only)
-    F acc = F::one();
+    // the two inputs of output p (the bucket cursor b moves with p: forwards in the first pass, backwards in the second)
+    struct Pair { const AffinePt<F>* p0; const AffinePt<F>* p1; bool has2, n0, n1; };
     uint32_t b = lo;
-    for (uint32_t i = 0; i < iters; i++) {
-        const uint32_t p = first + 32 * i;
+    auto locate = [&](uint32_t p) -> Pair {
         while (__ldg(&out_off[b + 1]) <= p) b++;
+        while (__ldg(&out_off[b]) > p) b--;
         const uint32_t j = p - __ldg(&out_off[b]);
         const uint32_t ib = __ldg(&in_off[b]), n_in = __ldg(&in_off[b + 1]) - ib;
-        const bool has2 = 2 * j + 1 < n_in;
-        bool n0, n1 = false;
-        const AffinePt<F>* pp0 = in_ptr(ib + 2 * j, n0);
-        const AffinePt<F>* pp1 = has2 ? in_ptr(ib + 2 * j + 1, n1) : pp0;
+        Pair pr;
+        pr.has2 = 2 * j + 1 < n_in; pr.n1 = false;
+        pr.p0 = in_ptr(ib + 2 * j, pr.n0);
+        pr.p1 = pr.has2 ? in_ptr(ib + 2 * j + 1, pr.n1) : pr.p0;
+        return pr;
+    };
+    // Each iteration is ~6 Fq2 products behind two dependent memory round trips (entry index -> table row), and the
+    // kernel runs at 8 warps per SM: ncu (profiles/r02_ncu_affine_round_v2.txt) put 23 % of its issue slots behind
+    // long-scoreboard stalls.  So the inputs of the NEXT iteration are located one iteration ahead and their cache
+    // lines requested with prefetch instructions (no registers, no shared memory) while this one computes.
+    auto prefetch_pair = [&](const Pair& pr, bool with_y) {
+        if (!prefetch) return;
+        sb_prefetch_span(pr.p0, with_y ? sizeof(AffinePt<F>) : sizeof(F));
+        if (pr.has2) sb_prefetch_span(pr.p1, with_y ? sizeof(AffinePt<F>) : sizeof(F));
+    };
+    // pass 1: prefix products of the denominators (x coordinates only)
+    F acc = F::one();
+    Pair cur = locate(first), nxt = cur;
+    for (uint32_t i = 0; i < iters; i++) {
+        if (i + 1 < iters) { nxt = locate(first + 32 * (i + 1)); prefetch_pair(nxt, false); }
+        const AffinePt<F>* pp0 = cur.p0; const AffinePt<F>* pp1 = cur.p1;
+        const bool has2 = cur.has2, n0 = cur.n0, n1 = cur.n1;
         const F px = ldg_elem(&pp0->x), qx = has2 ? ldg_elem(&pp1->x) : px;
         F d;
         pair_classify_x(px, qx, has2, [&](int k) { F y = ldg_elem(k ? &pp1->y : &pp0->y); return (k ? n1 : n0) ? F::neg(y) : y; }, d);
         st_elem(&prefix[(size_t)i * nthreads + t], acc);
         acc = F::mul(acc, d);
+        cur = nxt;
     }
     F inv = F::inv_fast(acc);
-    // pass 2, backwards: 1/d_k = inv * prefix_k, then inv *= d_k
+    // pass 2, backwards: 1/d_k = inv * prefix_k, then inv *= d_k   (cur is the last output's pair: the first pass left it there)
     for (uint32_t i = iters; i-- > 0;) {
+        if (i > 0) {
+            nxt = locate(first + 32 * (i - 1)); prefetch_pair(nxt, true);
+            if (prefetch) sb_prefetch_span(&prefix[(size_t)(i - 1) * nthreads + t], sizeof(F));
+        }
         const uint32_t p = first + 32 * i;
-        while (__ldg(&out_off[b]) > p) b--;
-        const uint32_t j = p - __ldg(&out_off[b]);
-        const uint32_t ib = __ldg(&in_off[b]), n_in = __ldg(&in_off[b + 1]) - ib;
-        const bool has2 = 2 * j + 1 < n_in;
-        bool n0, n1 = false;
-        const AffinePt<F>* pp0 = in_ptr(ib + 2 * j, n0);
-        const AffinePt<F>* pp1 = has2 ? in_ptr(ib + 2 * j + 1, n1) : pp0;
-        AffinePt<F> P = ldg_elem(pp0), Q = has2 ? ldg_elem(pp1) : P;
-        if (n0) P.y = F::neg(P.y);
-        if (has2 && n1) Q.y = F::neg(Q.y);
+        const bool has2 = cur.has2;
+        AffinePt<F> P = ldg_elem(cur.p0), Q = has2 ? ldg_elem(cur.p1) : P;
+        if (cur.n0) P.y = F::neg(P.y);
+        if (has2 && cur.n1) Q.y = F::neg(Q.y);
         if (!has2) Q = P;
         F d;
         const int kind = pair_classify_x(P.x, Q.x, has2, [&](int k) { return k ? Q.y : P.y; }, d);
@@ -487,6 +503,7 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>*
             r.y = F::sub(F::mul(lam, F::sub(P.x, r.x)), P.y);
         }
         st_elem(&out_aff[p], r);
+        cur = nxt;
     }
 }
 
@@ -581,16 +598,16 @@ __device__ XyzzPt<F> quad_mul_small(const XyzzPt<F>& p, uint32_t k) {
 // above) and R_c = the sum of its buckets.  Stage 2 (one CTA per slot) does the same to the CTAs: total = sum_c A_c + G sum_c c R_c.
 // Depth: 2 L + 2 log2(RED_QUADS) + 3 quad operations in stage 1 and about 30 in stage 2, ~7 us each, whatever the MSM size
 // (round 1: 2 L + ~22 doublings/additions of mul_small + 6 tree levels on single threads, ~30 us each).
-constexpr int RED_QUADS = 64, RED_THREADS = 4 * RED_QUADS;
-// suffix scan over the quads of a CTA: returns sum_{t' >= quad} v_{t'}; sh holds RED_QUADS points
+constexpr int RED_QUADS = 64, RED_THREADS = 4 * RED_QUADS;      // largest CTA; groups of tiny slots launch fewer quads (MsmGroup::red_quads, a power of two >= 8)
+// suffix scan over the quads of a CTA: returns sum_{t' >= quad} v_{t'}; sh holds one point per quad
 template <class F>
 __device__ XyzzPt<F> quad_block_suffix_scan(XyzzPt<F> v, XyzzPt<F>* sh) {
-    const uint32_t qd = threadIdx.x >> 2, r = threadIdx.x & 3;
+    const uint32_t qd = threadIdx.x >> 2, r = threadIdx.x & 3, nq = blockDim.x >> 2;
     if (r == 0) st_elem(&sh[qd], v);
     __syncthreads();
-    for (uint32_t off = 1; off < (uint32_t)RED_QUADS; off <<= 1) {
+    for (uint32_t off = 1; off < nq; off <<= 1) {
         XyzzPt<F> o = XyzzPt<F>::inf();
-        if (qd + off < (uint32_t)RED_QUADS) o = sh[qd + off];
+        if (qd + off < nq) o = sh[qd + off];
         __syncthreads();
         v = quad_add(v, o);
         if (r == 0) st_elem(&sh[qd], v);
@@ -605,7 +622,7 @@ __device__ XyzzPt<F> quad_block_tree_sum(XyzzPt<F> v, XyzzPt<F>* sh) {
     __syncthreads();
     if (r == 0) st_elem(&sh[qd], v);
     __syncthreads();
-    for (uint32_t stride = RED_QUADS / 2; stride > 0; stride >>= 1) {
+    for (uint32_t stride = blockDim.x >> 3; stride > 0; stride >>= 1) {
         if ((qd & ~7u) < stride) {                  // whole warps (8 quads) drop out once they hold no active quad; idle quads of a live warp add infinity
             XyzzPt<F> o = XyzzPt<F>::inf();
             if (qd < stride) o = sh[qd + stride];
@@ -631,7 +648,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce1(const XyzzPt<F>*
     const XyzzPt<F>* pts = ((levels - 1) & 1) ? ptsB : ptsA;
     const uint32_t* off = pp.plan[levels - 1];
     const uint32_t qd = threadIdx.x >> 2;
-    const uint64_t lo = ((uint64_t)(blockIdx.x - __ldg(&sl->rbase)) * RED_QUADS + qd) * L;
+    const uint64_t lo = ((uint64_t)(blockIdx.x - __ldg(&sl->rbase)) * (blockDim.x >> 2) + qd) * L;
     XyzzPt<F> run = XyzzPt<F>::inf(), sum = XyzzPt<F>::inf();
     for (uint32_t jj = L; jj-- > 0;) {
         const uint64_t b = lo + jj;
@@ -657,7 +674,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce2(const XyzzPt<F>*
     XyzzPt<F>* sh = reinterpret_cast<XyzzPt<F>*>(smem_raw);
     const MsmSlot* sl = slots + blockIdx.x;
     const uint32_t r0 = __ldg(&sl->rbase), nblocks = __ldg(&sl->rblocks), L = __ldg(&sl->red_l);
-    const uint32_t cpt = (nblocks + RED_QUADS - 1) / RED_QUADS, qd = threadIdx.x >> 2;
+    const uint32_t nq = blockDim.x >> 2, cpt = (nblocks + nq - 1) / nq, qd = threadIdx.x >> 2;
     XyzzPt<F> accA = XyzzPt<F>::inf(), run = XyzzPt<F>::inf(), sum = XyzzPt<F>::inf();       // sum_c A_c, sum_j R_{q cpt + j}, sum_j j R_{q cpt + j}
     for (uint32_t jj = cpt; jj-- > 0;) {
         const uint32_t c = qd * cpt + jj;
@@ -668,9 +685,9 @@ __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce2(const XyzzPt<F>*
         if (jj >= 1) sum = quad_add(sum, run);
     }
     const XyzzPt<F> suf = quad_block_suffix_scan(run, sh);
-    // sum_c c R_c = sum_q [ sum_j j R + cpt * q * run_q ]; the total weighs it by G = RED_QUADS * L buckets per stage-1 CTA
+    // sum_c c R_c = sum_q [ sum_j j R + cpt * q * run_q ]; the total weighs it by G = quads * L buckets per stage-1 CTA
     XyzzPt<F> v = quad_add(sum, quad_mul_small(qd ? suf : XyzzPt<F>::inf(), cpt));
-    v = quad_add(accA, quad_mul_small(v, RED_QUADS * L));
+    v = quad_add(accA, quad_mul_small(v, nq * L));
     const XyzzPt<F> total = quad_block_tree_sum(v, sh);
     if (threadIdx.x == 0) st_elem(&out[blockIdx.x], total);
 }
@@ -766,6 +783,21 @@ static uint32_t msm_affine_rounds(uint64_t etot) {
     return etot >= ((uint64_t)1 << lg) ? rounds : 0;
 }
 static uint32_t msm_affine_kmax() { static const uint32_t v = msm_env_u32("SB_MSM_AFFINE_K", 256, 1, 1024); return v; }
+// CTAs of the round kernel an SM holds (registers decide: 4 over Fq2, 6-8 over Fq); the rounds are sized to exactly one wave
+template <class F>
+static uint32_t msm_affine_ctas_per_sm() {
+    static const uint32_t forced = msm_env_u32("SB_MSM_AFFINE_CTAS", 0, 0, 16);
+    if (forced) return forced;
+    static uint32_t cached = 0;
+    if (!cached) {
+        int a = 0, b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_affine_round<F, true>, AFF_THREADS, 0) != cudaSuccess) a = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_affine_round<F, false>, AFF_THREADS, 0) != cudaSuccess) b = 4;
+        cached = (uint32_t)std::max(1, std::min(a, b));
+    }
+    return cached;
+}
+static uint32_t msm_prefetch() { static const uint32_t v = msm_env_u32("SB_MSM_PREFETCH", 1, 0, 1); return v; }   // software prefetch in the affine rounds (0: off, for A/B runs)
 static uint32_t msm_nlaunch() { static const uint32_t v = msm_env_u32("SB_MSM_LEVELS", 5, 2, MSM_MAX_LEVELS); return v; }
 
 template <class F>
@@ -775,6 +807,13 @@ void msm_group_prepare(const std::vector<const AffinePt<F>*>& bases_dev, const s
     out.slots.assign(J, MsmSlot{});
     uint64_t mtot = 0, etot = 0, btot = 0, rtot = 0;
     static const uint32_t red_env = msm_env_u32("SB_MSM_RED_L", 0, 0, 64);
+    {   // quads per reduction CTA: 64, fewer when every slot of the group is tiny
+        size_t mmax = 0;
+        for (size_t j = 0; j < J; j++) mmax = std::max(mmax, ms[j]);
+        const uint32_t nbmax = 1u << (msm_layout(mmax).c - 1);
+        out.red_quads = 8;
+        while (out.red_quads < (uint32_t)RED_QUADS && out.red_quads * 4 < nbmax) out.red_quads *= 2;
+    }
     for (size_t j = 0; j < J; j++) {
         MsmSlot& s = out.slots[j];
         SB_REQUIRE(ms[j] >= 1 && ms[j] < ((size_t)1 << 31), "msm: slot size out of range");
@@ -782,9 +821,9 @@ void msm_group_prepare(const std::vector<const AffinePt<F>*>& bases_dev, const s
         s.nb = 1u << (s.lay.c - 1);
         // buckets per quad in the first reduction stage (see k_bucket_reduce1): 2 L chained additions per quad
         const uint32_t red_l = red_env ? red_env : 4u;
-        s.red_l = s.nb >= red_l * RED_QUADS ? red_l : 1;
+        s.red_l = s.nb >= red_l * out.red_quads ? red_l : 1;
         const uint32_t nquads = (s.nb + s.red_l - 1) / s.red_l;
-        s.rblocks = (nquads + RED_QUADS - 1) / RED_QUADS;
+        s.rblocks = (nquads + out.red_quads - 1) / out.red_quads;
         s.mbase = (uint32_t)mtot; s.ebase = (uint32_t)etot; s.bbase = (uint32_t)btot; s.rbase = (uint32_t)rtot;
         mtot += s.m; etot += (uint64_t)s.lay.W * s.m; btot += s.nb; rtot += s.rblocks;
     }
@@ -799,7 +838,7 @@ void msm_group_prepare(const std::vector<const AffinePt<F>*>& bases_dev, const s
         for (int l = 0; l < MSM_MAX_LEVELS; l++, div *= msm_s1_min()) out.items_bound[l] = (uint32_t)(e0 / div + btot);
         for (uint32_t r = 0; r < out.R; r++) {
             const uint64_t bound = (etot >> (r + 1)) + btot;            // outputs of round r
-            const uint64_t resident = (uint64_t)SB_SMS * 4 * AFF_THREADS;  // threads one wave of the round kernel holds
+            const uint64_t resident = (uint64_t)SB_SMS * msm_affine_ctas_per_sm<F>() * AFF_THREADS;  // threads one wave of the round kernel holds
             uint64_t k = (bound + resident - 1) / resident;
             k = std::min<uint64_t>(std::max<uint64_t>(k, std::min<uint32_t>(8, msm_affine_kmax())), msm_affine_kmax());
             out.round_bound[r] = (uint32_t)bound; out.round_k[r] = (uint32_t)k; out.round_threads[r] = (uint32_t)(((bound + k - 1) / k + 31) / 32 * 32);   // whole warps (see k_affine_round)
@@ -904,10 +943,10 @@ void msm_group_accum(const MsmGroup<F>& g, cudaStream_t stream) {
         const int grid = (int)((g.round_threads[r] + AFF_THREADS - 1) / AFF_THREADS);
         if (r == 0)
             SB_LAUNCH_NAMED(SB_KNAME(F, "k_affine_round"), (k_affine_round<F, true>), grid, AFF_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), aff, seg0,
-                            sc.hplan[r].get(), B, g.round_threads[r], g.round_k[r], sc.prefix.get(), outp);
+                            sc.hplan[r].get(), B, g.round_threads[r], msm_prefetch(), sc.prefix.get(), outp);
         else
             SB_LAUNCH_NAMED(SB_KNAME(F, "k_affine_round"), (k_affine_round<F, false>), grid, AFF_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), aff, seg0,
-                            sc.hplan[r].get(), B, g.round_threads[r], g.round_k[r], sc.prefix.get(), outp);
+                            sc.hplan[r].get(), B, g.round_threads[r], msm_prefetch(), sc.prefix.get(), outp);
         aff = outp; seg0 = sc.hplan[r].get();
     }
     const int grid = (int)((std::max<uint32_t>(g.items_bound[0], 1) + ACC_THREADS - 1) / ACC_THREADS);
@@ -928,10 +967,11 @@ void msm_group_tail(const MsmGroup<F>& g, XyzzPt<F>* out_dev, cudaStream_t strea
         SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, false>), grid, ACC_THREADS, 0, stream, g.tab.get(), sc.sorted.get(),
                         (const AffinePt<F>*)nullptr, inp, sc.plan[l - 1].get(), sc.plan[l].get(), B, l, sc.info.get(), (const uint32_t*)nullptr, outp);
     }
-    const size_t smem = RED_QUADS * sizeof(XyzzPt<F>);
-    SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce1"), (k_bucket_reduce1<F>), (int)g.rtot, RED_THREADS, smem, stream, sc.ptsA.get(), sc.ptsB.get(), pp,
+    const size_t smem = g.red_quads * sizeof(XyzzPt<F>);
+    const int red_threads = 4 * (int)g.red_quads;
+    SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce1"), (k_bucket_reduce1<F>), (int)g.rtot, red_threads, smem, stream, sc.ptsA.get(), sc.ptsB.get(), pp,
                     g.slots_dev.get(), J, sc.block_out.get());
-    SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce2"), (k_bucket_reduce2<F>), (int)J, RED_THREADS, smem, stream, sc.block_out.get(), g.slots_dev.get(), out_dev);
+    SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce2"), (k_bucket_reduce2<F>), (int)J, red_threads, smem, stream, sc.block_out.get(), g.slots_dev.get(), out_dev);
     g_sb_prof_tag = -1;
 }
 template <class F>

@@ -46,7 +46,7 @@ struct MsmSlot {
     uint32_t ebase;      // table: tab[ebase + w * m + i] = 2^(shift[w]) * P_i; the same index space numbers the entries
     uint32_t bbase;      // first bucket; the slot owns nb = 2^(c-1) buckets
     uint32_t nb;
-    uint32_t red_l;      // buckets per thread in the first reduction stage
+    uint32_t red_l;      // buckets per quad of lanes in the first reduction stage
     uint32_t rbase;      // first CTA of the first reduction stage; the slot owns rblocks CTAs
     uint32_t rblocks;
     WinLayout lay;
@@ -71,6 +71,7 @@ struct MsmGroup {
     std::vector<MsmSlot> slots;
     DevBuf<MsmSlot> slots_dev;
     uint32_t mtot = 0, etot = 0, btot = 0, rtot = 0;
+    uint32_t red_quads = 64;         // quads of lanes per CTA of the bucket reduction
     uint32_t s0 = 0;                 // chunk length of the first accumulation level (fixed when the group is prepared)
     uint32_t items_bound[MSM_MAX_LEVELS] = {};   // upper bounds on the chunk count of every level (grid sizes)
     uint32_t R = 0;                  // pairwise affine rounds in front of the XYZZ accumulation (fixed when the group is prepared)

@@ -9,6 +9,7 @@
 #include "../../include/spartan_b200.h"
 #include "common.cuh"
 #include "kernels_fr.cuh"
+#include "indexer.cuh"
 #include "msm.cuh"
 #include "transcript.h"
 #include <algorithm>
@@ -114,6 +115,7 @@ struct sb_index {
     SegPlan cols;      // segments = local column, gathers X[k * n + row] (X is replicated)
     sbhost::Transcript fs_after_matrices;   // lib.rs:61-64 absorbed once
     size_t nnz[3] = {0, 0, 0};
+    double plan_ms = 0, hash_wait_ms = 0;   // sb_index_timing: validation + device-side plans; what the transcript hash added on top
 };
 
 // One multilinear-commitment parameter set over `nv` variables, expanded for the MSM kernels.
@@ -275,50 +277,28 @@ static Fr top_weight(const Fr* t_hi, int glog, int rho) {
 }
 
 // ====================================================================== index: plans + transcript prefix
-static void build_plan(sb_ctx* c, size_t nseg, const std::vector<uint64_t>& seg_ptr, const std::vector<uint32_t>& gather,
-                       const std::vector<Fr>& val, SegPlan& plan) {
-    size_t nnz = gather.size();
-    SB_REQUIRE(nnz < ((size_t)1 << 31), "too many non-zero entries");
-    const Fr one = Fr::one();
-    std::vector<uint32_t> idx(nnz);
-    for (size_t e = 0; e < nnz; e++) idx[e] = gather[e] | (val[e] == one ? SEG_UNIT_FLAG : 0u);
-    std::vector<SegItem> items;
-    std::vector<SegFixup> fix;
-    uint32_t n_partials = 0;
-    for (size_t s = 0; s < nseg; s++) {
-        uint64_t beg = seg_ptr[s], end = seg_ptr[s + 1];
-        uint64_t len = end - beg;
-        if (len == 0) continue;
-        if (len <= SEG_LMAX) { items.push_back({(uint32_t)beg, (uint32_t)len, (uint32_t)s}); continue; }
-        SegFixup f{(uint32_t)s, n_partials, 0};
-        for (uint64_t o = beg; o < end; o += SEG_LMAX) {
-            uint32_t l = (uint32_t)std::min<uint64_t>(SEG_LMAX, end - o);
-            items.push_back({(uint32_t)o, l, n_partials | 0x80000000u});
-            n_partials++; f.pcount++;
-        }
-        fix.push_back(f);
-    }
-    // longest items first so that the threads of a warp carry similar trip counts (stable counting sort)
-    {
-        std::vector<uint32_t> cnt(SEG_LMAX + 2, 0);
-        for (auto& it : items) cnt[SEG_LMAX - it.len + 1]++;
-        for (size_t i = 1; i < cnt.size(); i++) cnt[i] += cnt[i - 1];
-        std::vector<SegItem> sorted(items.size());
-        for (auto& it : items) sorted[cnt[SEG_LMAX - it.len]++] = it;
-        items.swap(sorted);
-    }
+// The plans are built ON THE DEVICE (csrc/indexer.cu) from the caller's CSR arrays; the host only reads back the counters
+// that size the allocations.  `seg_ptr` (device, nseg + 1 offsets into plan.val / plan.idx, which the caller has filled)
+// describes the segments; this turns them into length-sorted work items and fixups for k_segsum / k_seg_fixup.
+static void plan_finish_dev(sb_ctx* c, size_t nseg, const uint32_t* seg_ptr_dev, SegPlan& plan) {
     cudaStream_t st = c->stream;
-    plan.nnz = nnz; plan.n_items = (uint32_t)items.size(); plan.n_fix = (uint32_t)fix.size();
-    plan.val.alloc(nnz ? nnz : 1, st); plan.idx.alloc(nnz ? nnz : 1, st);
-    plan.items.alloc(items.size() ? items.size() : 1, st); plan.fix.alloc(fix.size() ? fix.size() : 1, st);
-    plan.partials.alloc(n_partials ? n_partials : 1, st);
-    if (nnz) {
-        SB_CUDA(cudaMemcpyAsync(plan.val.get(), val.data(), nnz * sizeof(Fr), cudaMemcpyHostToDevice, st));
-        SB_CUDA(cudaMemcpyAsync(plan.idx.get(), idx.data(), nnz * 4, cudaMemcpyHostToDevice, st));
-    }
-    if (!items.empty()) SB_CUDA(cudaMemcpyAsync(plan.items.get(), items.data(), items.size() * sizeof(SegItem), cudaMemcpyHostToDevice, st));
-    if (!fix.empty()) SB_CUDA(cudaMemcpyAsync(plan.fix.get(), fix.data(), fix.size() * sizeof(SegFixup), cudaMemcpyHostToDevice, st));
+    DevBuf<PlanCounts> counts_dev(1, st);
+    SB_CUDA(cudaMemsetAsync(counts_dev.get(), 0, sizeof(PlanCounts), st));
+    launch_seg_hist(seg_ptr_dev, nseg, counts_dev.get(), st);
+    PlanCounts counts;
+    SB_CUDA(cudaMemcpyAsync(&counts, counts_dev.get(), sizeof counts, cudaMemcpyDeviceToHost, st));
     ctx_sync(c);
+    PlanCursors cur{};
+    uint64_t n_items = 0;
+    for (uint32_t len = SEG_LMAX; len >= 1; len--) { cur.item[len] = (uint32_t)n_items; n_items += counts.hist[len]; }     // longest items first
+    SB_REQUIRE(n_items < ((uint64_t)1 << 31), "too many work items");
+    plan.n_items = (uint32_t)n_items; plan.n_fix = counts.n_fix;
+    plan.items.alloc(n_items ? n_items : 1, st); plan.fix.alloc(counts.n_fix ? counts.n_fix : 1, st);
+    plan.partials.alloc(counts.n_partials ? counts.n_partials : 1, st);
+    DevBuf<PlanCursors> cur_dev(1, st);
+    SB_CUDA(cudaMemcpyAsync(cur_dev.get(), &cur, sizeof cur, cudaMemcpyHostToDevice, st));
+    launch_seg_emit(seg_ptr_dev, nseg, cur_dev.get(), plan.items.get(), plan.fix.get(), counts.n_fix, st);
+    ctx_sync(c);       // `cur` (host) was the source of an asynchronous copy
 }
 
 static sb_index* index_create(sb_ctx* c, uint32_t log_n, const sb_csr* mats[3]) {
@@ -329,16 +309,39 @@ static sb_index* index_create(sb_ctx* c, uint32_t log_n, const sb_csr* mats[3]) 
     ix->ctx = c; ix->log_n = log_n; ix->n = n;
     ix->loc = log_n - c->glog; ix->nl = n >> c->glog;
     const size_t nl = ix->nl, lo = (size_t)c->rank * nl, hi = lo + nl;
-    // validation (r1cs_reader.rs:36-70)
+    cudaStream_t st = c->stream;
+    const double t_begin = now_ms();
+    // validation (r1cs_reader.rs:36-70), on the device: the row pointers first (everything else is sized by them)
+    DevBuf<uint64_t> rp_dev[3];
+    DevBuf<uint32_t> col_dev[3];
+    DevBuf<Fr> val_dev[3];
+    DevBuf<uint32_t> err_dev(1, st);
+    SB_CUDA(cudaMemsetAsync(err_dev.get(), 0, 4, st));
     for (int k = 0; k < 3; k++) {
         const sb_csr* m = mats[k];
         SB_REQUIRE(m && m->row_ptr, "null matrix");
-        SB_REQUIRE(m->row_ptr[0] == 0, "row_ptr[0] must be 0");
-        for (size_t r = 0; r < n; r++) SB_REQUIRE(m->row_ptr[r] <= m->row_ptr[r + 1], "row_ptr must be non-decreasing");
+        rp_dev[k].alloc(n + 1, st);
+        SB_CUDA(cudaMemcpyAsync(rp_dev[k].get(), m->row_ptr, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        launch_idx_validate_rows(rp_dev[k].get(), n, ((uint64_t)1 << 31) - 1, err_dev.get(), st);
+    }
+    uint32_t err = 0;
+    SB_CUDA(cudaMemcpyAsync(&err, err_dev.get(), 4, cudaMemcpyDeviceToHost, st));
+    ctx_sync(c);
+    SB_REQUIRE(!(err & IDX_ERR_ROWPTR), "row_ptr must start at 0, be non-decreasing and stay below 2^31 entries");
+    for (int k = 0; k < 3; k++) {
+        const sb_csr* m = mats[k];
         ix->nnz[k] = m->row_ptr[n];
         SB_REQUIRE(ix->nnz[k] == 0 || (m->col && m->val), "null col/val");
-        for (size_t e = 0; e < ix->nnz[k]; e++) SB_REQUIRE(m->col[e] < n, "sparse index out of bound");
+        col_dev[k].alloc(ix->nnz[k] ? ix->nnz[k] : 1, st); val_dev[k].alloc(ix->nnz[k] ? ix->nnz[k] : 1, st);
+        if (ix->nnz[k]) {
+            SB_CUDA(cudaMemcpyAsync(col_dev[k].get(), m->col, ix->nnz[k] * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            SB_CUDA(cudaMemcpyAsync(val_dev[k].get(), m->val, ix->nnz[k] * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        }
+        launch_idx_validate_cols(col_dev[k].get(), ix->nnz[k], (uint32_t)n, err_dev.get(), st);
     }
+    SB_CUDA(cudaMemcpyAsync(&err, err_dev.get(), 4, cudaMemcpyDeviceToHost, st));
+    ctx_sync(c);
+    SB_REQUIRE(!(err & IDX_ERR_COL), "sparse index out of bound");
     // transcript prefix: feed(matrix_a), feed(matrix_b), feed(matrix_c)  (lib.rs:61-64).  Blake2s is a serial
     // chain over ~40 bytes per non-zero entry (the largest host-side cost of indexing), so it runs on its own
     // thread while this one builds and uploads the plans; both only read the caller's arrays.
@@ -367,49 +370,46 @@ static sb_index* index_create(sb_ctx* c, uint32_t log_n, const sb_csr* mats[3]) 
         }
     });
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{hasher};
-    // row plan: segments k nl + (row - lo) for the rows of this rank's slice
+    // row plan: segments k nl + (row - lo) for the rows of this rank's slice -- the CSR slices themselves, back to back
     {
-        std::vector<uint64_t> seg_ptr(3 * nl + 1);
-        std::vector<uint32_t> gather;
-        std::vector<Fr> val;
-        size_t o = 0, local_nnz = 0;
-        for (int k = 0; k < 3; k++) local_nnz += mats[k]->row_ptr[hi] - mats[k]->row_ptr[lo];
-        gather.reserve(local_nnz); val.reserve(local_nnz);
+        uint64_t base[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 3; k++) base[k + 1] = base[k] + (mats[k]->row_ptr[hi] - mats[k]->row_ptr[lo]);
+        const uint64_t local_nnz = base[3];
+        SB_REQUIRE(local_nnz < ((uint64_t)1 << 31), "too many non-zero entries");
+        SegPlan& plan = ix->rows;
+        plan.nnz = local_nnz;
+        plan.val.alloc(local_nnz ? local_nnz : 1, st); plan.idx.alloc(local_nnz ? local_nnz : 1, st);
+        DevBuf<uint32_t> seg_ptr(3 * nl + 1, st);
         for (int k = 0; k < 3; k++) {
-            const sb_csr* m = mats[k];
-            const Fr* v = static_cast<const Fr*>(m->val);
-            for (size_t r = lo; r < hi; r++) {
-                seg_ptr[k * nl + (r - lo)] = o;
-                for (uint64_t e = m->row_ptr[r]; e < m->row_ptr[r + 1]; e++) { gather.push_back(m->col[e]); val.push_back(v[e]); o++; }
-            }
+            const uint64_t e0 = mats[k]->row_ptr[lo], cnt = base[k + 1] - base[k];
+            if (cnt) SB_CUDA(cudaMemcpyAsync(plan.val.get() + base[k], val_dev[k].get() + e0, cnt * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+            launch_idx_flags(col_dev[k].get() + e0, val_dev[k].get() + e0, plan.idx.get() + base[k], cnt, st);
+            launch_idx_row_segments(rp_dev[k].get(), lo, nl, (uint32_t)base[k], k == 2, seg_ptr.get() + (size_t)k * nl, st);
         }
-        seg_ptr[3 * nl] = o;
-        build_plan(c, 3 * nl, seg_ptr, gather, val, ix->rows);
+        plan_finish_dev(c, 3 * nl, seg_ptr.get(), plan);
     }
-    // column plan: segment = column y - lo of this rank's slice, entries (k n + row, value) of all three matrices
+    // column plan: segment = column y - lo of this rank's slice, entries (k n + row, value) of all three matrices: a counting
+    // sort by column (histogram, scan, scatter through atomic cursors)
     {
-        std::vector<uint64_t> seg_ptr(nl + 1, 0);
+        DevBuf<uint32_t> colptr(nl + 1, st), cursor(nl, st), ws(nl / 1024 + 4, st);
+        SB_CUDA(cudaMemsetAsync(colptr.get(), 0, (nl + 1) * sizeof(uint32_t), st));
+        for (int k = 0; k < 3; k++) launch_idx_col_count(col_dev[k].get(), ix->nnz[k], (uint32_t)lo, (uint32_t)hi, colptr.get(), st);
+        launch_idx_exscan(colptr.get(), nl, ws.get(), st);
+        uint32_t total = 0;
+        SB_CUDA(cudaMemcpyAsync(&total, colptr.get() + nl, 4, cudaMemcpyDeviceToHost, st));
+        ctx_sync(c);
+        SegPlan& plan = ix->cols;
+        plan.nnz = total;
+        plan.val.alloc(total ? total : 1, st); plan.idx.alloc(total ? total : 1, st);
+        SB_CUDA(cudaMemcpyAsync(cursor.get(), colptr.get(), nl * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
         for (int k = 0; k < 3; k++)
-            for (size_t e = 0; e < ix->nnz[k]; e++) { size_t y = mats[k]->col[e]; if (y >= lo && y < hi) seg_ptr[y - lo + 1]++; }
-        for (size_t y = 0; y < nl; y++) seg_ptr[y + 1] += seg_ptr[y];
-        std::vector<uint64_t> cur(seg_ptr.begin(), seg_ptr.end() - 1);
-        size_t total = seg_ptr[nl];
-        std::vector<uint32_t> gather(total);
-        std::vector<Fr> val(total);
-        for (int k = 0; k < 3; k++) {
-            const sb_csr* m = mats[k];
-            const Fr* v = static_cast<const Fr*>(m->val);
-            for (size_t r = 0; r < n; r++)
-                for (uint64_t e = m->row_ptr[r]; e < m->row_ptr[r + 1]; e++) {
-                    size_t y = m->col[e];
-                    if (y < lo || y >= hi) continue;
-                    uint64_t q = cur[y - lo]++;
-                    gather[q] = (uint32_t)(k * n + r); val[q] = v[e];
-                }
-        }
-        build_plan(c, nl, seg_ptr, gather, val, ix->cols);
+            launch_idx_col_scatter(rp_dev[k].get(), n, col_dev[k].get(), val_dev[k].get(), ix->nnz[k], (uint32_t)lo, (uint32_t)hi, (uint32_t)(k * n),
+                                   cursor.get(), plan.idx.get(), plan.val.get(), st);
+        plan_finish_dev(c, nl, colptr.get(), plan);
     }
+    const double t_plans = now_ms();
     hasher.join();
+    ix->plan_ms = t_plans - t_begin; ix->hash_wait_ms = now_ms() - t_plans;
     return ix.release();
 }
 
@@ -1216,6 +1216,11 @@ sb_status sb_index_create(sb_ctx* ctx, uint32_t log_n, const sb_csr* a, const sb
     const sb_csr* m[3] = {a, b, c};
     *out = index_create(ctx, log_n, m);
     SB_API_END
+}
+void sb_index_timing(const sb_index* ix, double* plan_ms, double* hash_wait_ms) {
+    const sb_index* p = (ix && !ix->parts.empty()) ? ix->parts[0] : ix;
+    if (plan_ms) *plan_ms = p ? p->plan_ms : 0;
+    if (hash_wait_ms) *hash_wait_ms = p ? p->hash_wait_ms : 0;
 }
 void sb_index_destroy(sb_index* ix) {
     if (!ix) return;

@@ -11,7 +11,7 @@ if [ -f "$OUT" ] && [ "$OUT" -nt "$newest" ]; then exit 0; fi
 mkdir -p "$HERE/obj"
 FLAGS="-std=c++20 -O2 -fPIC -pthread -I$HERE -include $HERE/cuda_runtime.h -Wno-unknown-pragmas -Wno-attributes"
 pids=()
-for f in kernels_fr msm prover comm_shm; do
+for f in kernels_fr msm prover comm_shm indexer; do
   $CXX_BIN $FLAGS -x c++ -c "$SRC/$f.cu" -o "$HERE/obj/$f.o" & pids+=($!)
 done
 $CXX_BIN $FLAGS -c "$HERE/emul_runtime.cpp" -o "$HERE/obj/emul_runtime.o" & pids+=($!)

@@ -31,7 +31,7 @@ print("workload %.1fs nnz %s" % (time.time() - t0, cs.nnz), flush=True)
 ctx = sb.Context(0)
 trap = np.stack([wl.mont_to_limbs([wl.fr_rand_mont(wl.SplitMix64(99 + i))])[0] for i in range(log_n)])
 t0 = time.time(); pp = sb.MLPolyCommit.keygen(log_n, G1_GENERATOR, G2_GENERATOR, trap, ctx=ctx); print("keygen %.1fs" % (time.time() - t0), flush=True)
-t0 = time.time(); pk = sb.MLArgumentForR1CS.index(*cs.mats, ctx=ctx); print("index %.1fs" % (time.time() - t0), flush=True)
+t0 = time.time(); pk = sb.MLArgumentForR1CS.index(*cs.mats, ctx=ctx); print("index %.2fs (device-side plans incl. upload %.0f ms, transcript hash added %.0f ms)" % ((time.time() - t0,) + pk.timing()), flush=True)
 wit = sb.Witness(pk, cs.v, cs.w)
 for i in range(4):
     t0 = time.time()
