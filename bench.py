@@ -339,58 +339,44 @@ def run_ours(args):
         return
     ms = 1e3 * dt / args.steps
     ms_e2e = 1e3 * dt_e2e / args.steps
-    # ---- roofline of the dominant kernel, from the CUDA-event split of the timed steps
+    # ---- roofline of the dominant kernel, from the CUDA-event split of the serialised steps
     n = 1 << LOG_N
     kernels = {k: {"launches_per_step": v["launches"] // args.steps, "ms_per_step": v["ms"] / args.steps} for k, v in prof.items()}
-    # the two profiler names of the G2 bucket accumulation are ONE kernel (k_seg_accum<Fq2, mixed>): its first
-    # (largest) ladder level is only named apart so that it can be matched with the ncu capture
-    merged = {}
-    for k, v in prof.items():
-        name = "k_seg_accum<Fq2,mixed>" if k in ("k_seg_accum_mixed:top<Fq2>", "k_seg_accum_mixed<Fq2>") else k
-        m = merged.setdefault(name, {"launches": 0, "ms": 0.0})
-        m["launches"] += v["launches"]; m["ms"] += v["ms"]
-    top = max(merged.items(), key=lambda kv: kv[1]["ms"]) if merged else (None, None)
-    roofline = None
-    extra = {}
-    if top[0]:
-        name, rec = top
-        per_launch_ms = rec["ms"] / rec["launches"]
-        launches_per_step = rec["launches"] // args.steps
-        alg = algorithmic_bytes(name, n, LOG_N, launches_per_step)      # average over the launches of a step
-        ach = alg / (per_launch_ms * 1e-3) / 1e9 if alg else None
-        roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": (ach / hbm_peak) if ach else None,
-                    "traffic": None, "algorithmic_bytes_per_launch": alg, "launches_per_step": launches_per_step,
-                    "peak_source": peak_src, "avg_launch_ms": per_launch_ms,
-                    "note": "the dominant kernel is bound by instruction issue on the integer pipe (IMAD.WIDE), not by HBM: see "
-                            "roofline_imad for its achieved Fq products per second against the ceiling measured in this run"}
-        if name == "k_seg_accum<Fq2,mixed>" and "k_seg_accum_mixed:top<Fq2>" in prof:
-            t = prof["k_seg_accum_mixed:top<Fq2>"]
-            t_ms = t["ms"] / t["launches"]
-            t_alg = algorithmic_bytes("k_seg_accum_mixed:top<Fq2>", n, LOG_N, 2)
-            ntr = NCU_TRAFFIC.get(("k_seg_accum_mixed:top<Fq2>", LOG_N))
-            roofline["largest_launch"] = {"avg_launch_ms": t_ms, "algorithmic_bytes": t_alg, "achieved": t_alg / (t_ms * 1e-3) / 1e9,
-                                          "frac": t_alg / (t_ms * 1e-3) / 1e9 / hbm_peak,
-                                          "traffic": ntr[0] if ntr else None, "traffic_source": ntr[1] if ntr else None}
-            roofline["traffic"] = ntr[0] if ntr else None
-            roofline["traffic_note"] = "dram bytes of the largest launch (ncu --set full); see largest_launch for its own algorithmic bytes"
     # integer-pipe ceiling measured in the same run: dependent-free Montgomery products (2 chains per thread)
     single = sb.Context(local_rank) if world > 1 else ctx
     fq_ms = single.mul_bench("fq", 148 * 1024, 1000)
     fr_ms = single.mul_bench("fr", 148 * 1024, 1000)
     fq_peak = 148 * 1024 * 1000 * 2 / fq_ms / 1e6     # G Fq-mul/s
     fr_peak = 148 * 1024 * 1000 * 2 / fr_ms / 1e6
-    extra["roofline_imad"] = imad_roofline(kernels, n, LOG_N, fq_peak, fr_peak)
+    work = msm_nominal_work(LOG_N - (world.bit_length() - 1), world)
+    extra = {"roofline_imad": imad_roofline(kernels, work, fq_peak)}
     extra["roofline_imad"]["peak_fq_gmul_s"] = fq_peak
-    if world == 1:
-        extra["roofline_imad"]["g2_accum_by_level"] = g2_levels(timeline, LOG_N, fq_peak)
     extra["roofline_imad"]["peak_fr_gmul_s"] = fr_peak
-    # the same dominant kernel against the roofline that actually bounds it (integer pipe), inside `roofline`
-    if roofline is not None:
-        top_lvl = extra["roofline_imad"].get("g2_accum_top_level")
-        if top_lvl:
-            roofline["integer_pipe"] = {"bound": "imad", "achieved": top_lvl["fq_gmul_s"], "peak": fq_peak, "unit": "G Fq-mul/s",
-                                        "frac": top_lvl["frac"], "of": "largest launch (28 Fq products per mixed addition in G2)",
-                                        "peak_source": "sb_mul_bench in this run (IMAD.WIDE issues at half rate: 148 SM x 32 lanes x clock)"}
+    roofline = None
+    msm_kernels = {k: v for k, v in kernels.items() if k in work}
+    if msm_kernels:
+        name = max(msm_kernels, key=lambda k: msm_kernels[k]["ms_per_step"])
+        rec, w = kernels[name], work[name]
+        per_launch_ms = rec["ms_per_step"] / rec["launches_per_step"]
+        ach = w["fq_products"] / rec["ms_per_step"] / 1e6                     # G Fq-mul/s over all its launches of a step
+        alg_bytes = w["bytes"] / rec["launches_per_step"]
+        hbm_ach = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+        ntr = NCU_TRAFFIC.get((name, LOG_N)) if world == 1 else None
+        roofline = {"kernel": name, "bound": "imad", "achieved": ach, "peak": fq_peak, "unit": "G Fq-mul/s", "frac": ach / fq_peak,
+                    "traffic": ntr[0] if ntr else None, "traffic_source": ntr[1] if ntr else None,
+                    "launches_per_step": rec["launches_per_step"], "avg_launch_ms": per_launch_ms,
+                    "algorithmic_fq_products_per_launch": w["fq_products"] / rec["launches_per_step"],
+                    "algorithmic_unit": w["unit"],
+                    "peak_source": "sb_mul_bench in this run (IMAD.WIDE issues at half rate: 148 SM x 32 lanes x clock; MEASURED_PEAKS.json holds no integer peak)",
+                    "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                            "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                            "note": "secondary: the kernel is bound by instruction issue on the integer pipe, not by HBM"}}
+        # the largest launch of that kernel (first pairwise round / first level of the largest group), from the serialised timeline
+        big = [(t1 - t0, tag) for (nm, t0, t1, tag) in timeline if nm == name]
+        if big and w.get("largest_launch_fq_products"):
+            d_ms = max(big)[0]
+            g = w["largest_launch_fq_products"] / d_ms / 1e6
+            roofline["largest_launch"] = {"ms": d_ms, "achieved": g, "frac": g / fq_peak, "fq_products": w["largest_launch_fq_products"]}
     # sumcheck kernels alone, L2 flushed between launches
     sc = {}
     for which, nm, mults, bts in ((0, "sc1_fused_round", 12 / 4.0, 152.0), (1, "sc1_first_round", 6 / 2.0, (6 * 32 + 32) / 2.0), (2, "sc2_fused_round", 7 / 4.0, (8 * 32 + 4 * 32) / 4.0)):
@@ -464,88 +450,64 @@ def msm_layout(m):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the `ncu --set full` capture under profiles/
-NCU_TRAFFIC = {("k_seg_accum_mixed:top<Fq2>", 20): (2.213844e9 + 1.025013e9, "profiles/r01_ncu_g2_accum_top.txt")}
+# (average over the launches captured; the first round of the largest group is the one captured with --set full)
+NCU_TRAFFIC = {}
 
 
-def chunk_s0(entries):
-    """chunk length of the first accumulation level (msm_s0 in csrc/msm.cu)"""
-    return 48 if entries >= (1 << 21) else 24
+def msm_nominal_work(ell, world=1):
+    """Nominal (algorithmic) work of one proof's MSM kernels on one rank, by profiler kernel name: Fq products and HBM bytes.
+    Mirrors the pipeline of csrc/prover.cu / csrc/msm.cu at its defaults: the commitment is one G1 group of 2^ell points; an
+    opening ladder has slots of 2^(ell-1) ... 1 points, split into {slot 0} (the shared first proof element, computed ONCE per
+    proof) and {the rest} (once per opening) when ell >= 12; a group of >= 2^21 (window, point) entries E runs R = 4 pairwise
+    affine rounds (E (1 - 2^-R) affine additions: 5M + 1S = 17 Fq products over Fq2, 6 over Fq; the shared inversion, one per
+    ~150 additions, is not counted) and then E / 2^R mixed XYZZ additions (8M + 2S = 28 / 10 Fq products); smaller groups
+    run E mixed additions.  Bytes per affine addition: two x coordinates + prefix out in the first pass, two points + prefix
+    in + result out in the second: 10 field elements (+ 16 bytes of entry indices in the first round); per mixed addition
+    one gathered affine point + a 4-byte entry.  (With world > 1 the tail ladders over the top variables are ignored.)"""
+    R = 4
 
-
-def algorithmic_bytes(name, n, ell, launches_per_step):
-    """Algorithmic HBM bytes of ONE launch of the named kernel."""
-    if name.startswith("k_seg_accum_mixed:top<Fq2>"):
-        # first level of an opening: m = n/2 bases; every (window, point) entry reads a 4-byte index and gathers one
-        # 192-byte affine base; every chunk of <= S entries writes one 384-byte partial sum
-        m = n // 2
-        c, W = msm_layout(m)
-        entries = W * m
-        return entries * (192 + 4) + (entries // chunk_s0(entries) + (1 << (c - 1))) * 384
-    if name == "k_seg_accum<Fq2,mixed>":
-        # all ladder levels of both openings (levels of 2^(ell-1) .. 1 bases), averaged per launch
-        total = 0
-        for k in range(ell):
-            m = 1 << k
-            c, W = msm_layout(m)
-            entries = W * m
-            total += entries * (192 + 4) + (entries // chunk_s0(entries) + (1 << (c - 1))) * 384
-        return 2.0 * total / launches_per_step
-    if name.startswith("k_seg_accum_mixed<Fq>"):
-        c, W = msm_layout(n)
-        entries = W * n
-        return entries * (96 + 4) + (entries // chunk_s0(entries) + (1 << (c - 1))) * 192
-    return None
-
-
-def imad_roofline(kernels, n, ell, fq_peak, fr_peak):
-    """Achieved Fq products per second of the bucket-accumulation kernels against the measured ceiling.
-    One mixed addition in XYZZ = 8M + 2S = 10 Fq products over G1, and 8*3 + 2*2 = 28 over G2 (Karatsuba Fq2)."""
+    def entries(ms):
+        return sum(msm_layout(m)[1] * m for m in ms)
     out = {}
-    k1 = kernels.get("k_seg_accum_mixed<Fq>")
-    if k1:
-        c, W = msm_layout(n)
-        out["g1_accum"] = {"ms": k1["ms_per_step"], "fq_gmul_s": W * n * 10 / k1["ms_per_step"] / 1e6}
-        out["g1_accum"]["frac"] = out["g1_accum"]["fq_gmul_s"] / fq_peak
-    kt = kernels.get("k_seg_accum_mixed:top<Fq2>")
-    if kt:
-        c, W = msm_layout(n // 2)
-        adds = 2 * W * (n // 2)                      # two openings per proof
-        out["g2_accum_top_level"] = {"ms": kt["ms_per_step"], "fq_gmul_s": adds * 28 / kt["ms_per_step"] / 1e6}
-        out["g2_accum_top_level"]["frac"] = out["g2_accum_top_level"]["fq_gmul_s"] / fq_peak
-    k2 = kernels.get("k_seg_accum_mixed<Fq2>")
-    if k2:
-        adds = 0
-        for k in range(0, ell - 1 if kt else ell):
-            c, W = msm_layout(1 << k)
-            adds += W * (1 << k)
-        adds *= 2
-        out["g2_accum_lower_levels"] = {"ms": k2["ms_per_step"], "fq_gmul_s": adds * 28 / k2["ms_per_step"] / 1e6}
-        out["g2_accum_lower_levels"]["frac"] = out["g2_accum_lower_levels"]["fq_gmul_s"] / fq_peak
+
+    def add(name, fq_products, nbytes, largest=0.0):
+        d = out.setdefault(name, {"fq_products": 0.0, "bytes": 0.0, "largest_launch_fq_products": 0.0})
+        d["fq_products"] += fq_products; d["bytes"] += nbytes
+        d["largest_launch_fq_products"] = max(d["largest_launch_fq_products"], largest)
+
+    def group(ms, g2, times):
+        e = entries(ms)
+        fsz = 96 if g2 else 48
+        aff_p, mix_p = (17, 28) if g2 else (6, 10)
+        suffix = "<Fq2>" if g2 else "<Fq>"
+        if e >= (1 << 21):
+            add("k_affine_round" + suffix, times * e * (1 - 2.0 ** -R) * aff_p, times * (e * (1 - 2.0 ** -R) * 10 * fsz + e / 2 * 16), e / 2 * aff_p)
+            add("k_seg_accum_mixed" + suffix, times * (e / 2 ** R) * mix_p, times * (e / 2 ** R) * 2 * fsz, (e / 2 ** R) * mix_p)
+        else:
+            add("k_seg_accum_mixed" + suffix, times * e * mix_p, times * e * (2 * fsz + 4), e * mix_p)
+    group([1 << ell], False, 1)
+    slots = [1 << k for k in range(ell - 1, -1, -1)]
+    if ell >= 12:
+        group(slots[:1], True, 1); group(slots[1:], True, 2)
+    else:
+        group(slots, True, 2)
+    for k, d in out.items():
+        d["unit"] = "Fq products: 17 per affine G2 addition (5M + 1S over Fq2), 6 over G1; 28 / 10 per mixed XYZZ addition"
     return out
 
 
-def g2_levels(timeline, ell, fq_peak):
-    """Serialised duration of the G2 mixed accumulation per ladder level (both openings) and its achieved Fq
-    products per second.  Levels below 2^14 points launch a handful of CTAs: alone they are latency-bound (a
-    chain of S0 dependent additions), in the real run they overlap the large levels, so their own fraction says
-    nothing about the kernel; they are reported as one group."""
-    per = {}
-    for name, t0, t1, tag in timeline:
-        if "k_seg_accum_mixed" in name and "Fq2" in name and tag >= 0:
-            per[tag] = per.get(tag, 0.0) + (t1 - t0)
-    out = {"levels": {}, "small_levels_below_2^14": {"ms": 0.0, "adds": 0}}
-    for tag, ms in sorted(per.items(), reverse=True):
-        c, W = msm_layout(1 << tag)
-        adds = 2 * W * (1 << tag)
-        if tag >= 14:
-            g = adds * 28 / ms / 1e6
-            out["levels"]["2^%d" % tag] = {"ms": ms, "window_bits": c, "windows": W, "fq_gmul_s": g, "frac": g / fq_peak}
-        else:
-            out["small_levels_below_2^14"]["ms"] += ms; out["small_levels_below_2^14"]["adds"] += adds
-    big_ms = sum(v["ms"] for v in out["levels"].values())
-    big_adds = sum(2 * msm_layout(1 << int(k[2:]))[1] * (1 << int(k[2:])) for k in out["levels"])
-    if big_ms:
-        out["levels_2^14_and_up"] = {"ms": big_ms, "fq_gmul_s": big_adds * 28 / big_ms / 1e6, "frac": big_adds * 28 / big_ms / 1e6 / fq_peak}
+def imad_roofline(kernels, work, fq_peak):
+    """Achieved nominal Fq products per second of every MSM kernel (serialised CUDA-event time) against the measured ceiling."""
+    out = {}
+    for name, w in work.items():
+        k = kernels.get(name)
+        if k and k["ms_per_step"] > 0:
+            g = w["fq_products"] / k["ms_per_step"] / 1e6
+            out[name] = {"ms_per_step": k["ms_per_step"], "launches_per_step": k["launches_per_step"], "fq_gmul_s": g, "frac": g / fq_peak}
+    tot_ms = sum(v["ms_per_step"] for v in out.values())
+    if tot_ms:
+        g = sum(work[k]["fq_products"] for k in out) / tot_ms / 1e6
+        out["all_msm_accumulation"] = {"ms_per_step": tot_ms, "fq_gmul_s": g, "frac": g / fq_peak}
     return out
 
 

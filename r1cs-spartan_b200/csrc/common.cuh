@@ -184,16 +184,3 @@ SB_D T shfl_elem(const T& v, int src) {
     return out;
 #endif
 }
-
-// Request the cache lines of [p, p + bytes) (an object of at most a few hundred bytes, 16-byte aligned) without
-// waiting for them: no destination registers, nothing to synchronise.
-SB_D void sb_prefetch_span(const void* p, uint32_t bytes) {
-#if defined(__CUDA_ARCH__)
-    const char* c = static_cast<const char*>(p);
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(c));
-    if (bytes > 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(c + 128));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(c + bytes - 16));
-#else
-    (void)p; (void)bytes;
-#endif
-}

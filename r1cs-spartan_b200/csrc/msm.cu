@@ -410,7 +410,7 @@ __device__ __forceinline__ int pair_classify_x(const F& px, const F& qx, bool ha
 template <class F, bool FIRST>
 __global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
                                                               const AffinePt<F>* __restrict__ in_aff, const uint32_t* __restrict__ in_off,
-                                                              const uint32_t* __restrict__ out_off, uint32_t B, uint32_t nthreads, uint32_t prefetch,
+                                                              const uint32_t* __restrict__ out_off, uint32_t B, uint32_t nthreads,
                                                               F* __restrict__ prefix, AffinePt<F>* __restrict__ out_aff) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = out_off[B];
@@ -451,20 +451,14 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>*
         pr.p1 = pr.has2 ? in_ptr(ib + 2 * j + 1, pr.n1) : pr.p0;
         return pr;
     };
-    // Each iteration is ~6 Fq2 products behind two dependent memory round trips (entry index -> table row), and the
-    // kernel runs at 8 warps per SM: ncu (profiles/r02_ncu_affine_round_v2.txt) put 23 % of its issue slots behind
-    // long-scoreboard stalls.  So the inputs of the NEXT iteration are located one iteration ahead and their cache
-    // lines requested with prefetch instructions (no registers, no shared memory) while this one computes.
-    auto prefetch_pair = [&](const Pair& pr, bool with_y) {
-        if (!prefetch) return;
-        sb_prefetch_span(pr.p0, with_y ? sizeof(AffinePt<F>) : sizeof(F));
-        if (pr.has2) sb_prefetch_span(pr.p1, with_y ? sizeof(AffinePt<F>) : sizeof(F));
-    };
+    // (Requesting the next iteration's cache lines one iteration ahead with prefetch instructions was measured in round 2,
+    // sweep 8: 41.6 against 41.0 ms per proof -- the long-scoreboard stalls ncu shows are the stack traffic of the outlined
+    // Fq2 products, not the table gathers -- and removed.)
     // pass 1: prefix products of the denominators (x coordinates only)
     F acc = F::one();
     Pair cur = locate(first), nxt = cur;
     for (uint32_t i = 0; i < iters; i++) {
-        if (i + 1 < iters) { nxt = locate(first + 32 * (i + 1)); prefetch_pair(nxt, false); }
+        if (i + 1 < iters) nxt = locate(first + 32 * (i + 1));
         const AffinePt<F>* pp0 = cur.p0; const AffinePt<F>* pp1 = cur.p1;
         const bool has2 = cur.has2, n0 = cur.n0, n1 = cur.n1;
         const F px = ldg_elem(&pp0->x), qx = has2 ? ldg_elem(&pp1->x) : px;
@@ -477,10 +471,7 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>*
     F inv = F::inv_fast(acc);
     // pass 2, backwards: 1/d_k = inv * prefix_k, then inv *= d_k   (cur is the last output's pair: the first pass left it there)
     for (uint32_t i = iters; i-- > 0;) {
-        if (i > 0) {
-            nxt = locate(first + 32 * (i - 1)); prefetch_pair(nxt, true);
-            if (prefetch) sb_prefetch_span(&prefix[(size_t)(i - 1) * nthreads + t], sizeof(F));
-        }
+        if (i > 0) nxt = locate(first + 32 * (i - 1));
         const uint32_t p = first + 32 * i;
         const bool has2 = cur.has2;
         AffinePt<F> P = ldg_elem(cur.p0), Q = has2 ? ldg_elem(cur.p1) : P;
@@ -797,7 +788,6 @@ static uint32_t msm_affine_ctas_per_sm() {
     }
     return cached;
 }
-static uint32_t msm_prefetch() { static const uint32_t v = msm_env_u32("SB_MSM_PREFETCH", 1, 0, 1); return v; }   // software prefetch in the affine rounds (0: off, for A/B runs)
 static uint32_t msm_nlaunch() { static const uint32_t v = msm_env_u32("SB_MSM_LEVELS", 5, 2, MSM_MAX_LEVELS); return v; }
 
 template <class F>
@@ -943,10 +933,10 @@ void msm_group_accum(const MsmGroup<F>& g, cudaStream_t stream) {
         const int grid = (int)((g.round_threads[r] + AFF_THREADS - 1) / AFF_THREADS);
         if (r == 0)
             SB_LAUNCH_NAMED(SB_KNAME(F, "k_affine_round"), (k_affine_round<F, true>), grid, AFF_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), aff, seg0,
-                            sc.hplan[r].get(), B, g.round_threads[r], msm_prefetch(), sc.prefix.get(), outp);
+                            sc.hplan[r].get(), B, g.round_threads[r], sc.prefix.get(), outp);
         else
             SB_LAUNCH_NAMED(SB_KNAME(F, "k_affine_round"), (k_affine_round<F, false>), grid, AFF_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), aff, seg0,
-                            sc.hplan[r].get(), B, g.round_threads[r], msm_prefetch(), sc.prefix.get(), outp);
+                            sc.hplan[r].get(), B, g.round_threads[r], sc.prefix.get(), outp);
         aff = outp; seg0 = sc.hplan[r].get();
     }
     const int grid = (int)((std::max<uint32_t>(g.items_bound[0], 1) + ACC_THREADS - 1) / ACC_THREADS);

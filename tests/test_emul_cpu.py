@@ -68,7 +68,7 @@ def test_sharded_prover_under_emulation(emul_env, world, oracle):
     old = {k: os.environ.get(k) for k in ("SB_EMUL_TESTS", "SB_LIB_PATH", "SB_EMUL_DEVICES")}
     os.environ.update(SB_EMUL_TESTS="1", SB_LIB_PATH=LIB, SB_EMUL_DEVICES="8")
     try:
-        tm._run(world, [(3, 4, 0, False), (5, 8, 30, True), (7, 32, 0, False)] if world == 2 else [(4, 4, 0, True), (6, 8, 0, False)], backend="gloo")
+        tm._run(world, [(3, 4, 0, False), (5, 8, 30, True)] if world == 2 else [(4, 4, 0, True)], backend="gloo")
     finally:
         for k, v in old.items():
             if v is None:
