@@ -441,10 +441,12 @@ def run_ours(args):
         dist.barrier(); dist.destroy_process_group()
 
 
-def msm_layout(m):
-    """window bits c and window count W of an MSM over m points (mirror of msm_layout in csrc/msm.cu)"""
+def msm_layout(m, group_max=None):
+    """window bits c and window count W of an MSM over m points in a group whose largest slot has group_max points
+    (mirror of msm_layout in csrc/msm.cu)"""
     lg = max(m - 1, 0).bit_length()
-    c = min(16, max(4, lg - 3))
+    off = 0 if max(m, group_max or m) <= (1 << 17) else -3
+    c = min(16, max(4, lg + off))
     rest = 255 - (c - 1)
     return c, (rest + c - 1) // c + 1
 
@@ -467,7 +469,7 @@ def msm_nominal_work(ell, world=1):
     R = 4
 
     def entries(ms):
-        return sum(msm_layout(m)[1] * m for m in ms)
+        return sum(msm_layout(m, max(ms))[1] * m for m in ms)
     out = {}
 
     def add(name, fq_products, nbytes, largest=0.0):

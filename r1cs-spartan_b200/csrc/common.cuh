@@ -167,20 +167,3 @@ SB_D void st_elem(T* p, const T& v) {
     *p = v;
 #endif
 }
-
-// A whole element from lane `src` of this warp (every lane of the warp calls it, converged): word-by-word warp shuffles on the
-// device, one exchange under the CUDA-on-CPU test shim.
-template <class T>
-SB_D T shfl_elem(const T& v, int src) {
-#if defined(SB_EMUL)
-    return emu_shfl_elem(v, src);
-#else
-    static_assert(sizeof(T) % 4 == 0, "element must be whole words");
-    T out;
-    const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
-    uint32_t* d = reinterpret_cast<uint32_t*>(&out);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(T) / 4); i++) d[i] = __shfl_sync(0xffffffffu, s[i], src);
-    return out;
-#endif
-}

@@ -4,14 +4,19 @@
 #include "msm.cuh"
 
 // ------------------------------------------------------------------ window geometry
-WinLayout msm_layout(size_t m) {
+WinLayout msm_layout(size_t m, size_t group_max_m) {
     int lg = 0;
     while (((size_t)1 << lg) < m) lg++;
-    // window bits: log2(m) - 3 balances the accumulation (m W additions) against the bucket reduction (~9 additions
-    // per bucket today).  SB_MSM_C_OFFSET / SB_MSM_C_MAX shift the rule for experiments (a cheaper reduction would
-    // favour one more bit); the layout is fixed when the bases are prepared, so the knobs only act at load time.
-    static const int c_off = getenv("SB_MSM_C_OFFSET") ? atoi(getenv("SB_MSM_C_OFFSET")) : -3;
+    // window bits: log2(m) - 3 for the slots of a LARGE group (throughput-bound: m W additions against the per-bucket
+    // work of the plan, the last accumulation level and the reduction), log2(m) for the slots of a group whose largest
+    // slot has at most 2^17 points (latency-bound: fewer entries per bucket = fewer dependent accumulation levels).
+    // Measured in round 2 (sweeps 7-9): at 2^20 constraints offsets -3 / -2 / -1 / 0 give 41.4 / 41.4 / 41.9 / 43.6 ms and a
+    // cap of 17-19 bits changes nothing or loses; at 2^17 (the per-GPU share of an 8-GPU proof) -3 / -2 / -1 / 0 / +1 give
+    // 14.1 / 13.4 / 12.9 / 12.7 / 13.9 ms.  SB_MSM_C_OFFSET / SB_MSM_C_MAX override the rule for experiments; the layout is
+    // fixed when the bases are prepared, so the knobs only act at load time.
+    static const int c_off_env = getenv("SB_MSM_C_OFFSET") ? atoi(getenv("SB_MSM_C_OFFSET")) : 99;
     static const int c_max = getenv("SB_MSM_C_MAX") ? atoi(getenv("SB_MSM_C_MAX")) : 16;
+    const int c_off = c_off_env != 99 ? c_off_env : (std::max(m, group_max_m) <= ((size_t)1 << 17) ? 0 : -3);
     int c = lg + c_off;
     if (c < 4) c = 4;
     if (c > c_max) c = c_max;
@@ -513,116 +518,162 @@ __device__ XyzzPt<F> mul_small(const XyzzPt<F>& p, uint32_t k) {
 // Fq2 products one after another (~18 k instructions, 25-30 us on a lone warp), and round 1 measured the two reduction
 // kernels at 1.2 + 0.65 ms per pipeline -- the latency floor of every commitment and opening, and what held the 8-GPU
 // efficiency at 0.42.  Here FOUR adjacent lanes (a "quad") share every operation: each stage of the XYZZ formulas has up
-// to four independent products, each lane takes one, and the results travel by warp shuffles -- 4 product latencies per
-// addition instead of 14, 3 per doubling instead of 9.  All four lanes hold the same inputs and obtain the same result.
-// Every lane of a warp must call these together (the shuffles are warp-wide); the exceptional cases of the group law
-// are resolved by selection AFTER the common path, so the calls never diverge.
+// to four independent products, each lane takes one -- 4 product latencies per addition instead of 14, 3 per doubling
+// instead of 9.
+// The operands live in SHARED memory: every quad owns a few point slots and a scratch area of field elements; a lane
+// picks POINTERS to the two operands of its product (the outlined field product reads its operands from memory
+// anyway), stores the result in the quad's scratch, and the quad meets at a __syncwarp.  (The first version kept the
+// points in registers and exchanged results by shuffles through address-taken temporaries: ncu,
+// profiles/r02_ncu_bucket_reduce1_quad.txt, showed 4.4 KB of stack per thread, local loads hitting L1 only 56 % of the
+// time, 715 MB of DRAM writes from a kernel whose results are a few kilobytes, ~10 cycles per instruction and warp.)
+// Every lane of a warp must call these together (__syncwarp is warp-wide); the exceptional cases of the group law are
+// resolved AFTER the common path, so the calls never diverge.
+constexpr int QUAD_WS = 14;          // field elements of scratch per quad
+constexpr int QUAD_SLOTS = 4;        // point slots per quad
 template <class F>
-SB_D F quad_pick(int r, const F& a0, const F& a1, const F& a2, const F& a3) {
-    F o;
-    const uint32_t* p0 = reinterpret_cast<const uint32_t*>(&a0); const uint32_t* p1 = reinterpret_cast<const uint32_t*>(&a1);
-    const uint32_t* p2 = reinterpret_cast<const uint32_t*>(&a2); const uint32_t* p3 = reinterpret_cast<const uint32_t*>(&a3);
-    uint32_t* d = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(F) / 4); i++) d[i] = r == 0 ? p0[i] : r == 1 ? p1[i] : r == 2 ? p2[i] : p3[i];
-    return o;
-}
-// add-2008-s, one product per lane and stage
+SB_D const F* quad_ptr(int r, const F* a0, const F* a1, const F* a2, const F* a3) { return r == 0 ? a0 : r == 1 ? a1 : r == 2 ? a2 : a3; }
 template <class F>
-__device__ __noinline__ XyzzPt<F> quad_add(const XyzzPt<F>& p, const XyzzPt<F>& q) {
-    const int lane = threadIdx.x & 31, r = lane & 3, base = lane & ~3;
-    const F m1 = F::mul(quad_pick(r, p.X, q.X, p.Y, q.Y), quad_pick(r, q.ZZ, p.ZZ, q.ZZZ, p.ZZZ));
-    const F U1 = shfl_elem(m1, base), U2 = shfl_elem(m1, base + 1), S1 = shfl_elem(m1, base + 2), S2 = shfl_elem(m1, base + 3);
-    const F Pp = F::sub(U2, U1), R = F::sub(S2, S1);
-    const F m2 = F::mul(quad_pick(r, Pp, p.ZZ, R, p.ZZZ), quad_pick(r, Pp, q.ZZ, R, q.ZZZ));      // PP, ZZ1 ZZ2, R^2, ZZZ1 ZZZ2
-    const F PP = shfl_elem(m2, base), RR = shfl_elem(m2, base + 2);
-    const F m3 = F::mul(quad_pick(r, Pp, m2, U1, m2), PP);                                         // PPP, ZZ3, Q, (unused)
-    const F PPP = shfl_elem(m3, base), Q = shfl_elem(m3, base + 2);
-    XyzzPt<F> o;
-    o.X = F::sub(F::sub(RR, PPP), F::dbl(Q));
-    const F m4 = F::mul(quad_pick(r, S1, S1, R, m2), quad_pick(r, PPP, PPP, F::sub(Q, o.X), PPP)); // S1 PPP, (unused), R (Q - X3), ZZZ3
-    o.Y = F::sub(shfl_elem(m4, base + 2), shfl_elem(m4, base));
-    o.ZZ = shfl_elem(m3, base + 1);
-    o.ZZZ = shfl_elem(m4, base + 3);
-    if (p.is_inf()) return q;
-    if (q.is_inf()) return p;
-    if (Pp.is_zero()) return R.is_zero() ? XyzzPt<F>::dbl(p) : XyzzPt<F>::inf();     // (no shuffles inside: may diverge)
-    return o;
-}
-// dbl-2008-s-1
+SB_D F* quad_comp(XyzzPt<F>* p, int r) { return r == 0 ? &p->X : r == 1 ? &p->Y : r == 2 ? &p->ZZ : &p->ZZZ; }
 template <class F>
-__device__ __noinline__ XyzzPt<F> quad_dbl(const XyzzPt<F>& p) {
-    const int lane = threadIdx.x & 31, r = lane & 3, base = lane & ~3;
-    const F U = F::dbl(p.Y);
-    const F m1 = F::mul(quad_pick(r, U, p.X, U, U), quad_pick(r, U, p.X, U, U));                   // V = U^2, XX
-    const F V = shfl_elem(m1, base), XX = shfl_elem(m1, base + 1);
-    const F M = F::add(F::dbl(XX), XX);
-    const F m2 = F::mul(quad_pick(r, U, p.X, M, p.ZZ), quad_pick(r, V, V, M, V));                  // W, S, M^2, ZZ3
-    const F W = shfl_elem(m2, base), S = shfl_elem(m2, base + 1), MM = shfl_elem(m2, base + 2);
-    XyzzPt<F> o;
-    o.X = F::sub(MM, F::dbl(S));
-    const F m3 = F::mul(quad_pick(r, M, W, W, W), quad_pick(r, F::sub(S, o.X), p.Y, p.ZZZ, p.Y));  // M (S - X3), W Y, ZZZ3, (unused)
-    o.Y = F::sub(shfl_elem(m3, base), shfl_elem(m3, base + 1));
-    o.ZZ = shfl_elem(m2, base + 3);
-    o.ZZZ = shfl_elem(m3, base + 2);
-    if (p.is_inf()) return p;
-    return o;
-}
-// k * p for a small k that is the same in every lane of the warp
+SB_D const F* quad_comp(const XyzzPt<F>* p, int r) { return r == 0 ? &p->X : r == 1 ? &p->Y : r == 2 ? &p->ZZ : &p->ZZZ; }
+// dst <- src, one coordinate per lane (dst != src)
 template <class F>
-__device__ XyzzPt<F> quad_mul_small(const XyzzPt<F>& p, uint32_t k) {
-    if (k == 0) return XyzzPt<F>::inf();
-    XyzzPt<F> acc = p;
-    for (int bit = 30 - __clz(k); bit >= 0; bit--) {
-        acc = quad_dbl(acc);
-        if ((k >> bit) & 1) acc = quad_add(acc, p);
+SB_D void quad_copy(XyzzPt<F>* dst, const XyzzPt<F>* src, int r) { *quad_comp(dst, r) = *quad_comp(src, r); }
+template <class F>
+SB_D void quad_set_inf(XyzzPt<F>* dst, int r) { *quad_comp(dst, r) = F::zero(); }
+
+// dst <- p + q (add-2008-s); dst may be p or q.  s: the quad's scratch (QUAD_WS field elements)
+template <class F>
+__device__ __noinline__ void quad_add(XyzzPt<F>* dst, const XyzzPt<F>* p, const XyzzPt<F>* q, F* s) {
+    const int r = threadIdx.x & 3;
+    const bool p_inf = p->ZZ.is_zero(), q_inf = q->ZZ.is_zero();
+    s[r] = F::mul(*quad_ptr(r, &p->X, &q->X, &p->Y, &q->Y), *quad_ptr(r, &q->ZZ, &p->ZZ, &q->ZZZ, &p->ZZZ));   // U1, U2, S1, S2
+    __syncwarp();
+    const F Pp = F::sub(s[1], s[0]), R = F::sub(s[3], s[2]);
+    const bool p_zero = Pp.is_zero(), r_zero = R.is_zero();
+    if (r == 0) s[4] = Pp;
+    if (r == 2) s[5] = R;
+    __syncwarp();
+    s[6 + r] = F::mul(*quad_ptr(r, &s[4], &p->ZZ, &s[5], &p->ZZZ), *quad_ptr(r, &s[4], &q->ZZ, &s[5], &q->ZZZ));   // PP, ZZ1 ZZ2, R^2, ZZZ1 ZZZ2
+    __syncwarp();
+    const F m3 = F::mul(*quad_ptr(r, &s[4], &s[7], &s[0], &s[7]), s[6]);                                       // PPP, ZZ3, Q, (unused)
+    if (r != 3) s[10 + r] = m3;
+    __syncwarp();
+    const F X3 = F::sub(F::sub(s[8], s[10]), F::dbl(s[12]));
+    if (r == 2) s[13] = F::sub(s[12], X3);
+    __syncwarp();
+    const F m4 = F::mul(*quad_ptr(r, &s[2], &s[2], &s[5], &s[9]), *quad_ptr(r, &s[10], &s[10], &s[13], &s[10]));   // S1 PPP, (unused), R (Q - X3), ZZZ3
+    if (r == 0) s[4] = m4;
+    __syncwarp();
+    if (p_inf | q_inf | p_zero) {                         // the same in all four lanes
+        if (p_inf) { if (dst != q) quad_copy(dst, q, r); }
+        else if (q_inf) { if (dst != p) quad_copy(dst, p, r); }
+        else if (r_zero) { if (r == 0) { const XyzzPt<F> d = XyzzPt<F>::dbl(*p); *dst = d; } }
+        else quad_set_inf(dst, r);
+    } else {
+        if (r == 0) dst->X = X3;
+        else if (r == 1) dst->ZZ = m3;
+        else if (r == 2) dst->Y = F::sub(m4, s[4]);
+        else dst->ZZZ = m4;
     }
-    return acc;
+    __syncwarp();
+}
+// dst <- 2 p (dbl-2008-s-1); dst may be p
+template <class F>
+__device__ __noinline__ void quad_dbl(XyzzPt<F>* dst, const XyzzPt<F>* p, F* s) {
+    const int r = threadIdx.x & 3;
+    const bool p_inf = p->ZZ.is_zero();
+    if (r == 0) s[0] = F::dbl(p->Y);                                                                           // U
+    __syncwarp();
+    const F m1 = F::mul(*quad_ptr(r, &s[0], &p->X, &s[0], &s[0]), *quad_ptr(r, &s[0], &p->X, &s[0], &s[0]));  // V = U^2, XX, (unused x 2)
+    if (r == 0) s[1] = m1;                                                                                     // V
+    if (r == 1) s[2] = F::add(F::dbl(m1), m1);                                                                 // M = 3 XX
+    __syncwarp();
+    s[3 + r] = F::mul(*quad_ptr(r, &s[0], &p->X, &s[2], &p->ZZ), *quad_ptr(r, &s[1], &s[1], &s[2], &s[1]));    // W, S, M^2, ZZ3
+    __syncwarp();
+    const F X3 = F::sub(s[5], F::dbl(s[4]));
+    if (r == 0) s[7] = F::sub(s[4], X3);
+    __syncwarp();
+    const F m3 = F::mul(*quad_ptr(r, &s[2], &s[3], &s[3], &s[3]), *quad_ptr(r, &s[7], &p->Y, &p->ZZZ, &p->Y)); // M (S - X3), W Y, ZZZ3, (unused)
+    if (r == 1) s[8] = m3;
+    __syncwarp();
+    if (!p_inf) {
+        if (r == 0) { dst->Y = F::sub(m3, s[8]); dst->X = X3; }
+        else if (r == 2) dst->ZZZ = m3;
+        else if (r == 3) dst->ZZ = s[6];
+    } else if (dst != p) quad_copy(dst, p, r);
+    __syncwarp();
+}
+// acc <- k acc for a small k that is the same in every lane of the warp; base: another point slot of the quad (clobbered)
+template <class F>
+__device__ void quad_mul_small(XyzzPt<F>* acc, XyzzPt<F>* base, uint32_t k, F* s) {
+    const int r = threadIdx.x & 3;
+    if (k == 0) { quad_set_inf(acc, r); __syncwarp(); return; }
+    quad_copy(base, acc, r);
+    __syncwarp();
+    for (int bit = 30 - __clz(k); bit >= 0; bit--) {
+        quad_dbl(acc, acc, s);
+        if ((k >> bit) & 1) quad_add(acc, acc, base, s);
+    }
 }
 
 // ------------------------------------------------------------------ bucket reduction: sum_b (b + 1) B_b per slot
-// Two stages of quads.  Stage 1: a CTA of RED_QUADS quads owns G = RED_QUADS * L consecutive buckets of one slot, quad t the
-// buckets [t L, (t + 1) L) of them.  With i = t L + j the local index of a bucket,
+// Two stages of quads.  Stage 1: a CTA of nq quads owns G = nq * L consecutive buckets of one slot, quad t the buckets
+// [t L, (t + 1) L) of them.  With i = t L + j the local index of a bucket,
 //     sum_i (i + 1) B_i = sum_t [ sum_j (j + 1) B_{tL+j} ] + L * sum_t t * run_t,     run_t = sum_j B_{tL+j},
 // the inner sums are running sums (2 L additions per quad), and sum_t t * run_t = sum_{t >= 1} (run_t + run_{t+1} + ...) is a
-// suffix scan over the quads (log2 RED_QUADS steps in shared memory) followed by one tree.  The CTA writes A_c (the local sum
-// above) and R_c = the sum of its buckets.  Stage 2 (one CTA per slot) does the same to the CTAs: total = sum_c A_c + G sum_c c R_c.
-// Depth: 2 L + 2 log2(RED_QUADS) + 3 quad operations in stage 1 and about 30 in stage 2, ~7 us each, whatever the MSM size
-// (round 1: 2 L + ~22 doublings/additions of mul_small + 6 tree levels on single threads, ~30 us each).
+// suffix scan over the quads (log2 nq steps) followed by one tree.  The CTA writes A_c (the local sum above) and R_c = the
+// sum of its buckets.  Stage 2 (one CTA per slot) does the same to the CTAs: total = sum_c A_c + G sum_c c R_c.
+// Depth: 2 L + 2 log2(nq) + 3 quad operations in stage 1 and about 30 in stage 2, whatever the MSM size (round 1: 2 L + ~22
+// doublings/additions of a scalar multiple + 6 tree levels on single threads).
 constexpr int RED_QUADS = 64, RED_THREADS = 4 * RED_QUADS;      // largest CTA; groups of tiny slots launch fewer quads (MsmGroup::red_quads, a power of two >= 8)
-// suffix scan over the quads of a CTA: returns sum_{t' >= quad} v_{t'}; sh holds one point per quad
+// shared memory of a reduction CTA: QUAD_SLOTS point slots and QUAD_WS scratch elements per quad
 template <class F>
-__device__ XyzzPt<F> quad_block_suffix_scan(XyzzPt<F> v, XyzzPt<F>* sh) {
+static size_t red_smem_bytes(uint32_t nq) { return (size_t)nq * (QUAD_SLOTS * sizeof(XyzzPt<F>) + QUAD_WS * sizeof(F)); }
+template <class F>
+struct QuadMem {
+    XyzzPt<F>* slot;      // this quad's QUAD_SLOTS points
+    F* ws;                // this quad's scratch
+    XyzzPt<F>* all;       // slot 0 of quad 0 (quad t's slots start at all + t * QUAD_SLOTS)
+    __device__ QuadMem(unsigned char* raw) {
+        const uint32_t nq = blockDim.x >> 2, qd = threadIdx.x >> 2;
+        all = reinterpret_cast<XyzzPt<F>*>(raw);
+        slot = all + (size_t)qd * QUAD_SLOTS;
+        ws = reinterpret_cast<F*>(all + (size_t)nq * QUAD_SLOTS) + (size_t)qd * QUAD_WS;
+    }
+};
+// suffix scan over the quads of a CTA of slot `k`: slot k of quad t <- sum_{t' >= t} (slot k of quad t'); slot `tmp` is clobbered
+template <class F>
+__device__ void quad_block_suffix_scan(QuadMem<F>& m, int k, int tmp) {
     const uint32_t qd = threadIdx.x >> 2, r = threadIdx.x & 3, nq = blockDim.x >> 2;
-    if (r == 0) st_elem(&sh[qd], v);
     __syncthreads();
     for (uint32_t off = 1; off < nq; off <<= 1) {
-        XyzzPt<F> o = XyzzPt<F>::inf();
-        if (qd + off < nq) o = sh[qd + off];
-        __syncthreads();
-        v = quad_add(v, o);
-        if (r == 0) st_elem(&sh[qd], v);
+        F c = F::zero();
+        if (qd + off < nq) c = *quad_comp(m.all + (size_t)(qd + off) * QUAD_SLOTS + k, r);
+        __syncthreads();                                   // every quad has read its neighbour before anybody updates
+        *quad_comp(m.slot + tmp, r) = c;
+        __syncwarp();
+        quad_add(m.slot + k, m.slot + k, m.slot + tmp, m.ws);
         __syncthreads();
     }
-    return v;
 }
-// tree sum over the quads of a CTA; the result is valid in quad 0
+// tree sum over the quads of a CTA of slot `k`; the result is left in slot k of quad 0; slot `tmp` is clobbered
 template <class F>
-__device__ XyzzPt<F> quad_block_tree_sum(XyzzPt<F> v, XyzzPt<F>* sh) {
+__device__ void quad_block_tree_sum(QuadMem<F>& m, int k, int tmp) {
     const uint32_t qd = threadIdx.x >> 2, r = threadIdx.x & 3;
     __syncthreads();
-    if (r == 0) st_elem(&sh[qd], v);
-    __syncthreads();
     for (uint32_t stride = blockDim.x >> 3; stride > 0; stride >>= 1) {
-        if ((qd & ~7u) < stride) {                  // whole warps (8 quads) drop out once they hold no active quad; idle quads of a live warp add infinity
-            XyzzPt<F> o = XyzzPt<F>::inf();
-            if (qd < stride) o = sh[qd + stride];
-            v = quad_add(v, o);
-            if (qd < stride && r == 0) st_elem(&sh[qd], v);
+        const bool live = (qd & ~7u) < stride;             // whole warps (8 quads) drop out once they hold no active quad; idle quads of a live warp add infinity
+        F c = F::zero();
+        if (live && qd < stride) c = *quad_comp(m.all + (size_t)(qd + stride) * QUAD_SLOTS + k, r);
+        __syncthreads();
+        if (live) {
+            *quad_comp(m.slot + tmp, r) = c;
+            __syncwarp();
+            quad_add(m.slot + k, m.slot + k, m.slot + tmp, m.ws);
         }
         __syncthreads();
     }
-    return v;
 }
 // CTA -> slot by the slots' rbase; the final points of the accumulation are found through the device-side plan
 // (levels = info[3]: the last level's output buffer and chunk plan).  block_out[2 c] = A_c, block_out[2 c + 1] = R_c.
@@ -630,7 +681,8 @@ template <class F>
 __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce1(const XyzzPt<F>* __restrict__ ptsA, const XyzzPt<F>* __restrict__ ptsB, PlanPtrs pp,
                                                                 const MsmSlot* __restrict__ slots, uint32_t nslots, XyzzPt<F>* __restrict__ block_out) {
     SB_DYN_SMEM(smem_raw);
-    XyzzPt<F>* sh = reinterpret_cast<XyzzPt<F>*>(smem_raw);
+    QuadMem<F> m(smem_raw);
+    enum { RUN = 0, SUM = 1, TMP = 2, AUX = 3 };
     uint32_t j = 0;
     while (j + 1 < nslots && blockIdx.x >= __ldg(&slots[j + 1].rbase)) j++;
     const MsmSlot* sl = slots + j;
@@ -638,49 +690,64 @@ __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce1(const XyzzPt<F>*
     const uint32_t levels = __ldg(&pp.info[3]);
     const XyzzPt<F>* pts = ((levels - 1) & 1) ? ptsB : ptsA;
     const uint32_t* off = pp.plan[levels - 1];
-    const uint32_t qd = threadIdx.x >> 2;
+    const uint32_t qd = threadIdx.x >> 2, r = threadIdx.x & 3;
     const uint64_t lo = ((uint64_t)(blockIdx.x - __ldg(&sl->rbase)) * (blockDim.x >> 2) + qd) * L;
-    XyzzPt<F> run = XyzzPt<F>::inf(), sum = XyzzPt<F>::inf();
+    quad_set_inf(m.slot + RUN, r); quad_set_inf(m.slot + SUM, r);
     for (uint32_t jj = L; jj-- > 0;) {
         const uint64_t b = lo + jj;
-        XyzzPt<F> v = XyzzPt<F>::inf();
+        F c = F::zero();
         if (b < B) {
             const uint32_t k = pp.invperm ? __ldg(&pp.invperm[bbase + (uint32_t)b]) : bbase + (uint32_t)b;      // bucket -> position in the accumulation order
             const uint32_t o = __ldg(&off[k]);
-            if (__ldg(&off[k + 1]) > o) v = ldg_elem(&pts[o]);
+            if (__ldg(&off[k + 1]) > o) c = ldg_elem(quad_comp(&pts[o], r));
         }
-        run = quad_add(run, v);
-        sum = quad_add(sum, run);
+        *quad_comp(m.slot + TMP, r) = c;
+        __syncwarp();
+        quad_add(m.slot + RUN, m.slot + RUN, m.slot + TMP, m.ws);
+        quad_add(m.slot + SUM, m.slot + SUM, m.slot + RUN, m.ws);
     }
-    const XyzzPt<F> suf = quad_block_suffix_scan(run, sh);            // quad 0: R_c
-    const XyzzPt<F> v = quad_add(sum, quad_mul_small(qd ? suf : XyzzPt<F>::inf(), L));
-    const XyzzPt<F> a = quad_block_tree_sum(v, sh);
-    if (threadIdx.x == 0) { st_elem(&block_out[2 * (size_t)blockIdx.x], a); st_elem(&block_out[2 * (size_t)blockIdx.x + 1], suf); }
+    quad_block_suffix_scan(m, RUN, TMP);                               // RUN <- sum of the runs of the quads >= this one; quad 0: R_c
+    if (qd == 0) st_elem(quad_comp(&block_out[2 * (size_t)blockIdx.x + 1], r), *quad_comp(m.slot + RUN, r));
+    if (qd == 0) quad_set_inf(m.slot + RUN, r);
+    __syncwarp();
+    quad_mul_small(m.slot + RUN, m.slot + AUX, L, m.ws);
+    quad_add(m.slot + SUM, m.slot + SUM, m.slot + RUN, m.ws);
+    quad_block_tree_sum(m, SUM, TMP);
+    if (qd == 0) st_elem(quad_comp(&block_out[2 * (size_t)blockIdx.x], r), *quad_comp(m.slot + SUM, r));
 }
 // stage 2: one CTA per slot; quad q takes the stage-1 CTAs [q cpt, (q + 1) cpt) of the slot
 template <class F>
 __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce2(const XyzzPt<F>* __restrict__ block_out, const MsmSlot* __restrict__ slots,
                                                                 XyzzPt<F>* __restrict__ out) {
     SB_DYN_SMEM(smem_raw);
-    XyzzPt<F>* sh = reinterpret_cast<XyzzPt<F>*>(smem_raw);
+    QuadMem<F> m(smem_raw);
+    enum { RUN = 0, SUM = 1, TMP = 2, ACC = 3 };       // sum_j R_{q cpt + j}, sum_j j R_{q cpt + j}, scratch, sum_c A_c
     const MsmSlot* sl = slots + blockIdx.x;
     const uint32_t r0 = __ldg(&sl->rbase), nblocks = __ldg(&sl->rblocks), L = __ldg(&sl->red_l);
-    const uint32_t nq = blockDim.x >> 2, cpt = (nblocks + nq - 1) / nq, qd = threadIdx.x >> 2;
-    XyzzPt<F> accA = XyzzPt<F>::inf(), run = XyzzPt<F>::inf(), sum = XyzzPt<F>::inf();       // sum_c A_c, sum_j R_{q cpt + j}, sum_j j R_{q cpt + j}
+    const uint32_t nq = blockDim.x >> 2, cpt = (nblocks + nq - 1) / nq, qd = threadIdx.x >> 2, r = threadIdx.x & 3;
+    quad_set_inf(m.slot + RUN, r); quad_set_inf(m.slot + SUM, r); quad_set_inf(m.slot + ACC, r);
     for (uint32_t jj = cpt; jj-- > 0;) {
         const uint32_t c = qd * cpt + jj;
-        XyzzPt<F> a = XyzzPt<F>::inf(), rr = XyzzPt<F>::inf();
-        if (c < nblocks) { a = ldg_elem(&block_out[2 * (size_t)(r0 + c)]); rr = ldg_elem(&block_out[2 * (size_t)(r0 + c) + 1]); }
-        accA = quad_add(accA, a);
-        run = quad_add(run, rr);
-        if (jj >= 1) sum = quad_add(sum, run);
+        F a = F::zero(), rr = F::zero();
+        if (c < nblocks) { a = ldg_elem(quad_comp(&block_out[2 * (size_t)(r0 + c)], r)); rr = ldg_elem(quad_comp(&block_out[2 * (size_t)(r0 + c) + 1], r)); }
+        *quad_comp(m.slot + TMP, r) = a;
+        __syncwarp();
+        quad_add(m.slot + ACC, m.slot + ACC, m.slot + TMP, m.ws);
+        *quad_comp(m.slot + TMP, r) = rr;
+        __syncwarp();
+        quad_add(m.slot + RUN, m.slot + RUN, m.slot + TMP, m.ws);
+        if (jj >= 1) quad_add(m.slot + SUM, m.slot + SUM, m.slot + RUN, m.ws);
     }
-    const XyzzPt<F> suf = quad_block_suffix_scan(run, sh);
+    quad_block_suffix_scan(m, RUN, TMP);
     // sum_c c R_c = sum_q [ sum_j j R + cpt * q * run_q ]; the total weighs it by G = quads * L buckets per stage-1 CTA
-    XyzzPt<F> v = quad_add(sum, quad_mul_small(qd ? suf : XyzzPt<F>::inf(), cpt));
-    v = quad_add(accA, quad_mul_small(v, nq * L));
-    const XyzzPt<F> total = quad_block_tree_sum(v, sh);
-    if (threadIdx.x == 0) st_elem(&out[blockIdx.x], total);
+    if (qd == 0) quad_set_inf(m.slot + RUN, r);
+    __syncwarp();
+    quad_mul_small(m.slot + RUN, m.slot + TMP, cpt, m.ws);
+    quad_add(m.slot + SUM, m.slot + SUM, m.slot + RUN, m.ws);
+    quad_mul_small(m.slot + SUM, m.slot + TMP, nq * L, m.ws);
+    quad_add(m.slot + SUM, m.slot + SUM, m.slot + ACC, m.ws);
+    quad_block_tree_sum(m, SUM, TMP);
+    if (qd == 0) st_elem(quad_comp(&out[blockIdx.x], r), *quad_comp(m.slot + SUM, r));
 }
 
 // ------------------------------------------------------------------ base expansion / affine conversion
@@ -800,14 +867,16 @@ void msm_group_prepare(const std::vector<const AffinePt<F>*>& bases_dev, const s
     {   // quads per reduction CTA: 64, fewer when every slot of the group is tiny
         size_t mmax = 0;
         for (size_t j = 0; j < J; j++) mmax = std::max(mmax, ms[j]);
-        const uint32_t nbmax = 1u << (msm_layout(mmax).c - 1);
+        const uint32_t nbmax = 1u << (msm_layout(mmax, mmax).c - 1);
         out.red_quads = 8;
         while (out.red_quads < (uint32_t)RED_QUADS && out.red_quads * 4 < nbmax) out.red_quads *= 2;
     }
+    size_t group_max = 0;
+    for (size_t j = 0; j < J; j++) group_max = std::max(group_max, ms[j]);
     for (size_t j = 0; j < J; j++) {
         MsmSlot& s = out.slots[j];
         SB_REQUIRE(ms[j] >= 1 && ms[j] < ((size_t)1 << 31), "msm: slot size out of range");
-        s.m = (uint32_t)ms[j]; s.lay = msm_layout(ms[j]);
+        s.m = (uint32_t)ms[j]; s.lay = msm_layout(ms[j], group_max);
         s.nb = 1u << (s.lay.c - 1);
         // buckets per quad in the first reduction stage (see k_bucket_reduce1): 2 L chained additions per quad
         const uint32_t red_l = red_env ? red_env : 4u;
@@ -957,8 +1026,15 @@ void msm_group_tail(const MsmGroup<F>& g, XyzzPt<F>* out_dev, cudaStream_t strea
         SB_LAUNCH_NAMED(SB_KNAME(F, "k_seg_accum_full"), (k_seg_accum<F, false>), grid, ACC_THREADS, 0, stream, g.tab.get(), sc.sorted.get(),
                         (const AffinePt<F>*)nullptr, inp, sc.plan[l - 1].get(), sc.plan[l].get(), B, l, sc.info.get(), (const uint32_t*)nullptr, outp);
     }
-    const size_t smem = g.red_quads * sizeof(XyzzPt<F>);
+    const size_t smem = red_smem_bytes<F>(g.red_quads);
     const int red_threads = 4 * (int)g.red_quads;
+    static bool attr_set = false;       // (per instantiation) more than the default 48 KB of dynamic shared memory
+    if (!attr_set) {
+        const int cap = (int)red_smem_bytes<F>(RED_QUADS);
+        SB_CUDA(cudaFuncSetAttribute((const void*)k_bucket_reduce1<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        SB_CUDA(cudaFuncSetAttribute((const void*)k_bucket_reduce2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        attr_set = true;
+    }
     SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce1"), (k_bucket_reduce1<F>), (int)g.rtot, red_threads, smem, stream, sc.ptsA.get(), sc.ptsB.get(), pp,
                     g.slots_dev.get(), J, sc.block_out.get());
     SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce2"), (k_bucket_reduce2<F>), (int)J, red_threads, smem, stream, sc.block_out.get(), g.slots_dev.get(), out_dev);

@@ -31,7 +31,7 @@ struct WinLayout {
     int c;
     uint16_t shift[72];
 };
-WinLayout msm_layout(size_t m);
+WinLayout msm_layout(size_t m, size_t group_max_m);   // group_max_m: the largest slot of the group the MSM belongs to
 
 constexpr int MSM_MAX_SLOTS = 32;
 constexpr int MSM_MAX_LEVELS = 8;        // accumulation levels a pipeline launches (levels the plan does not use exit at once)

@@ -38,11 +38,18 @@ def summary(path):
         print()
 
 
-def launches(path):
+def launches(path, marker=None, which=-2):
+    """marker: a kernel that runs once per proof (k_pair_diff opens every proof): only the launches between two of its
+    occurrences are counted (`which` = index of the first one; -2 = the last complete proof of the capture)."""
     rows = list(csv.reader(open(path)))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     hdr, data = rows[hi], rows[hi + 1:]
     kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    data = [r for r in data if len(r) > mv]
+    if marker:
+        idx = [i for i, r in enumerate(data) if marker in r[kn]]
+        data = data[idx[which]:idx[which + 1]] if which + 1 != 0 else data[idx[which]:]
+        print("one proof: the launches from one %s to the next" % marker)
     acc = collections.OrderedDict()
     for r in data:
         if len(r) > mv:
@@ -56,6 +63,6 @@ def launches(path):
 
 if __name__ == "__main__":
     if len(sys.argv) >= 3 and sys.argv[1] == "--launches":
-        launches(sys.argv[2])
+        launches(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
     else:
         summary(sys.argv[1])

@@ -48,7 +48,6 @@ struct BlockState {
     std::barrier<>* block_bar;
     std::vector<std::unique_ptr<std::barrier<>>>* warp_bar;
     uint32_t (*xch)[32];
-    unsigned char (*xchbig)[32][512];      // whole-element shuffles (shfl_elem in csrc/common.cuh)
     unsigned char* dyn_smem;
     unsigned nthreads;
 };
@@ -83,18 +82,6 @@ static inline uint32_t __shfl_sync(unsigned, uint32_t v, int src) {
     x[lane] = v;
     (*emu::g_block->warp_bar)[warp]->arrive_and_wait();
     const uint32_t r = ((unsigned)src < live) ? x[src] : v;
-    (*emu::g_block->warp_bar)[warp]->arrive_and_wait();
-    return r;
-}
-// a whole element from lane `src` in one exchange (the product shuffles it word by word on the device)
-template <class T> static inline T emu_shfl_elem(const T& v, int src) {
-    static_assert(sizeof(T) <= 512, "element too large for the emulated shuffle buffer");
-    const unsigned lane = emu::t_threadIdx.x & 31, warp = emu::t_threadIdx.x >> 5;
-    const unsigned live = std::min(32u, emu::g_block->nthreads - 32 * warp);
-    memcpy(emu::g_block->xchbig[warp][lane], &v, sizeof(T));
-    (*emu::g_block->warp_bar)[warp]->arrive_and_wait();
-    T r = v;
-    if ((unsigned)src < live) memcpy(&r, emu::g_block->xchbig[warp][src], sizeof(T));
     (*emu::g_block->warp_bar)[warp]->arrive_and_wait();
     return r;
 }

@@ -56,12 +56,11 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& fn)
     if (n == 0 || grid.x == 0) return;
     std::vector<unsigned char> dyn(smem + 64);
     uint32_t (*xch)[32] = new uint32_t[(n + 31) / 32][32];
-    unsigned char (*xchbig)[32][512] = new unsigned char[(n + 31) / 32][32][512];
     for (unsigned b = 0; b < grid.x; b++) {
         std::barrier<> bar((std::ptrdiff_t)n);
         std::vector<std::unique_ptr<std::barrier<>>> wb;
         for (unsigned w = 0; w < (n + 31) / 32; w++) wb.emplace_back(new std::barrier<>((std::ptrdiff_t)std::min(32u, n - 32 * w)));
-        BlockState st{&bar, &wb, xch, xchbig, (unsigned char*)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63), n};
+        BlockState st{&bar, &wb, xch, (unsigned char*)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63), n};
         g_block = &st;
         if (n == 1) {      // single-thread blocks run inline
             t_threadIdx = uint3{0, 0, 0}; t_blockIdx = uint3{b, 0, 0}; t_blockDim = block; t_gridDim = grid;
@@ -72,6 +71,5 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& fn)
         g_block = nullptr;
     }
     delete[] xch;
-    delete[] xchbig;
 }
 }  // namespace emu

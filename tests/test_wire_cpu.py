@@ -151,3 +151,21 @@ def test_commitment_keys_round_trip(oracle, compressed):
     if not compressed:
         pairs = wire.key_cache_from_bytes(wire.key_cache_to_bytes([(back, vback), (back, vback)]))
         assert len(pairs) == 2 and np.array_equal(pairs[1][0]["powers_of_h"][1], ph[1])
+
+
+def test_rust_shim_lists_every_export():
+    """rust/src/ffi.rs declares exactly the symbols include/spartan_b200.h exports, and rust/build.rs compiles exactly the
+    Makefile's source list (the Rust side cannot be compiled here: this keeps it from drifting)."""
+    import os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "spartan_b200.h")).read()
+    ffi = open(os.path.join(root, "rust", "src", "ffi.rs")).read()
+    c_syms = set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", hdr))
+    rs_syms = set(re.findall(r"pub fn (sb_[a-z0-9_]+)\s*\(", ffi))
+    assert c_syms == rs_syms, (sorted(c_syms - rs_syms), sorted(rs_syms - c_syms))
+    import r1cs_spartan_b200 as sb
+    assert set(sb.EXPORTS) <= c_syms | {"sb_selftest_inverse"}, sorted(set(sb.EXPORTS) - c_syms)
+    mk = open(os.path.join(root, "r1cs-spartan_b200", "Makefile")).read()
+    mk_src = set(re.findall(r"csrc/([a-z_]+\.cu)", re.search(r"^SRC := (.*)$", mk, re.M).group(1)))
+    rs_src = set(re.findall(r'"([a-z_]+\.cu)"', open(os.path.join(root, "rust", "build.rs")).read()))
+    assert mk_src == rs_src, (mk_src, rs_src)
