@@ -167,21 +167,3 @@ SB_D void st_elem(T* p, const T& v) {
     *p = v;
 #endif
 }
-
-// 16 bytes global -> shared without passing through registers (LDGSTS); sb_cp_async_wait: all copies this thread has issued
-// have landed.  Under the CUDA-on-CPU test shim the copy is immediate.
-SB_D void sb_cp_async16(void* smem_dst, const void* gmem_src) {
-#if defined(SB_EMUL)
-    memcpy(smem_dst, gmem_src, 16);
-#elif defined(__CUDA_ARCH__)
-    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-#else
-    (void)smem_dst; (void)gmem_src;
-#endif
-}
-SB_D void sb_cp_async_wait() {
-#if !defined(SB_EMUL) && defined(__CUDA_ARCH__)
-    asm volatile("cp.async.wait_all;" ::: "memory");
-#endif
-}

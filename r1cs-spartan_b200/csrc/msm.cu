@@ -412,12 +412,7 @@ __device__ __forceinline__ int pair_classify_x(const F& px, const F& qx, bool ha
 // warp, the entry indices and the results are read and written as contiguous runs, and every lane runs the same number
 // of iterations (a first version with per-thread contiguous shares and bucket-by-bucket loops had 17.9 of 32 lanes
 // active: ncu, profiles/r02_ncu_affine_round_v1.txt).
-// STAGED: the inputs of iteration i + 1 (two x coordinates in the first pass; two points and a prefix product in the second)
-// are copied global -> shared memory with cp.async while iteration i computes -- no destination registers (the kernel has
-// none to spare at 254), no waiting until the data is consumed.  ncu of the unstaged kernel
-// (profiles/r02_ncu_affine_round_v3.txt) attributes 24 % of its stall samples to long-scoreboard waits right behind these
-// loads.  Each thread owns a column of 16-byte chunks (chunk c of thread t at (c * AFF_THREADS + t) * 16: conflict-free).
-template <class F, bool FIRST, bool STAGED>
+template <class F, bool FIRST>
 __global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
                                                               const AffinePt<F>* __restrict__ in_aff, const uint32_t* __restrict__ in_off,
                                                               const uint32_t* __restrict__ out_off, uint32_t B, uint32_t nthreads,
@@ -461,39 +456,20 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>*
         pr.p1 = pr.has2 ? in_ptr(ib + 2 * j + 1, pr.n1) : pr.p0;
         return pr;
     };
-    // (Requesting the next iteration's cache lines one iteration ahead with prefetch instructions was measured in round 2,
-    // sweep 8: 41.6 against 41.0 ms per proof -- the long-scoreboard stalls ncu shows are the stack traffic of the outlined
-    // Fq2 products, not the table gathers -- and removed.)
-    // staging area of this thread (STAGED): chunks [0, 2 PT) = P, Q; [2 PT, 2 PT + FE) = prefix product
-    constexpr int FE = (int)(sizeof(F) / 16), PT = 2 * FE;
-    SB_DYN_SMEM(smem_raw);
-    uint4* const stg = reinterpret_cast<uint4*>(smem_raw) + threadIdx.x;
-    auto fetch = [&](const void* g, int chunk0, int n) {
-        const uint4* src = static_cast<const uint4*>(g);
-        for (int c = 0; c < n; c++) sb_cp_async16(stg + (size_t)(chunk0 + c) * AFF_THREADS, src + c);
-    };
-    auto take = [&](void* dst, int chunk0, int n) {
-        uint4* d = static_cast<uint4*>(dst);
-#pragma unroll
-        for (int c = 0; c < n; c++) d[c] = stg[(size_t)(chunk0 + c) * AFF_THREADS];
-    };
+    // (Two attempts at hiding the latency of these loads were measured in round 2 and removed: prefetch instructions one
+    // iteration ahead, sweep 8: 41.6 against 41.0 ms per proof; cp.async staging of the next iteration's points and prefix
+    // product in shared memory, sweep 11: 39.4 against 39.2 ms, the kernel itself 4.47 against 3.80 ms under ncu
+    // (profiles/r02_ncu_affine_round_v4_staged.txt) -- the long-scoreboard stalls are local-memory traffic of the register
+    // spills and of the outlined Fq2 products' operands, and the shared-memory carve-out took L1 away from exactly that:
+    // local-load hit rate 86 % -> 72 %.)
     // pass 1: prefix products of the denominators (x coordinates only)
     F acc = F::one();
     Pair cur = locate(first), nxt = cur;
-    if (STAGED) { fetch(&cur.p0->x, 0, FE); if (cur.has2) fetch(&cur.p1->x, PT, FE); }
     for (uint32_t i = 0; i < iters; i++) {
+        if (i + 1 < iters) nxt = locate(first + 32 * (i + 1));
         const AffinePt<F>* pp0 = cur.p0; const AffinePt<F>* pp1 = cur.p1;
         const bool has2 = cur.has2, n0 = cur.n0, n1 = cur.n1;
-        F px, qx;
-        if (STAGED) {
-            sb_cp_async_wait();
-            take(&px, 0, FE);
-            if (has2) take(&qx, PT, FE); else qx = px;
-            if (i + 1 < iters) { nxt = locate(first + 32 * (i + 1)); fetch(&nxt.p0->x, 0, FE); if (nxt.has2) fetch(&nxt.p1->x, PT, FE); }
-        } else {
-            if (i + 1 < iters) nxt = locate(first + 32 * (i + 1));
-            px = ldg_elem(&pp0->x); qx = has2 ? ldg_elem(&pp1->x) : px;
-        }
+        const F px = ldg_elem(&pp0->x), qx = has2 ? ldg_elem(&pp1->x) : px;
         F d;
         pair_classify_x(px, qx, has2, [&](int k) { F y = ldg_elem(k ? &pp1->y : &pp0->y); return (k ? n1 : n0) ? F::neg(y) : y; }, d);
         st_elem(&prefix[(size_t)i * nthreads + t], acc);
@@ -502,33 +478,17 @@ __global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>*
     }
     F inv = F::inv_fast(acc);
     // pass 2, backwards: 1/d_k = inv * prefix_k, then inv *= d_k   (cur is the last output's pair: the first pass left it there)
-    if (STAGED) { fetch(cur.p0, 0, PT); if (cur.has2) fetch(cur.p1, PT, PT); fetch(&prefix[(size_t)(iters - 1) * nthreads + t], 2 * PT, FE); }
     for (uint32_t i = iters; i-- > 0;) {
+        if (i > 0) nxt = locate(first + 32 * (i - 1));
         const uint32_t p = first + 32 * i;
         const bool has2 = cur.has2;
-        AffinePt<F> P, Q;
-        F pf;
-        if (STAGED) {
-            sb_cp_async_wait();
-            take(&P, 0, PT);
-            if (has2) take(&Q, PT, PT);
-            take(&pf, 2 * PT, FE);
-            if (i > 0) {
-                nxt = locate(first + 32 * (i - 1));
-                fetch(nxt.p0, 0, PT); if (nxt.has2) fetch(nxt.p1, PT, PT); fetch(&prefix[(size_t)(i - 1) * nthreads + t], 2 * PT, FE);
-            }
-        } else {
-            if (i > 0) nxt = locate(first + 32 * (i - 1));
-            P = ldg_elem(cur.p0);
-            if (has2) Q = ldg_elem(cur.p1);
-            pf = ldg_elem(&prefix[(size_t)i * nthreads + t]);
-        }
+        AffinePt<F> P = ldg_elem(cur.p0), Q = has2 ? ldg_elem(cur.p1) : P;
         if (cur.n0) P.y = F::neg(P.y);
         if (has2 && cur.n1) Q.y = F::neg(Q.y);
         if (!has2) Q = P;
         F d;
         const int kind = pair_classify_x(P.x, Q.x, has2, [&](int k) { return k ? Q.y : P.y; }, d);
-        const F dinv = F::mul(inv, pf);
+        const F dinv = F::mul(inv, ldg_elem(&prefix[(size_t)i * nthreads + t]));
         inv = F::mul(inv, d);
         AffinePt<F> r;
         if (kind == PAIR_COPY_P) r = P;
@@ -884,10 +844,6 @@ static uint32_t msm_affine_rounds(uint64_t etot) {
     return etot >= ((uint64_t)1 << lg) ? rounds : 0;
 }
 static uint32_t msm_affine_kmax() { static const uint32_t v = msm_env_u32("SB_MSM_AFFINE_K", 256, 1, 1024); return v; }
-// staging through shared memory in the affine rounds (see k_affine_round); SB_MSM_STAGED=0 selects the direct loads
-static bool msm_staged() { static const bool v = msm_env_u32("SB_MSM_STAGED", 1, 0, 1) != 0; return v; }
-template <class F>
-static size_t aff_smem_bytes() { return (size_t)AFF_THREADS * 5 * sizeof(F); }     // P, Q (2 F each) + one prefix product per thread
 // CTAs of the round kernel an SM holds (registers decide: 4 over Fq2, 6-8 over Fq); the rounds are sized to exactly one wave
 template <class F>
 static uint32_t msm_affine_ctas_per_sm() {
@@ -896,14 +852,8 @@ static uint32_t msm_affine_ctas_per_sm() {
     static uint32_t cached = 0;
     if (!cached) {
         int a = 0, b = 0;
-        const size_t smem = msm_staged() ? aff_smem_bytes<F>() : 0;
-        if (msm_staged()) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_affine_round<F, true, true>, AFF_THREADS, smem) != cudaSuccess) a = 4;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_affine_round<F, false, true>, AFF_THREADS, smem) != cudaSuccess) b = 4;
-        } else {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_affine_round<F, true, false>, AFF_THREADS, smem) != cudaSuccess) a = 4;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_affine_round<F, false, false>, AFF_THREADS, smem) != cudaSuccess) b = 4;
-        }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_affine_round<F, true>, AFF_THREADS, 0) != cudaSuccess) a = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_affine_round<F, false>, AFF_THREADS, 0) != cudaSuccess) b = 4;
         cached = (uint32_t)std::max(1, std::min(a, b));
     }
     return cached;
@@ -921,7 +871,7 @@ void msm_group_prepare(const std::vector<const AffinePt<F>*>& bases_dev, const s
         size_t mmax = 0;
         for (size_t j = 0; j < J; j++) mmax = std::max(mmax, ms[j]);
         const uint32_t nbmax = 1u << (msm_layout(mmax, mmax).c - 1);
-        static const uint32_t quads_cap = msm_env_u32("SB_MSM_RED_QUADS", RED_QUADS, 8, RED_QUADS);
+        static const uint32_t quads_cap = msm_env_u32("SB_MSM_RED_QUADS", 32, 8, RED_QUADS);
         out.red_quads = 8;
         while (out.red_quads * 2 <= quads_cap && out.red_quads * 4 < nbmax) out.red_quads *= 2;
     }
@@ -932,8 +882,11 @@ void msm_group_prepare(const std::vector<const AffinePt<F>*>& bases_dev, const s
         SB_REQUIRE(ms[j] >= 1 && ms[j] < ((size_t)1 << 31), "msm: slot size out of range");
         s.m = (uint32_t)ms[j]; s.lay = msm_layout(ms[j], group_max);
         s.nb = 1u << (s.lay.c - 1);
-        // buckets per quad in the first reduction stage (see k_bucket_reduce1): 2 L chained additions per quad
-        const uint32_t red_l = red_env ? red_env : 4u;
+        // buckets per quad in the first reduction stage (see k_bucket_reduce1): 2 L chained additions per quad.  Measured in
+        // round 2 (sweep 11), quads per CTA x L at 2^20 / 2^17 constraints: 64 x 4: 39.4 / 11.1 ms; 32 x 8: 39.4 / 10.6;
+        // 32 x 4: 39.5 / 11.2; 16 x 8: 39.8 / 11.2; 32 x 16: 40.0 / 11.0 -- 32 quads (one warp per scheduler: the quads'
+        // products do not queue behind one another on the integer pipe) with 8 buckets each
+        const uint32_t red_l = red_env ? red_env : 8u;
         s.red_l = s.nb >= red_l * out.red_quads ? red_l : 1;
         const uint32_t nquads = (s.nb + s.red_l - 1) / s.red_l;
         s.rblocks = (nquads + out.red_quads - 1) / out.red_quads;
@@ -1054,13 +1007,12 @@ void msm_group_accum(const MsmGroup<F>& g, cudaStream_t stream) {
     for (uint32_t r = 0; r < g.R; r++) {
         AffinePt<F>* outp = (r % 2 == 0) ? sc.affA.get() : sc.affB.get();
         const int grid = (int)((g.round_threads[r] + AFF_THREADS - 1) / AFF_THREADS);
-        const size_t smem = msm_staged() ? aff_smem_bytes<F>() : 0;
-#define SB_AFF_LAUNCH(FIRST_, STAGED_)                                                                                                              \
-        SB_LAUNCH_NAMED(SB_KNAME(F, "k_affine_round"), (k_affine_round<F, FIRST_, STAGED_>), grid, AFF_THREADS, smem, stream, g.tab.get(), sc.sorted.get(), \
-                        aff, seg0, sc.hplan[r].get(), B, g.round_threads[r], sc.prefix.get(), outp)
-        if (r == 0) { if (msm_staged()) SB_AFF_LAUNCH(true, true); else SB_AFF_LAUNCH(true, false); }
-        else { if (msm_staged()) SB_AFF_LAUNCH(false, true); else SB_AFF_LAUNCH(false, false); }
-#undef SB_AFF_LAUNCH
+        if (r == 0)
+            SB_LAUNCH_NAMED(SB_KNAME(F, "k_affine_round"), (k_affine_round<F, true>), grid, AFF_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), aff, seg0,
+                            sc.hplan[r].get(), B, g.round_threads[r], sc.prefix.get(), outp);
+        else
+            SB_LAUNCH_NAMED(SB_KNAME(F, "k_affine_round"), (k_affine_round<F, false>), grid, AFF_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), aff, seg0,
+                            sc.hplan[r].get(), B, g.round_threads[r], sc.prefix.get(), outp);
         aff = outp; seg0 = sc.hplan[r].get();
     }
     const int grid = (int)((std::max<uint32_t>(g.items_bound[0], 1) + ACC_THREADS - 1) / ACC_THREADS);
