@@ -69,6 +69,9 @@ typedef struct {
 sb_status sb_comm_shm_open(const char* name, int rank, int world, int create, sb_comm* out);
 /* The same mailbox in process memory for `world` contexts driven by threads of one process; fills out[0..world). */
 sb_status sb_comm_local_open(int world, sb_comm* out);
+/* a rank whose library call failed locally releases the peers that wait for it in an exchange (they fail that call at once
+ * instead of after SB_COMM_TIMEOUT_S); the multi-GPU context does this for its shards by itself */
+void sb_comm_shm_abort(sb_comm* comm);
 void sb_comm_shm_close(sb_comm* comm);
 
 /* ---- context ---------------------------------------------------------------------------------- */

@@ -133,6 +133,14 @@ sb_status sb_comm_local_open(int world, sb_comm* out) {
     }
     return SB_OK;
 }
+// A rank whose library call failed locally (bad argument on one rank only, out of memory, a CUDA error) tells its peers:
+// its sequence number jumps to the next epoch, so a peer waiting for it inside an allgather stops waiting and fails that
+// call with a mismatch at once instead of after the time-out.  The next library call re-aligns everybody (shm_barrier).
+void sb_comm_shm_abort(sb_comm* comm) {
+    if (!comm || !comm->user) return;
+    ShmComm* c = static_cast<ShmComm*>(comm->user);
+    c->reg->seq[c->rank].store((c->epoch + 1) << 32, std::memory_order_release);
+}
 void sb_comm_shm_close(sb_comm* comm) {
     if (!comm || !comm->user) return;
     ShmComm* c = static_cast<ShmComm*>(comm->user);

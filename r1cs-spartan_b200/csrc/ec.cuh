@@ -72,11 +72,7 @@ struct alignas(16) XyzzPt {
         F PP = F::sqr(Pp), PPP = F::mul(Pp, PP), Q = F::mul(p.X, PP);
         XyzzPt o;
         o.X = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
-#if defined(SB_LAZY_Y3)
-        o.Y = F::mul_sub_mul(R, F::sub(Q, o.X), p.Y, PPP);      // one Montgomery reduction per component instead of two
-#else
         o.Y = F::sub(F::mul(R, F::sub(Q, o.X)), F::mul(p.Y, PPP));
-#endif
         o.ZZ = F::mul(p.ZZ, PP);
         o.ZZZ = F::mul(p.ZZZ, PPP);
         return o;
@@ -95,11 +91,7 @@ struct alignas(16) XyzzPt {
         F PP = F::sqr(Pp), PPP = F::mul(Pp, PP), Q = F::mul(U1, PP);
         XyzzPt o;
         o.X = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
-#if defined(SB_LAZY_Y3)
-        o.Y = F::mul_sub_mul(R, F::sub(Q, o.X), S1, PPP);
-#else
         o.Y = F::sub(F::mul(R, F::sub(Q, o.X)), F::mul(S1, PPP));
-#endif
         o.ZZ = F::mul(F::mul(p.ZZ, q.ZZ), PP);
         o.ZZZ = F::mul(F::mul(p.ZZZ, q.ZZZ), PPP);
         return o;

@@ -130,20 +130,6 @@ struct alignas(16) Fp {
         return mul_portable(a, b);
 #endif
     }
-    // a b - c d.  With SB_LAZY_Y3 (Fq on the device): two wide products, ONE Montgomery reduction -- the operands are
-    // < p, so a b - c d + p^2 lies in (0, 2 p^2), below the p 2^384 that fq_redc_ptx accepts.
-    SB_HD static Fp mul_sub_mul(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
-#if defined(__CUDA_ARCH__) && defined(SB_LAZY_Y3)
-        if constexpr (N == 12) {
-            uint32_t t[24], w[24], u[24];
-            fq_mul_wide_ptx(t, a.l, b.l);
-            fq_mul_wide_ptx(w, c.l, d.l);
-            fq_wide_subp2_ptx(u, t, w);
-            Fp o; fq_redc_ptx(o.l, u); return o;
-        }
-#endif
-        return sub(mul(a, b), mul(c, d));
-    }
     SB_HD static Fp sqr(const Fp& a) { return mul(a, a); }
     SB_HD static Fp dbl(const Fp& a) { return add(a, a); }
     SB_HD static Fp neg(const Fp& a) { return sub(zero(), a); }
@@ -362,41 +348,6 @@ struct alignas(16) Fq2 {
         Fq v0 = Fq::mul(a.c0, b.c0), v1 = Fq::mul(a.c1, b.c1);
         Fq s = Fq::mul(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
         Fq2 o; o.c0 = Fq::sub(v0, v1); o.c1 = Fq::sub(Fq::sub(s, v0), v1); return o;
-#endif
-    }
-    // a b - c d with lazy reduction (SB_LAZY_Y3, device): six wide products, TWO Montgomery reductions instead of
-    // four.  With every operand limb-vector < p:  re = (a0 b0 - a1 b1 + p^2) + (c1 d1 - c0 d0 + p^2) in (0, 4 p^2);
-    // im = (a0 b1 + a1 b0) - (c0 d1 + c1 d0) + 2 p^2 in (0, 4 p^2); 4 p^2 < 0.67 * 2^764 < p 2^384 = 1.62 * 2^764,
-    // the bound fq_redc_ptx needs; no 768-bit intermediate overflows (sums of two products < 2 p^2 each, and
-    // (a0 + a1)(b0 + b1) < 4 p^2).  The same streams are executed on big integers by tests/test_cpu_oracle.py.
-    SB_FQ2_FN static Fq2 mul_sub_mul(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) {
-#if defined(__CUDA_ARCH__) && defined(SB_LAZY_Y3)
-        uint32_t t0[24], t1[24], t2[24], re[24], x[24], sum[24], sa[12], sb[12];
-        fq_mul_wide_ptx(t0, a.c0.l, b.c0.l);
-        fq_mul_wide_ptx(t1, a.c1.l, b.c1.l);
-        fq_wide_subp2_ptx(re, t0, t1);                 // a0 b0 - a1 b1 + p^2
-        fq_wide_add2_ptx(sum, t0, t1);
-        fq_wide_addn_ptx(sa, a.c0.l, a.c1.l);
-        fq_wide_addn_ptx(sb, b.c0.l, b.c1.l);
-        fq_mul_wide_ptx(t2, sa, sb);
-        fq_wide_sub_ptx(x, t2, sum);                   // a0 b1 + a1 b0
-        fq_mul_wide_ptx(t0, c.c0.l, d.c0.l);
-        fq_mul_wide_ptx(t1, c.c1.l, d.c1.l);
-        fq_wide_subp2_ptx(t2, t1, t0);                 // c1 d1 - c0 d0 + p^2
-        uint32_t re2[24];
-        fq_wide_add2_ptx(re2, re, t2);
-        Fq2 o;
-        fq_redc_ptx(o.c0.l, re2);
-        fq_wide_add2_ptx(sum, t0, t1);
-        fq_wide_addn_ptx(sa, c.c0.l, c.c1.l);
-        fq_wide_addn_ptx(sb, d.c0.l, d.c1.l);
-        fq_mul_wide_ptx(t2, sa, sb);
-        fq_wide_sub_ptx(re, t2, sum);                  // c0 d1 + c1 d0
-        fq_wide_sub2p2_ptx(t2, x, re);
-        fq_redc_ptx(o.c1.l, t2);
-        return o;
-#else
-        return sub(mul(a, b), mul(c, d));
 #endif
     }
     SB_FQ2_FN static Fq2 sqr(const Fq2& a) {

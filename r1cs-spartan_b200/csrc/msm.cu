@@ -1035,12 +1035,16 @@ void msm_group_tail(const MsmGroup<F>& g, XyzzPt<F>* out_dev, cudaStream_t strea
     }
     const size_t smem = red_smem_bytes<F>(g.red_quads);
     const int red_threads = 4 * (int)g.red_quads;
-    static bool attr_set = false;       // (per instantiation) more than the default 48 KB of dynamic shared memory
-    if (!attr_set) {
+    // more than the default 48 KB of dynamic shared memory: a function attribute, set once per DEVICE (a multi-GPU context
+    // drives several devices from one process) and per instantiation
+    static std::atomic<uint64_t> attr_set{0};
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    if (!((attr_set.load(std::memory_order_acquire) >> (dev & 63)) & 1)) {
         const int cap = (int)red_smem_bytes<F>(RED_QUADS);
         SB_CUDA(cudaFuncSetAttribute((const void*)k_bucket_reduce1<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
         SB_CUDA(cudaFuncSetAttribute((const void*)k_bucket_reduce2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-        attr_set = true;
+        attr_set.fetch_or((uint64_t)1 << (dev & 63), std::memory_order_release);
     }
     SB_LAUNCH_NAMED(SB_KNAME(F, "k_bucket_reduce1"), (k_bucket_reduce1<F>), (int)g.rtot, red_threads, smem, stream, sc.ptsA.get(), sc.ptsB.get(), pp,
                     g.slots_dev.get(), J, sc.block_out.get());

@@ -1055,7 +1055,12 @@ static sb_status multi_call(sb_ctx* m, Fn fn) {
         std::lock_guard<std::mutex> g(w.m);
         sb_ctx* sc = m->shards[r];
         const int rank = (int)r;
-        w.job = [fn, rank, sc]() -> sb_status { return fn(rank, sc); };
+        sb_comm* cm = &m->shard_comms[r];
+        w.job = [fn, rank, sc, cm]() -> sb_status {
+            const sb_status st = fn(rank, sc);
+            if (st != SB_OK) sb_comm_shm_abort(cm);         // peers waiting for this shard in an exchange fail at once, not after the time-out
+            return st;
+        };
         w.has_job = true; w.done = false;
         w.cv.notify_all();
     }
@@ -1064,7 +1069,10 @@ static sb_status multi_call(sb_ctx* m, Fn fn) {
         sb_ctx::Worker& w = *m->workers[r];
         std::unique_lock<std::mutex> lk(w.m);
         w.cv.wait(lk, [&] { return w.done; });
-        if (w.result != SB_OK && st == SB_OK) { st = w.result; m->last_error = "rank " + std::to_string(r) + ": " + m->shards[r]->last_error; }
+        // the root cause is the shard that failed for a reason of its own; the others only report the broken exchange
+        if (w.result != SB_OK && (st == SB_OK || (st == SB_ECOMM && w.result != SB_ECOMM))) {
+            st = w.result; m->last_error = "rank " + std::to_string(r) + ": " + m->shards[r]->last_error;
+        }
     }
     return st;
 }

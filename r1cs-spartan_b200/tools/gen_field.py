@@ -5,7 +5,7 @@ for the two BLS12-381 prime fields in 32-bit limbs (Fr: 8 limbs, Fq: 12 limbs).
 
 The instruction stream is produced ONCE as an abstract list and rendered twice: as PTX text for the
 header, and through a bit-exact 32-bit-register + carry-flag emulator (`emulate`) that
-tests/test_field_gen.py runs against Python big integers -- so the sequence nvcc compiles is the
+tests/test_cpu_oracle.py (test_generated_field_streams_under_emulation, test_lazy_reduction_sequences_under_emulation) runs against Python big integers -- so the sequence nvcc compiles is the
 sequence that was verified on the CPU.
 
 Scheme (per row i of b):   T = E + 2^32 * O   (E: even-offset accumulator, O: odd-offset accumulator)
@@ -442,7 +442,7 @@ def render_lazy(fname, f):
                                 [("t%d" % k, "t[%d]" % k) for k in range(2 * N)] + [("p%d" % k, "%s_MOD_C[%d]" % (U, k)) for k in range(N)] +
                                 [("pinv", "%s_MOD_C[%d]" % (U, N))],
                                 "uint32_t* __restrict__ r, const uint32_t* t"))
-    for kind, M in (("subp2", 2 * N), ("sub", 2 * N), ("addn", N), ("sub2p2", 2 * N), ("add2", 2 * N)):
+    for kind, M in (("subp2", 2 * N), ("sub", 2 * N), ("addn", N)):
         parts.append(render_general("%s_wide_%s_ptx" % (fname, kind), gen_wide_op(N, kind, p),
                                     [("r%d" % k, "r[%d]" % k) for k in range(M)],
                                     [("a%d" % k, "a[%d]" % k) for k in range(M)] + [("b%d" % k, "b[%d]" % k) for k in range(M)],
@@ -453,7 +453,7 @@ def render_lazy(fname, f):
 def main(out_path):
     parts = ["// GENERATED by tools/gen_field.py -- do not edit.  Unrolled PTX carry-chain field arithmetic\n"
              "// (32-bit limbs, Montgomery radix 2^(32 N)) for BLS12-381 Fr (N=8) and Fq (N=12).\n"
-             "// The same instruction streams are verified against big integers by tests/test_field_gen.py.\n"
+             "// The same instruction streams are verified against big integers by tests/test_cpu_oracle.py (test_generated_field_streams_under_emulation, test_lazy_reduction_sequences_under_emulation).\n"
              "#pragma once\n#include <cstdint>\n"]
     for fname, f in FIELDS.items():
         N = f["N"]; p = f["p"]; R = 1 << (32 * N)

@@ -52,6 +52,7 @@ extern "C" {
     // ---- exchange layers shipped with the library
     pub fn sb_comm_shm_open(name: *const c_char, rank: c_int, world: c_int, create: c_int, out: *mut sb_comm) -> c_int;
     pub fn sb_comm_local_open(world: c_int, out: *mut sb_comm) -> c_int;
+    pub fn sb_comm_shm_abort(comm: *mut sb_comm);
     pub fn sb_comm_shm_close(comm: *mut sb_comm);
 
     // ---- contexts.  sb_ctx_create_multi: ONE context over several GPUs of this process, so that

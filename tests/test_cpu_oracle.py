@@ -168,8 +168,8 @@ def test_generated_field_streams_under_emulation():
 
 
 def test_lazy_reduction_sequences_under_emulation():
-    # The Fq2 product (Fq2::mul, device path) and the fused a b - c d (Fp/Fq2::mul_sub_mul, -DSB_LAZY_Y3) are
-    # compositions of generated streams (wide product, wide add/sub, Montgomery reduction).  Execute the same
+    # The Fq2 product (Fq2::mul, device path) is a
+    # composition of generated streams (wide product, wide add/sub, Montgomery reduction).  Execute the same
     # compositions, stream by stream, on the emulator and compare with big-integer arithmetic; also check the
     # range facts the comments in field.cuh rely on (inputs of every reduction below p * 2^384, no 768-bit wrap).
     sys.path.insert(0, os.path.join(ROOT, "r1cs-spartan_b200", "tools"))
@@ -190,23 +190,6 @@ def test_lazy_reduction_sequences_under_emulation():
         re = op("subp2", t0, t1)
         return redc(re), redc(im)
 
-    def fq_msm(a, b, c, d):                               # Fp<FqParams>::mul_sub_mul
-        return redc(op("subp2", mw(a, b), mw(c, d)))
-
-    def fq2_msm(a, b, c, d):                              # Fq2::mul_sub_mul
-        t0, t1 = mw(a[0], b[0]), mw(a[1], b[1])
-        re = op("subp2", t0, t1); s = op("add2", t0, t1)
-        t2 = mw(op("addn", a[0], a[1]), op("addn", b[0], b[1]))
-        x = op("sub", t2, s)
-        t0, t1 = mw(c[0], d[0]), mw(c[1], d[1])
-        t2 = op("subp2", t1, t0)
-        assert re + t2 < W
-        o0 = redc(op("add2", re, t2))
-        s = op("add2", t0, t1)
-        t2 = mw(op("addn", c[0], c[1]), op("addn", d[0], d[1]))
-        y = op("sub", t2, s)
-        return o0, redc(op("sub2p2", x, y))
-
     def ref_mul(a, b):                                    # Montgomery-domain Fq2 product
         return ((a[0] * b[0] - a[1] * b[1]) * rinv % p, (a[0] * b[1] + a[1] * b[0]) * rinv % p)
 
@@ -216,16 +199,13 @@ def test_lazy_reduction_sequences_under_emulation():
     for _ in range(120):
         a, b, c, d = [(pick(), pick()) for _ in range(4)]
         assert fq2_mul(a, b) == ref_mul(a, b)
-        ab, cd = ref_mul(a, b), ref_mul(c, d)
-        assert fq2_msm(a, b, c, d) == ((ab[0] - cd[0]) % p, (ab[1] - cd[1]) % p)
-        assert fq_msm(a[0], b[0], c[0], d[0]) == (a[0] * b[0] - c[0] * d[0]) * rinv % p
+        assert fq2_mul(c, d) == ref_mul(c, d)
     # extremes of the ranges
     hi = (p - 1, p - 1); lo = (0, 0)
     for a, b, c, d in ((hi, hi, hi, hi), (hi, hi, lo, lo), (lo, lo, hi, hi), ((p - 1, 0), (p - 1, 0), (0, p - 1), (0, p - 1)),
                        ((0, p - 1), (0, p - 1), (p - 1, 0), (p - 1, 0))):
-        ab, cd = ref_mul(a, b), ref_mul(c, d)
-        assert fq2_msm(a, b, c, d) == ((ab[0] - cd[0]) % p, (ab[1] - cd[1]) % p)
-        assert fq2_mul(a, b) == ab
+        assert fq2_mul(a, b) == ref_mul(a, b)
+        assert fq2_mul(c, d) == ref_mul(c, d)
 
 
 def test_generated_header_is_up_to_date(tmp_path):

@@ -36,6 +36,23 @@ def _worker(rank, world, port, q):
             got = bytes(recv)
             for r in range(world):
                 assert got[r * nb:(r + 1) * nb] == bytes((r * 17 + rep + i) % 251 for i in range(nb)), (rep, r)
+        # a rank that failed locally releases its peers: they fail the exchange at once (not after the time-out), and the
+        # next epoch (the barrier every library call starts with) re-aligns everybody
+        import time
+        L = sb.load_library()
+        assert shm.struct.barrier(shm.struct.user) == 0
+        nb = 96
+        send = (C.c_uint8 * nb)(*[rank] * nb); recv = (C.c_uint8 * (nb * world))()
+        t0 = time.perf_counter()
+        if rank == world - 1:
+            L.sb_comm_shm_abort(C.byref(shm.struct))
+        else:
+            assert shm.cb(shm.struct.user, C.addressof(send), C.addressof(recv), nb) != 0
+        assert time.perf_counter() - t0 < 30.0
+        dist.barrier()
+        assert shm.struct.barrier(shm.struct.user) == 0
+        assert shm.cb(shm.struct.user, C.addressof(send), C.addressof(recv), nb) == 0
+        assert bytes(recv) == b"".join(bytes([r]) * nb for r in range(world))
         shm.close()
         comm = sbdist.TorchComm()
         assert (comm.rank, comm.world) == (rank, world)

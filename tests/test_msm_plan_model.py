@@ -103,27 +103,3 @@ def test_sorted_order_gives_warps_equal_length_chunks():
         if sort:
             assert (np.diff(lens) <= 1).all() and lens[:32].max() == lens.max() and lens[-32:].min() == lens.min()   # longest first (a run's own chunks differ by at most 1)
     assert eff[True] > 0.985 and eff[False] < 0.95, eff
-
-
-def test_cta_batch_inverse_model():
-    # cta_batch_inverse (msm.cu, cooperative batched-affine rounds): inclusive prefix and suffix products by
-    # Hillis-Steele, one inversion of the total, 1/a_t = total^-1 * I_{t-1} * U_{t+1}.  Same steps, integers mod q.
-    q = (1 << 61) - 1
-    rng = np.random.default_rng(3)
-    for T in (1, 2, 32, 256):
-        a = [int(x) % q or 1 for x in rng.integers(1, 1 << 62, T)]
-        sh = list(a)
-        off = 1
-        while off < T:                                         # inclusive prefix products
-            sh = [sh[t] if t < off else sh[t - off] * sh[t] % q for t in range(T)]
-            off <<= 1
-        before = [1 if t == 0 else sh[t - 1] for t in range(T)]
-        total_inv = pow(sh[T - 1], -1, q)
-        sh = list(a)
-        off = 1
-        while off < T:                                         # inclusive suffix products
-            sh = [sh[t] if t + off >= T else sh[t] * sh[t + off] % q for t in range(T)]
-            off <<= 1
-        after = [1 if t + 1 >= T else sh[t + 1] for t in range(T)]
-        for t in range(T):
-            assert total_inv * before[t] % q * after[t] % q == pow(a[t], -1, q)
