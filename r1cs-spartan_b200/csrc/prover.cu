@@ -1286,7 +1286,11 @@ sb_status sb_pp_export(sb_ctx* ctx, const sb_pp* pp, int group, uint32_t level, 
     SB_API_END
 }
 sb_status sb_pp_export_g_mask(sb_ctx* ctx, const sb_pp* pp, void* outp) {
-    if (ctx && ctx->is_multi()) return (pp && !pp->parts.empty()) ? sb_pp_export_g_mask(ctx->shards[0], pp->parts[0], outp) : SB_EINVAL;
+    if (ctx && ctx->is_multi()) {        // host data of shard 0's part (not through the shard's entry point: that would open an exchange epoch on one rank only)
+        if (!pp || pp->parts.empty() || !outp || pp->parts[0]->g_mask.size() != pp->nv_total) { ctx->last_error = "g_mask_random only exists after sb_pp_keygen"; return SB_EINVAL; }
+        memcpy(outp, pp->parts[0]->g_mask.data(), pp->nv_total * sizeof(G1Aff));
+        return SB_OK;
+    }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && pp && outp && pp->g_mask.size() == pp->nv_total, "g_mask_random only exists after sb_pp_keygen");
     memcpy(outp, pp->g_mask.data(), pp->nv_total * sizeof(G1Aff));

@@ -116,6 +116,7 @@ def _multi_context_cases(ndev, cases):
             pp = sb.MLPolyCommit.load(log_n, opp.g1(0), [opp.g2(i) for i in range(log_n)], h, ctx=ctx)
         else:
             pp = sb.MLPolyCommit.keygen(log_n, g, h, t, ctx=ctx)
+            assert np.array_equal(pp.g_mask_random(), opp.g_mask())        # vp.g_mask_random = g^{t_i} (setup.rs:92-94), host data of the multi context
         pk = sb.MLArgumentForR1CS.index(*cs.mats, ctx=ctx)
         ocs = ob.R1CS.from_csr(log_n, cs.mats)
         oproof, otr = ob.prove(ocs, opp, cs.v, cs.w)
