@@ -199,6 +199,9 @@ size_t sb_prof_report(char* buf, size_t cap);
 /* same records as a timeline: JSON array [[kernel, start_ms, end_ms], ...] relative to the first launch */
 size_t sb_prof_timeline(char* buf, size_t cap);
 /* out = a op b elementwise on the device.  field: 0 = Fr, 1 = Fq.  op: 0 add, 1 sub, 2 mul, 3 mul (portable path) */
+/* host field arithmetic against itself, no device needed: fast 64-bit product vs the portable loop, binary-GCD inversion vs
+ * the Fermat ladder, n operands per field; returns the number of mismatches */
+int sb_selftest_host_field(int n, uint64_t seed);
 sb_status sb_field_binop(sb_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
 /* integer-pipe microbenchmark: n_threads threads x 2 chains x iters Montgomery products; returns
  * milliseconds of the kernel (CUDA events).  field: 0 = Fr (8 limbs), 1 = Fq (12 limbs). */

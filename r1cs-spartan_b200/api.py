@@ -31,7 +31,7 @@ EXPORTS = [
     "sb_prover_second_sumcheck_round", "sb_prover_sixth_round", "sb_prover_export_abc", "sb_phase_name", "sb_phase_span", "sb_prove",
     "sb_proof_size", "sb_field_binop", "sb_mul_bench", "sb_kernel_bench",
     "sb_witness_upload", "sb_witness_destroy", "sb_prove_resident", "sb_copy_counters", "sb_prof_enable", "sb_prof_report",
-    "sb_set_serial_msm", "sb_prof_timeline", "sb_comm_shm_open", "sb_comm_shm_close", "sb_comm_shm_abort", "sb_comm_local_open",
+    "sb_set_serial_msm", "sb_selftest_host_field", "sb_prof_timeline", "sb_comm_shm_open", "sb_comm_shm_close", "sb_comm_shm_abort", "sb_comm_local_open",
 ]
 
 

@@ -108,6 +108,42 @@ struct alignas(16) Fp {
         return o;
     }
 
+    // ---- host fast path: the same Montgomery product (R = 2^(32 N) = 2^(64 N/2)) on 64-bit limbs with 128-bit products,
+    // ~8x faster than the 32-bit loop above.  The host sums the shards' partial group elements and converts every proof
+    // element to affine coordinates with these (round 2: at 8 GPUs 119 G2 additions per opening on the 32-bit path were
+    // 2 ms of a 5 ms phase).  Bit-identical by construction (the result is the unique residue below p); checked against
+    // mul_portable by sb_selftest_host_field.
+#if !defined(__CUDA_ARCH__) && defined(__SIZEOF_INT128__)
+    static inline Fp mul_host64(const Fp& a, const Fp& b) {
+        constexpr int M = N / 2;
+        static_assert(N % 2 == 0, "limb count must be even");
+        typedef unsigned __int128 u128;
+        uint64_t A[M], B[M], Pm[M], t[M + 2];
+        for (int i = 0; i < M; i++) {
+            A[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
+            B[i] = (uint64_t)b.l[2 * i] | ((uint64_t)b.l[2 * i + 1] << 32);
+            Pm[i] = (uint64_t)P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32);
+        }
+        // -p^-1 mod 2^64 from the 32-bit constant: y = p^-1 mod 2^32, one Newton step doubles the precision
+        const uint64_t y32 = (uint64_t)(uint32_t)(0u - P::INV);
+        const uint64_t inv64 = 0 - (y32 * (2 - Pm[0] * y32));
+        for (int i = 0; i < M + 2; i++) t[i] = 0;
+        for (int i = 0; i < M; i++) {
+            u128 c = 0;
+            for (int j = 0; j < M; j++) { c += (u128)A[j] * B[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+            c += t[M]; t[M] = (uint64_t)c; t[M + 1] = (uint64_t)(c >> 64);
+            const uint64_t m = t[0] * inv64;
+            c = (u128)m * Pm[0] + t[0]; c >>= 64;
+            for (int j = 1; j < M; j++) { c += (u128)m * Pm[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+            c += t[M]; t[M - 1] = (uint64_t)c; t[M] = t[M + 1] + (uint64_t)(c >> 64);
+        }
+        Fp o;
+        for (int i = 0; i < M; i++) { o.l[2 * i] = (uint32_t)t[i]; o.l[2 * i + 1] = (uint32_t)(t[i] >> 32); }
+        if (t[M] || geq_mod(o.l)) sub_mod(o.l);
+        return o;
+    }
+#endif
+
     // ---- dispatch
     SB_HD static Fp add(const Fp& a, const Fp& b) {
 #if defined(__CUDA_ARCH__)
@@ -126,6 +162,8 @@ struct alignas(16) Fp {
     SB_HD static Fp mul(const Fp& a, const Fp& b) {
 #if defined(__CUDA_ARCH__)
         Fp o; P::mul_ptx(o.l, a.l, b.l); return o;
+#elif defined(__SIZEOF_INT128__)
+        return mul_host64(a, b);
 #else
         return mul_portable(a, b);
 #endif
@@ -171,7 +209,7 @@ struct alignas(16) Fp {
     // exactly and to (u, v) modulo p -- about 30 k instructions against the 170 k of the Fermat ladder above, and no
     // Montgomery products at all.  Not constant time (the values inverted here are public).  The result is the exact
     // modular inverse, so it is bit-identical to inv() for every input (checked on the host by tests/test_cpu_oracle.py
-    // through sb_selftest_inverse, and on the device by the GPU parity tests of the batched-affine MSM rounds).
+    // through sb_selftest_host_field, and on the device by the GPU parity tests of the batched-affine MSM rounds).
     // a != 0 (mod p); returns the Montgomery form of the inverse of the Montgomery-form input.
 #if defined(__CUDACC__)
     __host__ __device__ __noinline__

@@ -427,9 +427,12 @@ SB_D const T* sb_launder(const T* p) {
 template <class F, bool FIRST, bool LEAN>
 __global__ void __launch_bounds__(AFF_THREADS, LEAN ? 6 : 4) k_affine_round(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
                                                               const AffinePt<F>* __restrict__ in_aff, const uint32_t* __restrict__ in_off,
-                                                              const uint32_t* __restrict__ out_off, uint32_t B, uint32_t nthreads,
+                                                              const uint32_t* __restrict__ out_off, uint32_t B, uint32_t nthreads, uint32_t streaming,
                                                               F* __restrict__ prefix, AffinePt<F>* __restrict__ out_aff) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    // (the entry indices and the plan arrays are re-read by neighbouring lanes and iterations: they keep the cached path)
+    auto LD = [&](const auto* q) { return streaming ? ld_stream_elem(q) : ldg_elem(q); };
+    auto ST = [&](auto* q, const auto& v) { if (streaming) st_stream_elem(q, v); else st_elem(q, v); };
     const uint32_t total = out_off[B];
     const uint32_t per = (total + nthreads - 1) / nthreads;
     if (t >= nthreads || per == 0) return;
@@ -481,10 +484,10 @@ __global__ void __launch_bounds__(AFF_THREADS, LEAN ? 6 : 4) k_affine_round(cons
         if (i + 1 < iters) nxt = locate(first + 32 * (i + 1));
         const AffinePt<F>* pp0 = cur.p0; const AffinePt<F>* pp1 = cur.p1;
         const bool has2 = cur.has2, n0 = cur.n0, n1 = cur.n1;
-        const F px = ldg_elem(&pp0->x), qx = has2 ? ldg_elem(&pp1->x) : px;
+        const F px = LD(&pp0->x), qx = has2 ? LD(&pp1->x) : px;
         F d;
-        pair_classify_x(px, qx, has2, [&](int k) { F y = ldg_elem(k ? &pp1->y : &pp0->y); return (k ? n1 : n0) ? F::neg(y) : y; }, d);
-        st_elem(&prefix[(size_t)i * nthreads + t], acc);
+        pair_classify_x(px, qx, has2, [&](int k) { F y = LD(k ? &pp1->y : &pp0->y); return (k ? n1 : n0) ? F::neg(y) : y; }, d);
+        ST(&prefix[(size_t)i * nthreads + t], acc);
         acc = F::mul(acc, d);
         cur = nxt;
     }
@@ -497,36 +500,36 @@ __global__ void __launch_bounds__(AFF_THREADS, LEAN ? 6 : 4) k_affine_round(cons
         if (LEAN) {
             const AffinePt<F>* p0 = cur.p0; const AffinePt<F>* p1 = cur.p1;
             const bool n0 = cur.n0, n1 = cur.n1;
-            auto ldx = [&](int k) { return ldg_elem(&sb_launder(k ? p1 : p0)->x); };
-            auto ldy = [&](int k) { const F y = ldg_elem(&sb_launder(k ? p1 : p0)->y); return (k ? n1 : n0) ? F::neg(y) : y; };
+            auto ldx = [&](int k) { return LD(&sb_launder(k ? p1 : p0)->x); };
+            auto ldy = [&](int k) { const F y = LD(&sb_launder(k ? p1 : p0)->y); return (k ? n1 : n0) ? F::neg(y) : y; };
             F d;
             int kind;
             { const F px = ldx(0); kind = pair_classify_x(px, has2 ? ldx(1) : px, has2, ldy, d); }
-            const F dinv = F::mul(inv, ldg_elem(&prefix[(size_t)i * nthreads + t]));
+            const F dinv = F::mul(inv, LD(&prefix[(size_t)i * nthreads + t]));
             inv = F::mul(inv, d);
             if (kind == PAIR_ADD || kind == PAIR_DBL) {
                 F lam;
                 if (kind == PAIR_ADD) lam = F::mul(F::sub(ldy(1), ldy(0)), dinv);
                 else { const F xx = F::sqr(ldx(0)); lam = F::mul(F::add(F::dbl(xx), xx), dinv); }
                 const F x3 = F::sub(F::sub(F::sqr(lam), ldx(0)), ldx(1));       // (has2 holds for both kinds)
-                st_elem(&out_aff[p].x, x3);
-                st_elem(&out_aff[p].y, F::sub(F::mul(lam, F::sub(ldx(0), x3)), ldy(0)));
+                ST(&out_aff[p].x, x3);
+                ST(&out_aff[p].y, F::sub(F::mul(lam, F::sub(ldx(0), x3)), ldy(0)));
             } else {
                 AffinePt<F> r = AffinePt<F>::inf();
                 if (kind == PAIR_COPY_P) { r.x = ldx(0); r.y = ldy(0); }
                 else if (kind == PAIR_COPY_Q) { r.x = ldx(1); r.y = ldy(1); }
-                st_elem(&out_aff[p], r);
+                ST(&out_aff[p], r);
             }
             cur = nxt;
             continue;
         }
-        AffinePt<F> P = ldg_elem(cur.p0), Q = has2 ? ldg_elem(cur.p1) : P;
+        AffinePt<F> P = LD(cur.p0), Q = has2 ? LD(cur.p1) : P;
         if (cur.n0) P.y = F::neg(P.y);
         if (has2 && cur.n1) Q.y = F::neg(Q.y);
         if (!has2) Q = P;
         F d;
         const int kind = pair_classify_x(P.x, Q.x, has2, [&](int k) { return k ? Q.y : P.y; }, d);
-        const F dinv = F::mul(inv, ldg_elem(&prefix[(size_t)i * nthreads + t]));
+        const F dinv = F::mul(inv, LD(&prefix[(size_t)i * nthreads + t]));
         inv = F::mul(inv, d);
         AffinePt<F> r;
         if (kind == PAIR_COPY_P) r = P;
@@ -539,7 +542,7 @@ __global__ void __launch_bounds__(AFF_THREADS, LEAN ? 6 : 4) k_affine_round(cons
             r.x = F::sub(F::sub(F::sqr(lam), P.x), Q.x);
             r.y = F::sub(F::mul(lam, F::sub(P.x, r.x)), P.y);
         }
-        st_elem(&out_aff[p], r);
+        ST(&out_aff[p], r);
         cur = nxt;
     }
 }
@@ -882,6 +885,7 @@ static uint32_t msm_affine_rounds(uint64_t etot) {
     return etot >= ((uint64_t)1 << lg) ? rounds : 0;
 }
 static uint32_t msm_affine_kmax() { static const uint32_t v = msm_env_u32("SB_MSM_AFFINE_K", 256, 1, 1024); return v; }
+static uint32_t msm_streaming() { static const uint32_t v = msm_env_u32("SB_MSM_STREAMING", 1, 0, 1); return v; }     // L1-bypassing loads / streaming stores in the affine rounds
 static bool msm_lean() { static const bool v = msm_env_u32("SB_MSM_LEAN", 1, 0, 1) != 0; return v; }      // register-lean second pass (see k_affine_round)
 // CTAs of the round kernel an SM holds (registers decide: 4 over Fq2, 6-8 over Fq); the rounds are sized to exactly one wave
 template <class F>
@@ -1053,7 +1057,7 @@ void msm_group_accum(const MsmGroup<F>& g, cudaStream_t stream) {
         const int grid = (int)((g.round_threads[r] + AFF_THREADS - 1) / AFF_THREADS);
 #define SB_AFF_LAUNCH(FIRST_, LEAN_)                                                                                                            \
         SB_LAUNCH_NAMED(SB_KNAME(F, "k_affine_round"), (k_affine_round<F, FIRST_, LEAN_>), grid, AFF_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), \
-                        aff, seg0, sc.hplan[r].get(), B, g.round_threads[r], sc.prefix.get(), outp)
+                        aff, seg0, sc.hplan[r].get(), B, g.round_threads[r], msm_streaming(), sc.prefix.get(), outp)
         if (r == 0) { if (msm_lean()) SB_AFF_LAUNCH(true, true); else SB_AFF_LAUNCH(true, false); }
         else { if (msm_lean()) SB_AFF_LAUNCH(false, true); else SB_AFF_LAUNCH(false, false); }
 #undef SB_AFF_LAUNCH

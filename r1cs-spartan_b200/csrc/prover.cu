@@ -1819,9 +1819,38 @@ size_t sb_prof_report(char* buf, size_t cap) {
 }
 }  // extern "C"
 
+// Host field arithmetic against itself (no device needed): the 64-bit host product against the 32-bit portable loop, and the
+// binary-GCD inversion against the Fermat ladder, on `n` pseudo-random and edge-case operands per field.  Returns the
+// number of mismatches (0 = pass).
+template <class F>
+static int selftest_field(int n, uint64_t seed) {
+    int bad = 0;
+    auto next = [&seed]() { seed += 0x9E3779B97F4A7C15ull; uint64_t z = seed; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); };
+    auto rnd = [&](int k) {
+        F x = F::zero();
+        if (k % 7 == 1) return F::one();
+        if (k % 7 == 2) return F::neg(F::one());                                     // p - R mod p: a large residue
+        if (k % 7 == 3) { x.l[0] = 1; return x; }
+        for (int i = 0; i < F::N; i++) x.l[i] = (uint32_t)next();
+        x.l[F::N - 1] &= 0x0fffffffu;                                                // below 2^(32 N - 4) < p for both fields
+        return x;
+    };
+    for (int k = 0; k < n; k++) {
+        const F a = rnd(k), b = rnd(3 * k + 1);
+        if (!(F::mul(a, b) == F::mul_portable(a, b))) bad++;
+        if (!(F::mul(a, a) == F::mul_portable(a, a))) bad++;
+        if (k < 64 && !a.is_zero()) {
+            const F i1 = F::inv_fast(a), i2 = F::inv(a);
+            if (!(i1 == i2) || !(F::mul(i1, a) == F::one())) bad++;
+        }
+    }
+    return bad;
+}
 extern "C" {
 
 // ---------------------------------------------------------------- self-test / measurement hooks
+int sb_selftest_host_field(int n, uint64_t seed) { return selftest_field<Fr>(n, seed) + selftest_field<Fq>(n, seed ^ 0x5b5b5b5bull); }
+
 sb_status sb_field_binop(sb_ctx* ctx, int field, int op, const void* a, const void* b, void* outp, size_t n) {
     if (ctx && ctx->is_multi()) { ctx->last_error = "this entry point is only available on a single-GPU context"; return SB_EINVAL; }
     SB_API_BEGIN(ctx)

@@ -118,6 +118,7 @@ extern "C" {
     pub fn sb_set_serial_msm(ctx: *mut sb_ctx, on: c_int);
     pub fn sb_prof_report(buf: *mut c_char, cap: usize) -> usize;
     pub fn sb_prof_timeline(buf: *mut c_char, cap: usize) -> usize;
+    pub fn sb_selftest_host_field(n: c_int, seed: u64) -> c_int;
     pub fn sb_field_binop(ctx: *mut sb_ctx, field: c_int, op: c_int, a: *const c_void, b: *const c_void, out: *mut c_void, n: usize) -> c_int;
     pub fn sb_mul_bench(ctx: *mut sb_ctx, field: c_int, n_threads: usize, iters: c_int, out_ms: *mut c_double) -> c_int;
     pub fn sb_kernel_bench(ctx: *mut sb_ctx, which: c_int, log_m: u32, reps: c_int, flush_l2: c_int, out_ms_avg: *mut c_double) -> c_int;
