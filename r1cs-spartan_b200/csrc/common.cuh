@@ -167,36 +167,3 @@ SB_D void st_elem(T* p, const T& v) {
     *p = v;
 #endif
 }
-
-// Streaming variants: data that is read or written exactly once (the inputs, prefix products and outputs of the pairwise
-// affine rounds) must not evict the lines L1 holds for local memory -- the operands of the outlined field products travel
-// through it on every call.  Loads bypass L1 allocation, stores are marked streaming.
-template <class T>
-SB_D T ld_stream_elem(const T* p) {
-#if defined(__CUDA_ARCH__)
-    static_assert(sizeof(T) % 16 == 0, "element must be a multiple of 16 bytes");
-    T out;
-    const uint4* src = reinterpret_cast<const uint4*>(p);
-    uint4* dst = reinterpret_cast<uint4*>(&out);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(T) / 16); i++) {
-        uint4 v;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i));
-        dst[i] = v;
-    }
-    return out;
-#else
-    return *p;
-#endif
-}
-template <class T>
-SB_D void st_stream_elem(T* p, const T& v) {
-#if defined(__CUDA_ARCH__)
-    uint4* dst = reinterpret_cast<uint4*>(p);
-    const uint4* src = reinterpret_cast<const uint4*>(&v);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(T) / 16); i++) __stcs(dst + i, src[i]);
-#else
-    *p = v;
-#endif
-}

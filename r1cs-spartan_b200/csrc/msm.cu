@@ -412,27 +412,12 @@ __device__ __forceinline__ int pair_classify_x(const F& px, const F& qx, bool ha
 // warp, the entry indices and the results are read and written as contiguous runs, and every lane runs the same number
 // of iterations (a first version with per-thread contiguous shares and bucket-by-bucket loops had 17.9 of 32 lanes
 // active: ncu, profiles/r02_ncu_affine_round_v1.txt).
-// LEAN: the second pass keeps only the running inverse, the slope and the new x coordinate in registers and re-reads the
-// coordinates of P and Q from memory (L1 hits: they were read a few hundred instructions earlier) each time the formulas
-// need them, through laundered pointers so that the compiler cannot keep them live instead; the kernel is then compiled
-// for 6 resident CTAs per SM (170 registers) instead of 4 (254): 12 warps per SM instead of 8 to cover the dependent
-// IMAD chains (ncu of the 254-register kernel: `wait` 2.9 and `long_scoreboard` 1.65 per issue with 2 warps per scheduler).
-template <class T>
-SB_D const T* sb_launder(const T* p) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("" : "+l"(p));
-#endif
-    return p;
-}
-template <class F, bool FIRST, bool LEAN>
-__global__ void __launch_bounds__(AFF_THREADS, LEAN ? 6 : 4) k_affine_round(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
+template <class F, bool FIRST>
+__global__ void __launch_bounds__(AFF_THREADS) k_affine_round(const AffinePt<F>* __restrict__ tab, const uint32_t* __restrict__ sorted,
                                                               const AffinePt<F>* __restrict__ in_aff, const uint32_t* __restrict__ in_off,
-                                                              const uint32_t* __restrict__ out_off, uint32_t B, uint32_t nthreads, uint32_t streaming,
+                                                              const uint32_t* __restrict__ out_off, uint32_t B, uint32_t nthreads,
                                                               F* __restrict__ prefix, AffinePt<F>* __restrict__ out_aff) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    // (the entry indices and the plan arrays are re-read by neighbouring lanes and iterations: they keep the cached path)
-    auto LD = [&](const auto* q) { return streaming ? ld_stream_elem(q) : ldg_elem(q); };
-    auto ST = [&](auto* q, const auto& v) { if (streaming) st_stream_elem(q, v); else st_elem(q, v); };
     const uint32_t total = out_off[B];
     const uint32_t per = (total + nthreads - 1) / nthreads;
     if (t >= nthreads || per == 0) return;
@@ -471,12 +456,16 @@ __global__ void __launch_bounds__(AFF_THREADS, LEAN ? 6 : 4) k_affine_round(cons
         pr.p1 = pr.has2 ? in_ptr(ib + 2 * j + 1, pr.n1) : pr.p0;
         return pr;
     };
-    // (Two attempts at hiding the latency of these loads were measured in round 2 and removed: prefetch instructions one
-    // iteration ahead, sweep 8: 41.6 against 41.0 ms per proof; cp.async staging of the next iteration's points and prefix
-    // product in shared memory, sweep 11: 39.4 against 39.2 ms, the kernel itself 4.47 against 3.80 ms under ncu
-    // (profiles/r02_ncu_affine_round_v4_staged.txt) -- the long-scoreboard stalls are local-memory traffic of the register
-    // spills and of the outlined Fq2 products' operands, and the shared-memory carve-out took L1 away from exactly that:
-    // local-load hit rate 86 % -> 72 %.)
+    // (Four attempts on the stalls around these loads were measured in round 2 and removed -- profiles/r02_ncu_affine_round_v3..v6:
+    //   prefetch instructions one iteration ahead (sweep 8): 41.6 against 41.0 ms per proof;
+    //   cp.async staging of the next iteration's points and prefix product in shared memory (sweep 11): 39.4 against 39.2 ms, the
+    //     kernel itself 4.47 against 3.80 ms -- the carve-out took L1 away from local memory (hit rate 86 % -> 72 %);
+    //   a register-lean second pass (re-reading coordinates through laundered pointers: 148 registers, 12 warps per SM instead
+    //     of 8; sweep 12): 39.1 against 39.4 ms, the kernel 3.91 ms -- more warps, same traffic, more instruction-cache misses;
+    //   L1-bypassing loads and streaming stores for the once-read data (sweep 13): 40.4 against 39.4 ms, 4.53 ms, although the
+    //     local loads then hit L1 90 % of the time.
+    // What ncu counts as local traffic here is the OPERANDS of the outlined Fq2 products -- 14 STL.128 by the caller and 48 LD.E
+    // by the callee per call, 35 M + 11 M warp-instructions per launch -- not spills of this loop.)
     // pass 1: prefix products of the denominators (x coordinates only)
     F acc = F::one();
     Pair cur = locate(first), nxt = cur;
@@ -484,10 +473,10 @@ __global__ void __launch_bounds__(AFF_THREADS, LEAN ? 6 : 4) k_affine_round(cons
         if (i + 1 < iters) nxt = locate(first + 32 * (i + 1));
         const AffinePt<F>* pp0 = cur.p0; const AffinePt<F>* pp1 = cur.p1;
         const bool has2 = cur.has2, n0 = cur.n0, n1 = cur.n1;
-        const F px = LD(&pp0->x), qx = has2 ? LD(&pp1->x) : px;
+        const F px = ldg_elem(&pp0->x), qx = has2 ? ldg_elem(&pp1->x) : px;
         F d;
-        pair_classify_x(px, qx, has2, [&](int k) { F y = LD(k ? &pp1->y : &pp0->y); return (k ? n1 : n0) ? F::neg(y) : y; }, d);
-        ST(&prefix[(size_t)i * nthreads + t], acc);
+        pair_classify_x(px, qx, has2, [&](int k) { F y = ldg_elem(k ? &pp1->y : &pp0->y); return (k ? n1 : n0) ? F::neg(y) : y; }, d);
+        st_elem(&prefix[(size_t)i * nthreads + t], acc);
         acc = F::mul(acc, d);
         cur = nxt;
     }
@@ -497,39 +486,13 @@ __global__ void __launch_bounds__(AFF_THREADS, LEAN ? 6 : 4) k_affine_round(cons
         if (i > 0) nxt = locate(first + 32 * (i - 1));
         const uint32_t p = first + 32 * i;
         const bool has2 = cur.has2;
-        if (LEAN) {
-            const AffinePt<F>* p0 = cur.p0; const AffinePt<F>* p1 = cur.p1;
-            const bool n0 = cur.n0, n1 = cur.n1;
-            auto ldx = [&](int k) { return LD(&sb_launder(k ? p1 : p0)->x); };
-            auto ldy = [&](int k) { const F y = LD(&sb_launder(k ? p1 : p0)->y); return (k ? n1 : n0) ? F::neg(y) : y; };
-            F d;
-            int kind;
-            { const F px = ldx(0); kind = pair_classify_x(px, has2 ? ldx(1) : px, has2, ldy, d); }
-            const F dinv = F::mul(inv, LD(&prefix[(size_t)i * nthreads + t]));
-            inv = F::mul(inv, d);
-            if (kind == PAIR_ADD || kind == PAIR_DBL) {
-                F lam;
-                if (kind == PAIR_ADD) lam = F::mul(F::sub(ldy(1), ldy(0)), dinv);
-                else { const F xx = F::sqr(ldx(0)); lam = F::mul(F::add(F::dbl(xx), xx), dinv); }
-                const F x3 = F::sub(F::sub(F::sqr(lam), ldx(0)), ldx(1));       // (has2 holds for both kinds)
-                ST(&out_aff[p].x, x3);
-                ST(&out_aff[p].y, F::sub(F::mul(lam, F::sub(ldx(0), x3)), ldy(0)));
-            } else {
-                AffinePt<F> r = AffinePt<F>::inf();
-                if (kind == PAIR_COPY_P) { r.x = ldx(0); r.y = ldy(0); }
-                else if (kind == PAIR_COPY_Q) { r.x = ldx(1); r.y = ldy(1); }
-                ST(&out_aff[p], r);
-            }
-            cur = nxt;
-            continue;
-        }
-        AffinePt<F> P = LD(cur.p0), Q = has2 ? LD(cur.p1) : P;
+        AffinePt<F> P = ldg_elem(cur.p0), Q = has2 ? ldg_elem(cur.p1) : P;
         if (cur.n0) P.y = F::neg(P.y);
         if (has2 && cur.n1) Q.y = F::neg(Q.y);
         if (!has2) Q = P;
         F d;
         const int kind = pair_classify_x(P.x, Q.x, has2, [&](int k) { return k ? Q.y : P.y; }, d);
-        const F dinv = F::mul(inv, LD(&prefix[(size_t)i * nthreads + t]));
+        const F dinv = F::mul(inv, ldg_elem(&prefix[(size_t)i * nthreads + t]));
         inv = F::mul(inv, d);
         AffinePt<F> r;
         if (kind == PAIR_COPY_P) r = P;
@@ -542,7 +505,7 @@ __global__ void __launch_bounds__(AFF_THREADS, LEAN ? 6 : 4) k_affine_round(cons
             r.x = F::sub(F::sub(F::sqr(lam), P.x), Q.x);
             r.y = F::sub(F::mul(lam, F::sub(P.x, r.x)), P.y);
         }
-        ST(&out_aff[p], r);
+        st_elem(&out_aff[p], r);
         cur = nxt;
     }
 }
@@ -885,8 +848,6 @@ static uint32_t msm_affine_rounds(uint64_t etot) {
     return etot >= ((uint64_t)1 << lg) ? rounds : 0;
 }
 static uint32_t msm_affine_kmax() { static const uint32_t v = msm_env_u32("SB_MSM_AFFINE_K", 256, 1, 1024); return v; }
-static uint32_t msm_streaming() { static const uint32_t v = msm_env_u32("SB_MSM_STREAMING", 1, 0, 1); return v; }     // L1-bypassing loads / streaming stores in the affine rounds
-static bool msm_lean() { static const bool v = msm_env_u32("SB_MSM_LEAN", 1, 0, 1) != 0; return v; }      // register-lean second pass (see k_affine_round)
 // CTAs of the round kernel an SM holds (registers decide: 4 over Fq2, 6-8 over Fq); the rounds are sized to exactly one wave
 template <class F>
 static uint32_t msm_affine_ctas_per_sm() {
@@ -895,13 +856,8 @@ static uint32_t msm_affine_ctas_per_sm() {
     static uint32_t cached = 0;
     if (!cached) {
         int a = 0, b = 0;
-        if (msm_lean()) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_affine_round<F, true, true>, AFF_THREADS, 0) != cudaSuccess) a = 4;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_affine_round<F, false, true>, AFF_THREADS, 0) != cudaSuccess) b = 4;
-        } else {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_affine_round<F, true, false>, AFF_THREADS, 0) != cudaSuccess) a = 4;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_affine_round<F, false, false>, AFF_THREADS, 0) != cudaSuccess) b = 4;
-        }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_affine_round<F, true>, AFF_THREADS, 0) != cudaSuccess) a = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_affine_round<F, false>, AFF_THREADS, 0) != cudaSuccess) b = 4;
         cached = (uint32_t)std::max(1, std::min(a, b));
     }
     return cached;
@@ -1055,12 +1011,12 @@ void msm_group_accum(const MsmGroup<F>& g, cudaStream_t stream) {
     for (uint32_t r = 0; r < g.R; r++) {
         AffinePt<F>* outp = (r % 2 == 0) ? sc.affA.get() : sc.affB.get();
         const int grid = (int)((g.round_threads[r] + AFF_THREADS - 1) / AFF_THREADS);
-#define SB_AFF_LAUNCH(FIRST_, LEAN_)                                                                                                            \
-        SB_LAUNCH_NAMED(SB_KNAME(F, "k_affine_round"), (k_affine_round<F, FIRST_, LEAN_>), grid, AFF_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), \
-                        aff, seg0, sc.hplan[r].get(), B, g.round_threads[r], msm_streaming(), sc.prefix.get(), outp)
-        if (r == 0) { if (msm_lean()) SB_AFF_LAUNCH(true, true); else SB_AFF_LAUNCH(true, false); }
-        else { if (msm_lean()) SB_AFF_LAUNCH(false, true); else SB_AFF_LAUNCH(false, false); }
-#undef SB_AFF_LAUNCH
+        if (r == 0)
+            SB_LAUNCH_NAMED(SB_KNAME(F, "k_affine_round"), (k_affine_round<F, true>), grid, AFF_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), aff, seg0,
+                            sc.hplan[r].get(), B, g.round_threads[r], sc.prefix.get(), outp);
+        else
+            SB_LAUNCH_NAMED(SB_KNAME(F, "k_affine_round"), (k_affine_round<F, false>), grid, AFF_THREADS, 0, stream, g.tab.get(), sc.sorted.get(), aff, seg0,
+                            sc.hplan[r].get(), B, g.round_threads[r], sc.prefix.get(), outp);
         aff = outp; seg0 = sc.hplan[r].get();
     }
     const int grid = (int)((std::max<uint32_t>(g.items_bound[0], 1) + ACC_THREADS - 1) / ACC_THREADS);
