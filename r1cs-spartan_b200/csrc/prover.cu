@@ -48,6 +48,11 @@ struct sb_ctx {
     std::vector<std::unique_ptr<Worker>> workers;
     std::vector<sb_comm> shard_comms;
     bool is_multi() const { return !shards.empty(); }
+    // Handles made from a context (index, parameters, witness, prover state) use its device and streams when they are
+    // destroyed.  The context counts them; sb_ctx_destroy on a context that still has handles only marks it, and the
+    // destruction of the last handle completes it -- any destruction order is safe.
+    std::atomic<int> children{0};
+    bool zombie = false;
     // per-round reduction workspace + mailbox
     DevBuf<Fr> block_partials;
     DevBuf<unsigned int> ticket;
@@ -1076,8 +1081,12 @@ static sb_status multi_call(sb_ctx* m, Fn fn) {
     }
     return st;
 }
-template <class T>
-static std::vector<T*> multi_parts(const std::vector<T*>& v) { return v; }
+extern "C" void sb_ctx_destroy(sb_ctx* c);
+// a handle of `c` is gone; completes a destruction that was requested while handles were alive
+static void ctx_release_child(sb_ctx* c) {
+    if (!c) return;
+    if (--c->children == 0 && c->zombie) { c->zombie = false; sb_ctx_destroy(c); }
+}
 
 extern "C" {
 
@@ -1090,6 +1099,10 @@ size_t sb_proof_size(uint32_t l) {
     return (8 + 48) + open + 16 + 8 + (size_t)l * (8 + 32 * ((size_t)l + 3)) + 96 + 16 + 8 + (size_t)l * (8 + 96) + open;
 }
 
+// live single-GPU contexts per device: the last one to go gives the default memory pool back (sb_ctx_create raises its release
+// threshold so that the steady state performs no device allocation; other users of the device -- PyTorch in bench.py's
+// process -- should not find tens of gigabytes parked there afterwards)
+static std::atomic<int> g_ctx_per_device[64];
 sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
     try {
         if (!out) throw SbError(SB_EINVAL, "null out pointer");
@@ -1112,6 +1125,7 @@ sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
         SB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
         uint64_t thresh = UINT64_MAX;
         SB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+        g_ctx_per_device[device & 63]++;
         // grid cap of the sumcheck round kernels, in CTAs per SM.  2 = one resident wave (persistent, grid-stride).
         // SB_SC_CTAS_PER_SM > 2 (experiment) launches more, smaller-work CTAs so that the
         // partial last wave of a large round spreads over all SMs.
@@ -1182,6 +1196,7 @@ sb_status sb_ctx_create_multi(const int* devices, int ndev, sb_ctx** out) {
 
 void sb_ctx_destroy(sb_ctx* c) {
     if (!c) return;
+    if (c->children.load() > 0) { c->zombie = true; return; }      // completed by the destruction of the last handle (ctx_release_child)
     if (c->is_multi()) {
         for (auto& w : c->workers) { { std::lock_guard<std::mutex> g(w->m); w->quit = true; } w->cv.notify_all(); w->th.join(); }
         for (sb_ctx* sc : c->shards) sb_ctx_destroy(sc);
@@ -1204,6 +1219,14 @@ void sb_ctx_destroy(sb_ctx* c) {
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     cudaStreamDestroy(c->stream);
+    if (--g_ctx_per_device[c->device & 63] == 0) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+            uint64_t thresh = 0;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+            cudaMemPoolTrimTo(pool, 0);
+        }
+    }
     delete c;
 }
 const char* sb_last_error(const sb_ctx* c) { return c ? c->last_error.c_str() : g_create_error.c_str(); }
@@ -1217,12 +1240,14 @@ sb_status sb_index_create(sb_ctx* ctx, uint32_t log_n, const sb_csr* a, const sb
         sb_status st = multi_call(ctx, [=](int r, sb_ctx* sc) { return sb_index_create(sc, log_n, a, b, c, &parts[r]); });
         if (st != SB_OK) { for (sb_index* p : ix->parts) sb_index_destroy(p); return st; }
         *out = ix.release();
+        ctx->children++;
         return SB_OK;
     }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && out, "null argument");
     const sb_csr* m[3] = {a, b, c};
     *out = index_create(ctx, log_n, m);
+    ctx->children++;
     SB_API_END
 }
 void sb_index_timing(const sb_index* ix, double* plan_ms, double* hash_wait_ms) {
@@ -1232,9 +1257,11 @@ void sb_index_timing(const sb_index* ix, double* plan_ms, double* hash_wait_ms) 
 }
 void sb_index_destroy(sb_index* ix) {
     if (!ix) return;
-    if (!ix->parts.empty()) { for (sb_index* p : ix->parts) sb_index_destroy(p); delete ix; return; }
+    sb_ctx* owner = ix->ctx;
+    if (!ix->parts.empty()) { for (sb_index* p : ix->parts) sb_index_destroy(p); delete ix; ctx_release_child(owner); return; }
     cudaSetDevice(ix->ctx->device);
     delete ix;
+    ctx_release_child(owner);
 }
 
 sb_status sb_pp_load(sb_ctx* ctx, uint32_t nv, const void* g0, const void* const* hs, const void* h, sb_pp** out) {
@@ -1246,11 +1273,13 @@ sb_status sb_pp_load(sb_ctx* ctx, uint32_t nv, const void* g0, const void* const
         sb_status st = multi_call(ctx, [=](int r, sb_ctx* sc) { return sb_pp_load(sc, nv, g0, hs, h, &parts[r]); });
         if (st != SB_OK) { for (sb_pp* p : pp->parts) sb_pp_destroy(p); return st; }
         *out = pp.release();
+        ctx->children++;
         return SB_OK;
     }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && out, "null argument");
     *out = pp_load(ctx, nv, g0, hs, h);
+    ctx->children++;
     SB_API_END
 }
 sb_status sb_pp_keygen(sb_ctx* ctx, uint32_t nv, const void* g, const void* h, const void* t, int keep_all, sb_pp** out) {
@@ -1262,11 +1291,13 @@ sb_status sb_pp_keygen(sb_ctx* ctx, uint32_t nv, const void* g, const void* h, c
         sb_status st = multi_call(ctx, [=](int r, sb_ctx* sc) { return sb_pp_keygen(sc, nv, g, h, t, keep_all, &parts[r]); });
         if (st != SB_OK) { for (sb_pp* p : pp->parts) sb_pp_destroy(p); return st; }
         *out = pp.release();
+        ctx->children++;
         return SB_OK;
     }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && out, "null argument");
     *out = pp_keygen(ctx, nv, g, h, t, keep_all != 0);
+    ctx->children++;
     SB_API_END
 }
 sb_status sb_pp_export(sb_ctx* ctx, const sb_pp* pp, int group, uint32_t level, void* outp) {
@@ -1298,9 +1329,11 @@ sb_status sb_pp_export_g_mask(sb_ctx* ctx, const sb_pp* pp, void* outp) {
 }
 void sb_pp_destroy(sb_pp* pp) {
     if (!pp) return;
-    if (!pp->parts.empty()) { for (sb_pp* p : pp->parts) sb_pp_destroy(p); delete pp; return; }
+    sb_ctx* owner = pp->ctx;
+    if (!pp->parts.empty()) { for (sb_pp* p : pp->parts) sb_pp_destroy(p); delete pp; ctx_release_child(owner); return; }
     cudaSetDevice(pp->ctx->device);
     delete pp;
+    ctx_release_child(owner);
 }
 
 sb_status sb_commit(sb_ctx* ctx, const sb_pp* pp, const void* z, void* out_g1) {
@@ -1432,18 +1465,22 @@ sb_status sb_prover_init(sb_ctx* ctx, const sb_index* ix, const void* v, size_t 
         sb_status st = multi_call(ctx, [=](int r, sb_ctx* sc) { return sb_prover_init(sc, ix->parts[r], v, nv_len, w, nw_len, &parts[r]); });
         if (st != SB_OK) { for (sb_prover* q : p->parts) sb_prover_destroy(q); return st; }
         *out = p.release();
+        ctx->children++;
         return SB_OK;
     }
     SB_API_BEGIN(ctx)
     SB_REQUIRE(ctx && ix && out, "null argument");
     *out = prover_init(ctx, ix, v, nv_len, w, nw_len);
+    ctx->children++;
     SB_API_END
 }
 void sb_prover_destroy(sb_prover* p) {
     if (!p) return;
-    if (!p->parts.empty()) { for (sb_prover* q : p->parts) sb_prover_destroy(q); p->ctx = nullptr; delete p; return; }
+    sb_ctx* owner = p->ctx;
+    if (!p->parts.empty()) { for (sb_prover* q : p->parts) sb_prover_destroy(q); p->ctx = nullptr; delete p; ctx_release_child(owner); return; }
     cudaSetDevice(p->ctx->device);
     delete p;
+    ctx_release_child(owner);
 }
 sb_status sb_prover_first_round(sb_prover* p, const sb_pp* pp, void* out_commit) {
     if (p && !p->parts.empty()) {
@@ -1768,6 +1805,7 @@ sb_status sb_witness_upload(sb_ctx* ctx, const sb_index* ix, const void* v, size
         sb_status st = multi_call(ctx, [=](int r, sb_ctx* sc) { return sb_witness_upload(sc, ix->parts[r], v, nv_len, w, nw_len, &parts[r]); });
         if (st != SB_OK) { for (sb_witness* p : wt->parts) sb_witness_destroy(p); return st; }
         *out = wt.release();
+        ctx->children++;
         return SB_OK;
     }
     SB_API_BEGIN(ctx)
@@ -1782,13 +1820,16 @@ sb_status sb_witness_upload(sb_ctx* ctx, const sb_index* ix, const void* v, size
     if (nw_len) SB_CUDA(cudaMemcpyAsync(wt->z.get() + nv_len, w, nw_len * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     ctx_sync(ctx);
     *out = wt.release();
+    ctx->children++;
     SB_API_END
 }
 void sb_witness_destroy(sb_witness* w) {
     if (!w) return;
-    if (!w->parts.empty()) { for (sb_witness* p : w->parts) sb_witness_destroy(p); delete w; return; }
+    sb_ctx* owner = w->ctx;
+    if (!w->parts.empty()) { for (sb_witness* p : w->parts) sb_witness_destroy(p); delete w; ctx_release_child(owner); return; }
     cudaSetDevice(w->ctx->device);
     delete w;
+    ctx_release_child(owner);
 }
 sb_status sb_prove_resident(sb_ctx* ctx, const sb_index* ix, const sb_pp* pp, const sb_witness* wt, uint8_t* proof, size_t* len, sb_trace* tr) {
     if (ctx && ctx->is_multi()) return wt ? multi_prove(ctx, ix, pp, nullptr, 0, nullptr, 0, wt, proof, len, tr) : SB_EINVAL;

@@ -310,6 +310,25 @@ def test_prove_is_deterministic_and_handles_are_reusable(sb, oracle, gpu_ctx):
     assert sb.MLArgumentForR1CS.prove(pk, cs.v, w2, pp) != p1
 
 
+def test_context_may_be_closed_before_its_handles(sb, oracle):
+    # handles use their context's device and streams when they are destroyed; the context counts them, so closing it
+    # first only marks it and the last handle to go completes the destruction (use-after-free otherwise)
+    ctx = sb.Context(0)
+    cs = sb.SyntheticR1CS(4, 12, 0, 9)
+    g, h = oracle.generators()
+    pp = sb.MLPolyCommit.keygen(4, g, h, oracle.fr_rand(2, 4), ctx=ctx)
+    pk = sb.MLArgumentForR1CS.index(*cs.mats, ctx=ctx)
+    wit = sb.Witness(pk, cs.v, cs.w)
+    proof = sb.MLArgumentForR1CS.prove(pk, cs.v, cs.w, pp)
+    ctx.close()                       # deferred: three handles are alive
+    wit.close(); pk.close(); pp.close()
+    ctx2 = sb.Context(0)              # a fresh context works and gives the same proof
+    pp2 = sb.MLPolyCommit.keygen(4, g, h, oracle.fr_rand(2, 4), ctx=ctx2)
+    pk2 = sb.MLArgumentForR1CS.index(*cs.mats, ctx=ctx2)
+    assert sb.MLArgumentForR1CS.prove(pk2, cs.v, cs.w, pp2) == proof
+    pk2.close(); pp2.close(); ctx2.close()
+
+
 def test_proof_size_formula(sb):
     L = sb.load_library()
     # proof sizes derived from the reference's struct layout
