@@ -68,10 +68,8 @@ struct sb_ctx {
     // accumulation of the next; the sharded prover's tail opening is one more group
     static constexpr int NAUX = 6;
     cudaStream_t aux[NAUX] = {};       // front + accumulation of group k
-    cudaStream_t tail[NAUX] = {};      // high priority: the latency-bound tail of group k (later levels, bucket reduction)
-    cudaEvent_t ev_main = nullptr, ev_acc[NAUX] = {}, ev_done[NAUX] = {};
+    cudaEvent_t ev_main = nullptr, ev_done[NAUX] = {};
     int next_aux = 0;                  // groups take the auxiliary streams in rotation
-    int chain_prev = -1;               // stream index of the last queued accumulation: the next one is chained behind it
     cudaStream_t copy_stream = nullptr; // witness upload that overlaps the commitment (sharded sb_prove)
     cudaEvent_t ev_copy = nullptr;
     bool serial_msm = false;           // profiling aid: keep every MSM group on the main stream
@@ -593,11 +591,10 @@ static sb_pp* pp_keygen(sb_ctx* c, uint32_t nv, const void* g, const void* h, co
 // have been recorded on the main stream at the point the groups may start from; the main stream is joined to every group
 // unless `done_instead_of_join` asks for an event instead (the caller joins later).  A single group runs on the main
 // stream itself when main_too.
-// Two scheduling experiments, both measured SLOWER on B200 at 2^20 and 2^17 and therefore off (round 2, gpurun sweep 4):
-//   SB_MSM_CHAIN=1      chain the throughput-bound accumulations one after another by events (each gets the whole machine)
-//   SB_MSM_TAIL_PRIO=1  run every group's latency-bound tail on a high-priority stream beside the next accumulation
-// (the machine drains at every chain link, and the tails' 2-warp CTAs take SM slots from the accumulations: 62.6 against
-// 58.7 ms at 2^20).
+// (Two scheduling experiments were measured SLOWER on B200 at 2^20 and 2^17 in round 2, sweep 4, and removed: chaining the
+// groups' throughput-bound accumulations one after another by events -- the machine drains at every link -- and running
+// every group's latency-bound tail on a high-priority stream beside the next accumulation -- the tails' CTAs take SM
+// slots from the accumulations: 62.6 against 58.7 ms at 2^20.)
 template <class F>
 static void msm_groups_run(sb_ctx* c, const std::vector<const MsmGroup<F>*>& gs, const std::vector<MsmScalarPtrs>& sps,
                            const std::vector<XyzzPt<F>*>& outs, bool main_too, cudaEvent_t done_instead_of_join = nullptr) {
@@ -608,25 +605,15 @@ static void msm_groups_run(sb_ctx* c, const std::vector<const MsmGroup<F>*>& gs,
         if (done_instead_of_join) SB_CUDA(cudaEventRecord(done_instead_of_join, st));
         return;
     }
-    static const bool chain = getenv("SB_MSM_CHAIN") && atoi(getenv("SB_MSM_CHAIN")) != 0;
-    static const bool tail_prio = getenv("SB_MSM_TAIL_PRIO") && atoi(getenv("SB_MSM_TAIL_PRIO")) != 0;
     for (size_t k = 0; k < ng; k++) {
         const int a = c->next_aux;
         c->next_aux = (c->next_aux + 1) % sb_ctx::NAUX;
-        cudaStream_t s = c->aux[a], t = tail_prio ? c->tail[a] : s;
+        cudaStream_t s = c->aux[a];
         SB_CUDA(cudaStreamWaitEvent(s, c->ev_main, 0));
-        msm_group_front<F>(*gs[k], sps[k], s);
-        if (chain && c->chain_prev >= 0) SB_CUDA(cudaStreamWaitEvent(s, c->ev_acc[c->chain_prev], 0));
-        msm_group_accum<F>(*gs[k], s);
-        if (chain || tail_prio) {
-            SB_CUDA(cudaEventRecord(c->ev_acc[a], s));
-            c->chain_prev = a;
-            if (tail_prio) SB_CUDA(cudaStreamWaitEvent(t, c->ev_acc[a], 0));
-        }
-        msm_group_tail<F>(*gs[k], outs[k], t);
-        if (done_instead_of_join && k + 1 == ng) SB_CUDA(cudaEventRecord(done_instead_of_join, t));
+        msm_group_run<F>(*gs[k], sps[k], outs[k], s);
+        if (done_instead_of_join && k + 1 == ng) SB_CUDA(cudaEventRecord(done_instead_of_join, s));
         else {
-            SB_CUDA(cudaEventRecord(c->ev_done[a], t));
+            SB_CUDA(cudaEventRecord(c->ev_done[a], s));
             SB_CUDA(cudaStreamWaitEvent(st, c->ev_done[a], 0));
         }
     }
@@ -1140,12 +1127,8 @@ sb_status sb_ctx_create_sharded(int device, const sb_comm* comm, sb_ctx** out) {
         c->d_mail.alloc(sb_ctx::MAIL, c->stream);
         c->h_mail.alloc(sb_ctx::MAIL);
         c->round_out.alloc(4); c->round_flag.alloc(16);
-        int prio_least = 0, prio_greatest = 0;
-        SB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
         for (int i = 0; i < sb_ctx::NAUX; i++) {
-            SB_CUDA(cudaStreamCreateWithPriority(&c->aux[i], cudaStreamNonBlocking, prio_least));
-            SB_CUDA(cudaStreamCreateWithPriority(&c->tail[i], cudaStreamNonBlocking, prio_greatest));
-            SB_CUDA(cudaEventCreateWithFlags(&c->ev_acc[i], cudaEventDisableTiming));
+            SB_CUDA(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
             SB_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
         }
         SB_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
@@ -1211,8 +1194,6 @@ void sb_ctx_destroy(sb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < sb_ctx::NAUX; i++) {
         if (c->aux[i]) { cudaStreamSynchronize(c->aux[i]); cudaStreamDestroy(c->aux[i]); }
-        if (c->tail[i]) { cudaStreamSynchronize(c->tail[i]); cudaStreamDestroy(c->tail[i]); }
-        if (c->ev_acc[i]) cudaEventDestroy(c->ev_acc[i]);
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
     }
     if (c->ev_main) cudaEventDestroy(c->ev_main);
