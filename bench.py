@@ -52,6 +52,12 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            # nvidia-smi takes a few hundred milliseconds to initialise NVML, and while it does, driver calls of other
+            # processes can stall: seen in round 2 as ONE 0.6-1.3 s step somewhere after the sampler was started (once in
+            # the e2e region: 160 ms instead of 40 ms per step).  Wait for its first sample before any timed region starts.
+            t0 = time.perf_counter()
+            while not self.rows and self.proc.poll() is None and time.perf_counter() - t0 < 8.0:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
