@@ -85,3 +85,41 @@ def test_multi_context_one_process_under_emulation(emul_env):
                         "multi_context_one_process_2gpu or multi_context_one_process_4gpu"], env=e, cwd=ROOT, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])
     assert "2 passed" in r.stdout, r.stdout[-500:]
+
+
+def test_multi_context_argument_checks_under_emulation(emul_env):
+    # sb_ctx_create_multi: a power-of-two number of devices, every index in range; one device gives a plain context;
+    # the single-matrix helpers refuse a multi context with InvalidArgument instead of touching a shard behind the exchange
+    code = """
+import numpy as np, r1cs_spartan_b200 as sb
+assert sb.device_count() == 8
+for bad in ([0, 1, 2], [], [0, 99]):
+    try:
+        sb.Context(devices=bad)
+    except (sb.InvalidArgument, sb.CudaError, ValueError):
+        pass
+    else:
+        raise SystemExit("accepted devices=%r" % (bad,))
+one = sb.Context(devices=[3])
+assert np.array_equal(sb.eq_extension(np.zeros((2, 4), dtype=np.uint64), ctx=one).shape, (4, 4))
+one.close()
+m = sb.Context(devices=[0, 1])
+try:
+    sb.eq_extension(np.zeros((2, 4), dtype=np.uint64), ctx=m)
+except sb.InvalidArgument:
+    pass
+else:
+    raise SystemExit("eq_extension accepted a multi context")
+cs = sb.SyntheticR1CS(4, 12, 0, 9)
+pk = sb.MLArgumentForR1CS.index(*cs.mats, ctx=m)
+try:
+    pk.sum_over_y(np.concatenate([cs.v, cs.w]))
+except sb.InvalidArgument:
+    pass
+else:
+    raise SystemExit("sum_over_y accepted a multi context")
+m.close(); pk.close()          # context first: its destruction completes with the last handle
+print("ok")
+"""
+    r = subprocess.run([sys.executable, "-c", code], env=dict(emul_env, SB_EMUL_DEVICES="8"), cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
