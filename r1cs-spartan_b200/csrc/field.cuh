@@ -369,11 +369,23 @@ struct alignas(16) Fq2 {
         // Karatsuba with lazy reduction: three 768-bit products, combined before reducing, two Montgomery
         // reductions instead of three (720 instead of 864 IMAD.WIDE).  Bounds: every product of operands < 2p is
         // < 4p^2 < 2^764; c1 = a0 b1 + a1 b0 < 2p^2 and c0 = a0 b0 - a1 b1 + p^2 in (0, 2p^2), both < p 2^384.
+        // (the operands arrive by reference -- this function is outlined -- and usually sit in local or shared memory:
+        // fetch each with six 128-bit loads instead of 24 scalar ones)
+        uint32_t al[24], bl[24];
+        {
+            const uint4* pa = reinterpret_cast<const uint4*>(&a); const uint4* pb = reinterpret_cast<const uint4*>(&b);
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                const uint4 x = pa[i], y = pb[i];
+                al[4 * i] = x.x; al[4 * i + 1] = x.y; al[4 * i + 2] = x.z; al[4 * i + 3] = x.w;
+                bl[4 * i] = y.x; bl[4 * i + 1] = y.y; bl[4 * i + 2] = y.z; bl[4 * i + 3] = y.w;
+            }
+        }
         uint32_t t0[24], t1[24], t2[24], u[24], sa[12], sb[12];
-        fq_mul_wide_ptx(t0, a.c0.l, b.c0.l);
-        fq_mul_wide_ptx(t1, a.c1.l, b.c1.l);
-        fq_wide_addn_ptx(sa, a.c0.l, a.c1.l);
-        fq_wide_addn_ptx(sb, b.c0.l, b.c1.l);
+        fq_mul_wide_ptx(t0, al, bl);
+        fq_mul_wide_ptx(t1, al + 12, bl + 12);
+        fq_wide_addn_ptx(sa, al, al + 12);
+        fq_wide_addn_ptx(sb, bl, bl + 12);
         fq_mul_wide_ptx(t2, sa, sb);
         fq_wide_sub_ptx(u, t2, t0);
         fq_wide_sub_ptx(t2, u, t1);
@@ -388,7 +400,18 @@ struct alignas(16) Fq2 {
         Fq2 o; o.c0 = Fq::sub(v0, v1); o.c1 = Fq::sub(Fq::sub(s, v0), v1); return o;
 #endif
     }
-    SB_FQ2_FN static Fq2 sqr(const Fq2& a) {
+    SB_FQ2_FN static Fq2 sqr(const Fq2& a_) {
+#if defined(__CUDA_ARCH__)
+        Fq2 a;                       // six 128-bit loads of the by-reference operand (see mul)
+        {
+            const uint4* pa = reinterpret_cast<const uint4*>(&a_);
+            uint4* da = reinterpret_cast<uint4*>(&a);
+#pragma unroll
+            for (int i = 0; i < 6; i++) da[i] = pa[i];
+        }
+#else
+        const Fq2& a = a_;
+#endif
         Fq s = Fq::add(a.c0, a.c1), d = Fq::sub(a.c0, a.c1), m = Fq::mul(a.c0, a.c1);
         Fq2 o; o.c0 = Fq::mul(s, d); o.c1 = Fq::dbl(m); return o;
     }
