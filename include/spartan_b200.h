@@ -93,7 +93,11 @@ int sb_device_count(void);
 /* ---- indexer: MLArgumentForR1CS::index, src/lib.rs:45-51 -> src/ahp/indexer.rs:41-64 ------------ */
 /* Same checks as the reference: n = 2^log_n rows per matrix (indexer.rs:49, r1cs_reader.rs:38-52),
  * every column index < n (r1cs_reader.rs:55-62) -> SB_EINVAL otherwise.  Also absorbs the three
- * matrices into the Fiat-Shamir transcript once (src/lib.rs:62-64) and keeps the hash state. */
+ * matrices into the Fiat-Shamir transcript once (src/lib.rs:62-64) and keeps the hash state.
+ * Both sparse-product plans are built on the device from these arrays (the caller's buffers are only read during the call).
+ * The columns of a row should be distinct, as upstream `to_matrices` produces them; they need not be sorted.  (With a
+ * repeated (row, column) the reference's own sum_over_y adds both terms while its eval_on_x keeps one; this library adds
+ * them in both.) */
 sb_status sb_index_create(sb_ctx* ctx, uint32_t log_n, const sb_csr* a, const sb_csr* b, const sb_csr* c, sb_index** out);
 void sb_index_destroy(sb_index* idx);
 /* wall time of sb_index_create, in two parts: validation + device-side plan construction (upload included), and what the

@@ -44,7 +44,7 @@ def test_emulated_library_refuses_to_run_outside_the_tests(emul_env):
 
 def test_product_kernels_match_oracle_under_emulation(emul_env):
     # the stage tests and small complete proofs of tests/test_gpu_parity.py, through the C ABI of the emulated build
-    _pytest_gpu_subset(emul_env, "eq_table or sum_over_y or eval_on_x or synthetic_circuit or keygen or pp_load or msm_matches or structured "
+    _pytest_gpu_subset(emul_env, "eq_table or sum_over_y or eval_on_x or synthetic_circuit or device_indexer or keygen or pp_load or msm_matches or structured "
                                  "or adversarial or commit_and_open or padded or interactive or invalid_arguments or resident or closed_before "
                                  "or prove_bytes_and_trace_match_oracle[3 or prove_bytes_and_trace_match_oracle[6 or prove_bytes_and_trace_match_oracle[8")
 

@@ -140,6 +140,49 @@ def test_synthetic_circuit_long_row_and_column(sb, oracle, gpu_ctx):
         assert np.array_equal(pk.eval_on_x(r_x, which=k), ocs.eval_on_x(k, r_x))
 
 
+def test_device_indexer_edge_cases(sb, oracle, gpu_ctx):
+    # the plans are built by kernels (csrc/indexer.cu): an empty matrix, a row and a column longer than SEG_LMAX = 32 with a
+    # remainder chunk (100 = 3 * 32 + 4 and 70 = 2 * 32 + 6 entries), a row that is exactly one full chunk, unit and non-unit
+    # coefficients side by side, unsorted columns inside a row, and empty rows at both ends.  (Columns are distinct within a
+    # row, as upstream `to_matrices` produces them: with duplicates the reference's own sum_over_y adds both terms,
+    # r1cs_reader.rs:79-83, while its eval_on_x keeps one of them, :100-108 -- the library adds them in both.)
+    log_n = 7
+    n = 1 << log_n
+    rnd = random.Random(99)
+    one = oracle.fr_from_ints([1])[0]
+
+    def build(rows):
+        row_ptr = np.zeros(n + 1, dtype=np.uint64); col = []
+        for x in range(n):
+            row_ptr[x + 1] = row_ptr[x] + len(rows[x]); col += rows[x]
+        vals = oracle.fr_rand(len(col) + 3, max(len(col), 1))[:len(col)]
+        for e in range(len(col)):
+            if rnd.random() < 0.4:
+                vals[e] = one
+        return row_ptr, np.array(col, dtype=np.uint32), vals
+
+    rows_a = [[] for _ in range(n)]
+    rows_a[5] = rnd.sample(range(n), 100)                              # long row, columns in random order
+    rows_a[6] = list(range(32))                                        # exactly one full chunk
+    for x in range(10, 80):
+        rows_a[x] = [3] + rnd.sample(range(4, n), rnd.randrange(3))                # column 3 holds 70 entries
+    rows_b = [rnd.sample(range(n), rnd.randrange(4)) for _ in range(n)]
+    rows_b[0] = []; rows_b[n - 1] = []
+    rows_c = [[] for _ in range(n)]                                    # an empty matrix
+    mats = [build(rows_a), build(rows_b), build(rows_c)]
+    pk = sb.MLProofForR1CS.index(*mats, ctx=gpu_ctx)
+    ocs = oracle.R1CS.from_csr(log_n, mats)
+    z = oracle.fr_rand(17, n)
+    got = pk.sum_over_y(z)
+    for k in range(3):
+        assert np.array_equal(got[k], ocs.sum_over_y(k, z)), k
+    r_x = oracle.fr_rand(18, log_n)
+    for k in range(3):
+        assert np.array_equal(pk.eval_on_x(r_x, which=k), ocs.eval_on_x(k, r_x)), k
+    plan_ms, hash_ms = pk.timing()
+    assert plan_ms >= 0 and hash_ms >= 0
+
+
 # ---------------------------------------------------------------- keygen / MSM / commitment (K7-K9)
 @pytest.fixture(scope="module")
 def small_pp(sb, oracle, gpu_ctx):
