@@ -359,31 +359,7 @@ def run_ours(args):
     extra = {"roofline_imad": imad_roofline(kernels, work, fq_peak)}
     extra["roofline_imad"]["peak_fq_gmul_s"] = fq_peak
     extra["roofline_imad"]["peak_fr_gmul_s"] = fr_peak
-    roofline = None
-    msm_kernels = {k: v for k, v in kernels.items() if k in work}
-    if msm_kernels:
-        name = max(msm_kernels, key=lambda k: msm_kernels[k]["ms_per_step"])
-        rec, w = kernels[name], work[name]
-        per_launch_ms = rec["ms_per_step"] / rec["launches_per_step"]
-        ach = w["fq_products"] / rec["ms_per_step"] / 1e6                     # G Fq-mul/s over all its launches of a step
-        alg_bytes = w["bytes"] / rec["launches_per_step"]
-        hbm_ach = alg_bytes / (per_launch_ms * 1e-3) / 1e9
-        ntr = NCU_TRAFFIC.get((name, LOG_N)) if world == 1 else None
-        roofline = {"kernel": name, "bound": "imad", "achieved": ach, "peak": fq_peak, "unit": "G Fq-mul/s", "frac": ach / fq_peak,
-                    "traffic": ntr[0] if ntr else None, "traffic_source": ntr[1] if ntr else None,
-                    "launches_per_step": rec["launches_per_step"], "avg_launch_ms": per_launch_ms,
-                    "algorithmic_fq_products_per_launch": w["fq_products"] / rec["launches_per_step"],
-                    "algorithmic_unit": w["unit"],
-                    "peak_source": "sb_mul_bench in this run (IMAD.WIDE issues at half rate: 148 SM x 32 lanes x clock; MEASURED_PEAKS.json holds no integer peak)",
-                    "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                            "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                            "note": "secondary: the kernel is bound by instruction issue on the integer pipe, not by HBM"}}
-        # the largest launch of that kernel (first pairwise round / first level of the largest group), from the serialised timeline
-        big = [(t1 - t0, tag) for (nm, t0, t1, tag) in timeline if nm == name]
-        if big and w.get("largest_launch_fq_products"):
-            d_ms = max(big)[0]
-            g = w["largest_launch_fq_products"] / d_ms / 1e6
-            roofline["largest_launch"] = {"ms": d_ms, "achieved": g, "frac": g / fq_peak, "fq_products": w["largest_launch_fq_products"]}
+    roofline = build_roofline(kernels, timeline, work, fq_peak, hbm_peak, peak_src, LOG_N, world)
     # sumcheck kernels alone, L2 flushed between launches
     sc = {}
     for which, nm, mults, bts in ((0, "sc1_fused_round", 12 / 4.0, 152.0), (1, "sc1_first_round", 6 / 2.0, (6 * 32 + 32) / 2.0), (2, "sc2_fused_round", 7 / 4.0, (8 * 32 + 4 * 32) / 4.0)):
@@ -459,8 +435,46 @@ def msm_layout(m, group_max=None):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the `ncu --set full` capture under profiles/
-# (average over the launches captured; the first round of the largest group is the one captured with --set full)
-NCU_TRAFFIC = {}
+# The launch captured with --set full is the LARGEST one of the kernel (first pairwise round of the rest-of-ladder group of an
+# opening: 5.0 M additions, 4.9 GB algorithmic); bench.py reports it as `roofline.traffic` with that caveat and repeats it, next
+# to the launch's own algorithmic bytes, in `roofline.largest_launch`.
+NCU_TRAFFIC = {("k_affine_round<Fq2>", 20): (4.194155e9 + 1.879138e9, "profiles/r02_ncu_affine_round_v3.txt")}
+
+
+def build_roofline(kernels, timeline, work, fq_peak, hbm_peak, peak_src, log_n, world):
+    """The `roofline` object of the bench line: the MSM kernel with the most serialised CUDA-event time against the
+    integer-pipe ceiling (nominal Fq products per second), its largest launch, and HBM as the secondary figure.
+    kernels: {name: {launches_per_step, ms_per_step}}; timeline: [(name, t0_ms, t1_ms, tag)]; work: msm_nominal_work()."""
+    roofline = None
+    msm_kernels = {k: v for k, v in kernels.items() if k in work}
+    if msm_kernels:
+        name = max(msm_kernels, key=lambda k: msm_kernels[k]["ms_per_step"])
+        rec, w = kernels[name], work[name]
+        per_launch_ms = rec["ms_per_step"] / rec["launches_per_step"]
+        ach = w["fq_products"] / rec["ms_per_step"] / 1e6                     # G Fq-mul/s over all its launches of a step
+        alg_bytes = w["bytes"] / rec["launches_per_step"]
+        hbm_ach = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+        ntr = NCU_TRAFFIC.get((name, log_n)) if world == 1 else None
+        roofline = {"kernel": name, "bound": "imad", "achieved": ach, "peak": fq_peak, "unit": "G Fq-mul/s", "frac": ach / fq_peak,
+                    "traffic": ntr[0] if ntr else None, "traffic_source": ntr[1] if ntr else None,
+                    "launches_per_step": rec["launches_per_step"], "avg_launch_ms": per_launch_ms,
+                    "algorithmic_fq_products_per_launch": w["fq_products"] / rec["launches_per_step"],
+                    "algorithmic_unit": w["unit"],
+                    "peak_source": "sb_mul_bench in this run (IMAD.WIDE issues at half rate: 148 SM x 32 lanes x clock; MEASURED_PEAKS.json holds no integer peak)",
+                    "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                            "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                            "note": "secondary: the kernel is bound by instruction issue on the integer pipe, not by HBM"}}
+        # the largest launch of that kernel (first pairwise round / first level of the largest group), from the serialised timeline
+        big = [(t1 - t0, tag) for (nm, t0, t1, tag) in timeline if nm == name]
+        if big and w.get("largest_launch_fq_products"):
+            d_ms = max(big)[0]
+            g = w["largest_launch_fq_products"] / d_ms / 1e6
+            roofline["largest_launch"] = {"ms": d_ms, "achieved": g, "frac": g / fq_peak, "fq_products": w["largest_launch_fq_products"],
+                                          "algorithmic_bytes": w.get("largest_launch_bytes"), "traffic": ntr[0] if ntr else None}
+            if ntr:
+                roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of the LARGEST launch (ncu --set full); compare it with "
+                                            "largest_launch.algorithmic_bytes, not with the per-launch average above")
+    return roofline
 
 
 def msm_nominal_work(ell, world=1):
@@ -479,10 +493,11 @@ def msm_nominal_work(ell, world=1):
         return sum(msm_layout(m, max(ms))[1] * m for m in ms)
     out = {}
 
-    def add(name, fq_products, nbytes, largest=0.0):
-        d = out.setdefault(name, {"fq_products": 0.0, "bytes": 0.0, "largest_launch_fq_products": 0.0})
+    def add(name, fq_products, nbytes, largest=0.0, largest_bytes=0.0):
+        d = out.setdefault(name, {"fq_products": 0.0, "bytes": 0.0, "largest_launch_fq_products": 0.0, "largest_launch_bytes": 0.0})
         d["fq_products"] += fq_products; d["bytes"] += nbytes
-        d["largest_launch_fq_products"] = max(d["largest_launch_fq_products"], largest)
+        if largest > d["largest_launch_fq_products"]:
+            d["largest_launch_fq_products"] = largest; d["largest_launch_bytes"] = largest_bytes
 
     def group(ms, g2, times):
         e = entries(ms)
@@ -490,10 +505,11 @@ def msm_nominal_work(ell, world=1):
         aff_p, mix_p = (17, 28) if g2 else (6, 10)
         suffix = "<Fq2>" if g2 else "<Fq>"
         if e >= (1 << 21):
-            add("k_affine_round" + suffix, times * e * (1 - 2.0 ** -R) * aff_p, times * (e * (1 - 2.0 ** -R) * 10 * fsz + e / 2 * 16), e / 2 * aff_p)
-            add("k_seg_accum_mixed" + suffix, times * (e / 2 ** R) * mix_p, times * (e / 2 ** R) * 2 * fsz, (e / 2 ** R) * mix_p)
+            add("k_affine_round" + suffix, times * e * (1 - 2.0 ** -R) * aff_p, times * (e * (1 - 2.0 ** -R) * 10 * fsz + e / 2 * 16), e / 2 * aff_p,
+                e / 2 * (10 * fsz + 16))
+            add("k_seg_accum_mixed" + suffix, times * (e / 2 ** R) * mix_p, times * (e / 2 ** R) * 2 * fsz, (e / 2 ** R) * mix_p, (e / 2 ** R) * 2 * fsz)
         else:
-            add("k_seg_accum_mixed" + suffix, times * e * mix_p, times * e * (2 * fsz + 4), e * mix_p)
+            add("k_seg_accum_mixed" + suffix, times * e * mix_p, times * e * (2 * fsz + 4), e * mix_p, e * (2 * fsz + 4))
     group([1 << ell], False, 1)
     slots = [1 << k for k in range(ell - 1, -1, -1)]
     if ell >= 12:
