@@ -56,7 +56,7 @@ def test_product_kernels_match_oracle_under_emulation(emul_env):
     {"SB_MSM_AFFINE_LOG2": "3", "SB_MSM_AFFINE_ROUNDS": "3", "SB_MSM_AFFINE_K": "3", "SB_MSM_S0": "4"},   # pairwise affine rounds in front of the accumulation (G1 and G2)
 ])
 def test_msm_pipeline_knobs_under_emulation(emul_env, knobs):
-    _pytest_gpu_subset(emul_env, "msm_matches or structured or adversarial or commit_and_open or padded or prove_bytes_and_trace_match_oracle[6", knobs)
+    _pytest_gpu_subset(emul_env, "structured or adversarial or commit_and_open or prove_bytes_and_trace_match_oracle[6", knobs)
 
 
 @pytest.mark.parametrize("world", [2, 4])
